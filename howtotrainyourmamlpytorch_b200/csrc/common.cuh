@@ -1,0 +1,221 @@
+// Shared declarations for the B200 MAML engine (sm_100a only).
+//
+// Activation layout ("padded pixel grid"): every activation-like tensor of block l lives as a
+// row-major matrix [n * G_l, C] with G_l = (h_l + 2) * (w_l + 2): one row per position of the
+// zero-padded image, channels innermost (NHWC with an explicit border).  Row index of pixel
+// (img, y, x) is img*G + (y+1)*gw + (x+1), gw = w+2.  With that layout a 3x3 / pad-1
+// convolution is a GEMM whose A operand for tap (ky,kx) is the SAME matrix shifted by
+// s_tap = (ky-1)*gw + (kx-1) rows -- plain 2-D tiles, which is what TMA wants.  Border rows of
+// conv inputs are zero and are never written; border rows of conv outputs are garbage and are
+// never read (they are masked out of every reduction).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MAML_MAX_LAYERS 4
+#define MAML_MAX_STEPS 8
+#define BN_EPS_D 1e-5
+#define LEAKY_SLOPE_F 0.01f
+
+struct LayerGeom {
+  int h, w;        // conv output (= input) spatial size of this block
+  int cin;         // input channels
+  int gw, G;       // padded grid: gw = w + 2, G = (h + 2) * (w + 2)
+  int ph, pw;      // pooled size (floor)
+  int pgw, pG, pb; // grid the pooled output is written to: pitch, rows per image, border (1 or 0)
+  int guard;       // guard rows before/after a conv-input matrix on this grid (gw + 2)
+};
+
+// ---------------------------------------------------------------------------------------------
+// launcher argument blocks (plain structs passed by value)
+// ---------------------------------------------------------------------------------------------
+struct ConvSrc {
+  const float* A; long long a_stride;   // A: row 0 of the (guarded) input matrix; per-task stride in floats
+  const float* W; long long w_stride;   // weights, per-task stride
+  int kc;                               // channels of A (= K per tap), multiple of 16
+  int wt;                               // 0: W[tap][kc][ncols]; 1: W[tap][ncols][kc] (dgrad: transposed use)
+  int sign;                             // +1: row j + s_tap (conv); -1: row j - s_tap (dgrad)
+};
+
+enum { CONV_PLAIN = 0, CONV_FWD_STATS = 1, CONV_TAN_STATS = 2 };
+
+struct ConvArgs {
+  ConvSrc src[2]; int nsrc;
+  const float* bias; long long bias_stride;    // nullable
+  float* out; long long out_stride;
+  int rows;                                    // n * G
+  int gw, G, h, w;
+  int ncols;                                   // output columns (16 * FN)
+  int mode;
+  const float* zh; long long zh_stride;        // CONV_TAN_STATS: normalised activations of the primal pass
+  double* stats; long long stats_stride;       // [task][ncols][2]
+  int tasks;
+};
+
+struct Conv0Args {                             // first block: K = 9 * C0 is tiny, direct conv
+  const float* X; long long x_stride;          // padded-grid image matrix [n*G][C0] (guarded)
+  const float* W; long long w_stride;          // [9][C0][F]
+  const float* bias; long long bias_stride;
+  float* out; long long out_stride;
+  int rows, gw, G, h, w, c0, ncols, mode;
+  const float* zh; long long zh_stride;
+  double* stats; long long stats_stride;
+  int tasks;
+};
+
+struct WgradArgs {
+  const float* A[2]; long long a_stride[2];    // conv inputs (guarded matrices) [rows][kc]
+  const float* D[2]; long long d_stride[2];    // output gradients (zero-border matrices) [rows][ncols]
+  int nsrc;
+  int kc, ncols, rows, gw;
+  int rows_per_chunk, nchunks;
+  float* partial; long long partial_task_stride; long long chunk_stride;  // [task][chunk][9*kc*ncols + ncols]
+  int tasks;
+};
+
+struct BnGeom { int n, h, w, gw, G, ph, pw, pgw, pG, pb, F; };
+
+struct BnActArgs {                // forward: z -> zh (in place), pooled activation p
+  float* z; long long z_stride;
+  const double* stats; long long stats_stride;     // (sum z, sum z^2)
+  const float* gamma; const float* beta;
+  float* p; long long p_stride;
+  BnGeom g; int tasks;
+};
+
+struct BnActTanArgs {             // tangent forward: zdot -> zhdot (in place), pdot
+  float* zdot; long long zdot_stride;
+  const float* zh; long long zh_stride;
+  const double* stats_fwd; long long stats_fwd_stride;   // primal (sum z, sum z^2) -> r
+  const double* stats_tan; long long stats_tan_stride;   // (sum zdot, sum zh*zdot)
+  const float* gamma; const float* beta;
+  float* pdot; long long pdot_stride;
+  BnGeom g; int tasks;
+};
+
+struct BnBwdArgs {                // backward reduce / apply (primal)
+  const float* dp; long long dp_stride;
+  const float* zh; long long zh_stride;
+  const double* stats_fwd; long long stats_fwd_stride;
+  double* stats_bwd; long long stats_bwd_stride;          // (S1 = sum dy, S2 = sum dy*zh)
+  const float* gamma; const float* beta;
+  float* dz; long long dz_stride;
+  BnGeom g; int tasks;
+};
+
+struct BnBwdTanArgs {             // backward reduce / apply (tangent)
+  const float* dp; long long dp_stride;
+  const float* dpdot; long long dpdot_stride;
+  const float* zh; long long zh_stride;
+  const float* zhdot; long long zhdot_stride;
+  const float* dz; long long dz_stride;
+  const double* stats_fwd; long long stats_fwd_stride;
+  const double* stats_bwd; long long stats_bwd_stride;    // primal (S1, S2)
+  const double* stats_tan; long long stats_tan_stride;    // tangent forward (sum zdot, sum zh*zdot)
+  double* stats_tbwd; long long stats_tbwd_stride;        // (T1, T2)
+  const float* gamma; const float* beta;
+  float* dzdot; long long dzdot_stride;
+  BnGeom g; int tasks;
+};
+
+enum { HEAD_SUPPORT = 0, HEAD_TARGET_FWD = 1, HEAD_TARGET_BWD = 2, HEAD_TANGENT = 3 };
+
+struct HeadArgs {
+  int mode;
+  int n, N, D;
+  const float* f; long long f_stride;             // [n][D] features (grid order: pixel-major, channel-minor)
+  const float* fdot; long long fdot_stride;       // tangent of f (HEAD_TANGENT)
+  const float* Wfc; const float* bfc; long long theta_stride;     // [N][D], [N] (internal order), per task
+  const float* uW; const float* ub; long long u_stride;           // tangent direction (HEAD_TANGENT)
+  const long long* y; long long y_stride;         // labels [n]
+  const float* scale_ptr;                         // nullable: loss weight (device scalar)
+  float* gW; float* gb; long long g_stride;       // gradient (or H*u) output for the head tensors
+  float* df; long long df_stride;                 // [n][D] gradient (or its tangent) w.r.t. features
+  float* loss_out; long long loss_stride;         // per-task scalar (HEAD_TARGET_FWD)
+  float* logits_out; long long logits_stride;     // nullable [n][N]
+  float* correct_out; long long correct_stride;   // nullable per-task count
+  int tasks;
+};
+
+// ---------------------------------------------------------------------------------------------
+// parameter-space description (internal fast-weight layout)
+// ---------------------------------------------------------------------------------------------
+struct ParamLayout {
+  int L, F, N, S, per_step_bn;
+  int cin[MAML_MAX_LAYERS];
+  int pix;                        // pooled pixels of the last block (D = pix * F)
+  // internal (per task) fast-weight vector: W_l [9][cin][F], b_l [F], ..., Wfc [N][pix][F], bfc [N]
+  long long w_off[MAML_MAX_LAYERS], b_off[MAML_MAX_LAYERS], fcw_off, fcb_off, P;
+  // reference-layout flat meta vector offsets
+  long long m_w[MAML_MAX_LAYERS], m_b[MAML_MAX_LAYERS], m_beta[MAML_MAX_LAYERS], m_gamma[MAML_MAX_LAYERS];
+  long long m_fcw, m_fcb, m_lslr, meta_size;     // lslr: (2L+2) vectors of S+1
+  int nseg_inner;                 // 2L + 2 inner tensors
+  // per inner segment: internal offset / size and number of gradient chunks in a partial buffer
+  long long seg_off[2 * MAML_MAX_LAYERS + 2];
+  long long seg_size[2 * MAML_MAX_LAYERS + 2];
+};
+
+enum { PR_UPDATE = 0, PR_STORE = 1, PR_SUB = 2 };
+
+struct PartialDesc {              // where each inner segment's gradient chunks live in a partial buffer
+  long long off[2 * MAML_MAX_LAYERS + 2];   // offset (floats) of chunk 0 inside the per-task partial block
+  long long cstride[2 * MAML_MAX_LAYERS + 2];
+  int nchunks[2 * MAML_MAX_LAYERS + 2];
+  long long task_stride;
+};
+
+// ---------------------------------------------------------------------------------------------
+// launchers (kernels_*.cu)
+// ---------------------------------------------------------------------------------------------
+void launch_prep_x(const float* x, float* xg, long long xg_task_stride, int tasks, int n, int C, int H, int W,
+                   cudaStream_t st);
+void launch_conv_rows(const ConvArgs& a, cudaStream_t st);
+void launch_conv0(const Conv0Args& a, cudaStream_t st);
+void launch_wgrad(const WgradArgs& a, cudaStream_t st);
+void launch_wgrad0(const WgradArgs& a, cudaStream_t st);
+void launch_bnact(const BnActArgs& a, cudaStream_t st);
+void launch_bnact_tan(const BnActTanArgs& a, cudaStream_t st);
+void launch_bnbwd_reduce(const BnBwdArgs& a, cudaStream_t st);
+void launch_bnbwd_apply(const BnBwdArgs& a, cudaStream_t st);
+void launch_bnbwd_tan_reduce(const BnBwdTanArgs& a, cudaStream_t st);
+void launch_bnbwd_tan_apply(const BnBwdTanArgs& a, cudaStream_t st);
+void launch_head(const HeadArgs& a, cudaStream_t st);
+
+void launch_import_theta(const ParamLayout& pl, const float* meta, float* theta0, long long theta_task_stride,
+                         int tasks, cudaStream_t st);
+void launch_param_reduce(const ParamLayout& pl, const PartialDesc& pd, const float* partial, int mode,
+                         const float* theta_in, float* theta_out, float* g_out, float* tbar,
+                         const float* meta, int step, long long task_stride, int tasks, cudaStream_t st);
+void launch_dots_u(const ParamLayout& pl, float* tbar, const float* tgrad, const float* g, float* u, float* abar,
+                   const float* meta, int step, long long task_stride, int tasks, cudaStream_t st);
+
+struct ExportArgs {
+  ParamLayout pl;
+  const float* tbar; long long task_stride;          // [tasks][P]
+  const float* abar;                                 // [tasks][nseg_inner][MAML_MAX_STEPS]
+  const double* stats; long long stats_task_stride;  // stats arena
+  long long st_pass_stride, st_layer_stride;         // arena strides (doubles)
+  const float* losses;                               // [tasks][MAML_MAX_STEPS] target losses
+  const float* correct;                              // [tasks]
+  const float* weights;                              // device [MAML_MAX_STEPS] target weights
+  unsigned target_mask; int num_steps; int training;
+  int tasks, task_offset, tasks_global;
+  int n_s, n_t;
+  int hw[MAML_MAX_LAYERS];                           // h*w per block
+  float* result;
+};
+void launch_export(const ExportArgs& a, cudaStream_t st);
+
+void launch_adam(float* meta, const float* grad, float* m, float* v, long long n, float lr, float bc1, float bc2,
+                 const long long* seg_end_host, int nseg, unsigned trainable_mask, unsigned clamp_mask,
+                 cudaStream_t st);
+void launch_running_update(const float* part_mean, const float* part_var, float* rm, float* rv,
+                           const float* decay_dev, int L, int S, int F, cudaStream_t st);
+
+// stats arena pass ids
+enum { PASS_SUP_FWD = 0, PASS_SUP_BWD = 1, PASS_TGT_FWD = 2, PASS_TGT_BWD = 3, PASS_TAN_FWD = 4, PASS_TAN_BWD = 5,
+       PASS_KINDS = 6 };
+
+extern long long g_launch_counter;   // bumped by every launcher
+
+#define CUDA_CHECK_LAUNCH() do { g_launch_counter++; } while (0)

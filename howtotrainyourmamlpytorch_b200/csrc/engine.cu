@@ -1,0 +1,655 @@
+// Host-side orchestration + C ABI (include/maml_b200.h) of the B200 MAML / MAML++ engine.
+//
+// One call of maml_b200_meta_batch_fwd_bwd replaces, for the local shard of tasks, the reference's
+//   forward()   few_shot_learning_system.py:170-263  (task loop x inner-step loop, Python, autograd)
+//   backward()  few_shot_learning_system.py:331      (second-order reverse sweep)
+// with a fixed sequence of kernels batched over tasks (grid.y = task):
+//   phase A (unroll):   for s: support forward -> hand-rolled support gradient -> LSLR update,
+//                       target forward (+ its backward, stored as tgrad[s]) at theta^{s+1}
+//   phase B (reverse):  for s = S-1..0: tbar += tgrad[s]; abar[s] = -<tbar, g_s>; u = alpha_s * tbar;
+//                       Hessian-vector product by a forward-mode tangent pass; tbar -= H u
+// No host synchronisation, no fast-weight round trip to the host; all intermediates stay in HBM / L2.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../include/maml_b200.h"
+#include "common.cuh"
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return 1; }
+
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
+  return fail(std::string(#call) + ": " + cudaGetErrorString(e__)); } } while (0)
+
+static inline long long rup(long long x, long long m) { return (x + m - 1) / m * m; }
+
+struct PassSet {            // activation buffers of one kind of pass (support: S slots, target / tangent: 1)
+  int n = 0, slots = 0;
+  float* xg = nullptr; long long xg_stride = 0;                       // block-0 input grid (row 0), per task
+  float* ain[MAML_MAX_LAYERS + 1] = {}; long long ain_sz[MAML_MAX_LAYERS + 1] = {};   // per (task,slot) size; ptr at row 0
+  float* zh[MAML_MAX_LAYERS] = {}; long long zh_sz[MAML_MAX_LAYERS] = {};
+  float* dz[MAML_MAX_LAYERS] = {}; long long dz_sz[MAML_MAX_LAYERS] = {};
+  float* dp[MAML_MAX_LAYERS] = {}; long long dp_sz[MAML_MAX_LAYERS] = {};
+};
+
+struct ChunkPlan { int rows_per_chunk[MAML_MAX_LAYERS]; int nchunks[MAML_MAX_LAYERS]; PartialDesc pd; long long size; };
+
+struct maml_b200_handle {
+  maml_b200_config cfg;
+  int L, F, N, S, C, H, W, n_s, n_t, maxT, D, pix;
+  LayerGeom geo[MAML_MAX_LAYERS];
+  ParamLayout pl;
+  long long Ppad;
+  // meta segments
+  std::vector<long long> seg_off, seg_size;
+  // workspace
+  char* ws = nullptr; long long ws_bytes = 0;
+  PassSet sup, tgt, tan;
+  float *theta = nullptr, *g = nullptr, *tgrad = nullptr, *tbar = nullptr, *u = nullptr;
+  float *sup_partial = nullptr, *tgt_partial = nullptr;
+  ChunkPlan plan_sup, plan_tgt;
+  double* stats = nullptr; long long stats_task_stride = 0, st_pass_stride = 0, st_layer_stride = 0, stats_count = 0;
+  float *losses = nullptr, *correct = nullptr, *abar = nullptr, *weights_dev = nullptr, *decay_dev = nullptr;
+  float* pinned = nullptr;            // host staging ring for small per-call scalars (16 slots x 32 floats)
+  int pin_slot = 0;
+  long long last_launches = 0;
+  int last_tasks = 0;
+};
+
+extern "C" int maml_b200_abi_version(void) { return MAML_B200_ABI_VERSION; }
+extern "C" const char* maml_b200_last_error(void) { return g_err.c_str(); }
+
+static void build_geometry(maml_b200_handle* h) {
+  int hh = h->H, ww = h->W, cin = h->C;
+  for (int l = 0; l < h->L; ++l) {
+    LayerGeom& g = h->geo[l];
+    g.h = hh; g.w = ww; g.cin = cin;
+    g.gw = ww + 2; g.G = (hh + 2) * (ww + 2);
+    g.ph = hh / 2; g.pw = ww / 2;
+    if (l < h->L - 1) { g.pgw = g.pw + 2; g.pG = (g.ph + 2) * (g.pw + 2); g.pb = 1; }
+    else { g.pgw = g.pw; g.pG = g.ph * g.pw; g.pb = 0; }
+    g.guard = g.gw + 2;
+    hh = g.ph; ww = g.pw; cin = h->F;
+  }
+  h->pix = h->geo[h->L - 1].ph * h->geo[h->L - 1].pw;
+  h->D = h->pix * h->F;
+}
+
+static void build_layout(maml_b200_handle* h) {
+  ParamLayout& pl = h->pl;
+  memset(&pl, 0, sizeof(pl));
+  pl.L = h->L; pl.F = h->F; pl.N = h->N; pl.S = h->S; pl.per_step_bn = h->cfg.per_step_bn; pl.pix = h->pix;
+  long long o = 0, m = 0;
+  const long long bnsz = (long long)(pl.per_step_bn ? h->S : 1) * h->F;
+  for (int l = 0; l < h->L; ++l) {
+    pl.cin[l] = h->geo[l].cin;
+    const long long wsz = 9LL * pl.cin[l] * h->F;
+    pl.w_off[l] = o; o += wsz;
+    pl.b_off[l] = o; o += h->F;
+    pl.m_w[l] = m; h->seg_off.push_back(m); h->seg_size.push_back(wsz); m += wsz;
+    pl.m_b[l] = m; h->seg_off.push_back(m); h->seg_size.push_back(h->F); m += h->F;
+    pl.m_beta[l] = m; h->seg_off.push_back(m); h->seg_size.push_back(bnsz); m += bnsz;
+    pl.m_gamma[l] = m; h->seg_off.push_back(m); h->seg_size.push_back(bnsz); m += bnsz;
+    pl.seg_off[2 * l] = pl.w_off[l]; pl.seg_size[2 * l] = wsz;
+    pl.seg_off[2 * l + 1] = pl.b_off[l]; pl.seg_size[2 * l + 1] = h->F;
+  }
+  pl.fcw_off = o; o += (long long)h->N * h->D;
+  pl.fcb_off = o; o += h->N;
+  pl.P = o;
+  pl.m_fcw = m; h->seg_off.push_back(m); h->seg_size.push_back((long long)h->N * h->D); m += (long long)h->N * h->D;
+  pl.m_fcb = m; h->seg_off.push_back(m); h->seg_size.push_back(h->N); m += h->N;
+  pl.nseg_inner = 2 * h->L + 2;
+  pl.seg_off[2 * h->L] = pl.fcw_off; pl.seg_size[2 * h->L] = (long long)h->N * h->D;
+  pl.seg_off[2 * h->L + 1] = pl.fcb_off; pl.seg_size[2 * h->L + 1] = h->N;
+  pl.m_lslr = m;
+  for (int k = 0; k < pl.nseg_inner; ++k) { h->seg_off.push_back(m); h->seg_size.push_back(h->S + 1); m += h->S + 1; }
+  pl.meta_size = m;
+  h->Ppad = rup(pl.P, 64);
+}
+
+static void plan_chunks(maml_b200_handle* h, int n, ChunkPlan* cp) {
+  long long off = 0;
+  memset(&cp->pd, 0, sizeof(cp->pd));
+  for (int l = 0; l < h->L; ++l) {
+    const long long rows = (long long)n * h->geo[l].G;
+    int nch, rpc;
+    if (l == 0) {
+      nch = (int)std::min<long long>(256, std::max<long long>(1, (rows + 255) / 256));
+    } else {
+      nch = (int)std::min<long long>(64, std::max<long long>(1, (rows + 511) / 512));
+    }
+    rpc = (int)rup((rows + nch - 1) / nch, 16);
+    nch = (int)((rows + rpc - 1) / rpc);
+    cp->rows_per_chunk[l] = rpc; cp->nchunks[l] = nch;
+    const long long cs = 9LL * h->geo[l].cin * h->F + h->F;
+    cp->pd.off[2 * l] = off; cp->pd.cstride[2 * l] = cs; cp->pd.nchunks[2 * l] = nch;
+    cp->pd.off[2 * l + 1] = off + 9LL * h->geo[l].cin * h->F; cp->pd.cstride[2 * l + 1] = cs; cp->pd.nchunks[2 * l + 1] = nch;
+    off += cs * nch;
+  }
+  cp->pd.off[2 * h->L] = off; cp->pd.cstride[2 * h->L] = 0; cp->pd.nchunks[2 * h->L] = 1; off += (long long)h->N * h->D;
+  cp->pd.off[2 * h->L + 1] = off; cp->pd.cstride[2 * h->L + 1] = 0; cp->pd.nchunks[2 * h->L + 1] = 1; off += h->N;
+  cp->size = rup(off, 64);
+  cp->pd.task_stride = cp->size;
+}
+
+// bump allocator over the workspace (two passes: size, then assign)
+struct Bump {
+  char* base; long long off;
+  float* f(long long count) { float* p = base ? (float*)(base + off) : nullptr; off += rup(count * 4, 256); return p; }
+  double* d(long long count) { double* p = base ? (double*)(base + off) : nullptr; off += rup(count * 8, 256); return p; }
+};
+
+static void carve_pass(maml_b200_handle* h, Bump& b, PassSet& ps, int n, int slots, bool need_x, bool need_bwd) {
+  ps.n = n; ps.slots = slots;
+  const long long T = h->maxT;
+  if (need_x) {
+    const long long gr = (long long)h->geo[0].guard * h->C;
+    const long long body = (long long)n * h->geo[0].G * h->C;
+    ps.xg_stride = rup(body + 2 * gr, 64);
+    float* p = b.f(ps.xg_stride * T);
+    ps.xg = p ? p + gr : nullptr;
+  }
+  for (int l = 1; l < h->L; ++l) {
+    const long long gr = (long long)h->geo[l].guard * h->F;
+    const long long body = (long long)n * h->geo[l].G * h->F;
+    ps.ain_sz[l] = rup(body + 2 * gr, 64);
+    float* p = b.f(ps.ain_sz[l] * T * slots);
+    ps.ain[l] = p ? p + gr : nullptr;
+  }
+  ps.ain_sz[h->L] = rup((long long)n * h->D, 64);
+  ps.ain[h->L] = b.f(ps.ain_sz[h->L] * T * slots);
+  for (int l = 0; l < h->L; ++l) {
+    ps.zh_sz[l] = rup((long long)n * h->geo[l].G * h->F, 64);
+    ps.zh[l] = b.f(ps.zh_sz[l] * T * slots);
+    if (need_bwd) {
+      const long long gr = (long long)h->geo[l].guard * h->F;
+      ps.dz_sz[l] = rup((long long)n * h->geo[l].G * h->F + 2 * gr, 64);
+      float* p = b.f(ps.dz_sz[l] * T * slots);
+      ps.dz[l] = p ? p + gr : nullptr;
+      ps.dp_sz[l] = rup((long long)n * h->geo[l].pG * h->F, 64);
+      ps.dp[l] = b.f(ps.dp_sz[l] * T * slots);
+    }
+  }
+}
+
+static void carve(maml_b200_handle* h, Bump& b) {
+  const long long T = h->maxT;
+  carve_pass(h, b, h->sup, h->n_s, h->S, true, true);
+  carve_pass(h, b, h->tgt, h->n_t, 1, true, true);
+  carve_pass(h, b, h->tan, h->n_s, 1, false, true);
+  h->theta = b.f((long long)(h->S + 1) * T * h->Ppad);
+  h->g = b.f((long long)h->S * T * h->Ppad);
+  h->tgrad = b.f((long long)h->S * T * h->Ppad);
+  h->tbar = b.f(T * h->Ppad);
+  h->u = b.f(T * h->Ppad);
+  h->sup_partial = b.f(T * h->plan_sup.size);
+  h->tgt_partial = b.f(T * h->plan_tgt.size);
+  h->st_layer_stride = (long long)h->F * 2;
+  h->st_pass_stride = (long long)h->L * h->F * 2;
+  h->stats_task_stride = (long long)PASS_KINDS * MAML_MAX_STEPS * h->st_pass_stride;
+  h->stats_count = h->stats_task_stride * T;
+  h->stats = b.d(h->stats_count);
+  h->losses = b.f(T * MAML_MAX_STEPS);
+  h->correct = b.f(T);
+  h->abar = b.f(T * h->pl.nseg_inner * MAML_MAX_STEPS);
+  h->weights_dev = b.f(MAML_MAX_STEPS);
+  h->decay_dev = b.f(MAML_MAX_STEPS);
+}
+
+extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** out) {
+  if (!cfg || !out) return fail("null argument");
+  if (cfg->filters % 16 != 0 || cfg->filters < 16 || cfg->filters > 64) return fail("filters must be a multiple of 16 in [16, 64]");
+  if (cfg->num_stages < 1 || cfg->num_stages > MAML_MAX_LAYERS) return fail("num_stages must be in [1, 4]");
+  if (cfg->inner_steps < 1 || cfg->inner_steps > MAML_MAX_STEPS) return fail("inner_steps must be in [1, 8]");
+  if (cfg->channels < 1 || cfg->channels > 4) return fail("channels must be in [1, 4]");
+  if (cfg->max_tasks < 1) return fail("max_tasks must be >= 1");
+  if (cfg->n_way < 2 || cfg->n_way > 32) return fail("n_way must be in [2, 32]");
+  const int n_s = cfg->n_way * cfg->k_shot, n_t = cfg->n_way * cfg->t_target;
+  if (n_s < 1 || n_t < 1 || n_s > 128 || n_t > 128) return fail("N*K and N*T must be in [1, 128]");
+  if ((long long)5 * std::max(n_s, n_t) * cfg->n_way * 4 > 48 * 1024) return fail("head tile does not fit shared memory");
+  {
+    int hh = cfg->height, ww = cfg->width;
+    for (int l = 0; l < cfg->num_stages; ++l) { if (hh < 2 || ww < 2) return fail("image too small for num_stages"); hh /= 2; ww /= 2; }
+  }
+  maml_b200_handle* h = new maml_b200_handle();
+  h->cfg = *cfg;
+  h->L = cfg->num_stages; h->F = cfg->filters; h->N = cfg->n_way; h->S = cfg->inner_steps;
+  h->C = cfg->channels; h->H = cfg->height; h->W = cfg->width; h->n_s = n_s; h->n_t = n_t; h->maxT = cfg->max_tasks;
+  build_geometry(h);
+  build_layout(h);
+  plan_chunks(h, h->n_s, &h->plan_sup);
+  plan_chunks(h, h->n_t, &h->plan_tgt);
+  Bump sz{nullptr, 0};
+  carve(h, sz);
+  h->ws_bytes = sz.off;
+  cudaError_t e = cudaMalloc((void**)&h->ws, (size_t)h->ws_bytes);
+  if (e != cudaSuccess) { std::string m = std::string("cudaMalloc workspace (") + std::to_string(h->ws_bytes) + " B): " + cudaGetErrorString(e); delete h; return fail(m); }
+  e = cudaMemset(h->ws, 0, (size_t)h->ws_bytes);
+  if (e != cudaSuccess) { cudaFree(h->ws); delete h; return fail(std::string("cudaMemset: ") + cudaGetErrorString(e)); }
+  Bump as{h->ws, 0};
+  carve(h, as);
+  e = cudaMallocHost((void**)&h->pinned, 16 * 32 * sizeof(float));
+  if (e != cudaSuccess) { cudaFree(h->ws); delete h; return fail(std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
+  *out = h;
+  return 0;
+}
+
+extern "C" void maml_b200_destroy(maml_b200_handle* h) {
+  if (!h) return;
+  if (h->ws) cudaFree(h->ws);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  delete h;
+}
+
+extern "C" int64_t maml_b200_workspace_bytes(const maml_b200_handle* h) { return h ? h->ws_bytes : -1; }
+extern "C" int32_t maml_b200_num_segments(const maml_b200_handle* h) { return h ? (int32_t)h->seg_off.size() : -1; }
+extern "C" int maml_b200_segment(const maml_b200_handle* h, int32_t idx, int64_t* offset, int64_t* size) {
+  if (!h || idx < 0 || idx >= (int)h->seg_off.size()) return fail("bad segment index");
+  *offset = h->seg_off[idx]; *size = h->seg_size[idx];
+  return 0;
+}
+extern "C" int64_t maml_b200_meta_size(const maml_b200_handle* h) { return h ? h->pl.meta_size : -1; }
+extern "C" int64_t maml_b200_result_size(const maml_b200_handle* h) {
+  if (!h) return -1;
+  return h->pl.meta_size + 2 + (h->cfg.per_step_bn ? 2LL * h->L * h->S * h->F : 0);
+}
+extern "C" int64_t maml_b200_last_launch_count(const maml_b200_handle* h) { return h ? h->last_launches : -1; }
+
+// ---------------------------------------------------------------------------------------------
+// pass helpers
+// ---------------------------------------------------------------------------------------------
+static BnGeom bn_geom(const maml_b200_handle* h, int l, int n) {
+  const LayerGeom& g = h->geo[l];
+  BnGeom b; b.n = n; b.h = g.h; b.w = g.w; b.gw = g.gw; b.G = g.G; b.ph = g.ph; b.pw = g.pw; b.pgw = g.pgw; b.pG = g.pG; b.pb = g.pb; b.F = h->F;
+  return b;
+}
+static double* stat_at(const maml_b200_handle* h, int kind, int step, int layer) {
+  return h->stats + ((long long)kind * MAML_MAX_STEPS + step) * h->st_pass_stride + (long long)layer * h->st_layer_stride;
+}
+static const float* gamma_at(const maml_b200_handle* h, const float* meta, int l, int step) {
+  return meta + h->pl.m_gamma[l] + (h->cfg.per_step_bn ? (long long)step * h->F : 0);
+}
+static const float* beta_at(const maml_b200_handle* h, const float* meta, int l, int step) {
+  return meta + h->pl.m_beta[l] + (h->cfg.per_step_bn ? (long long)step * h->F : 0);
+}
+
+struct Slot { const PassSet* ps; int slot; };
+static float* slot_ptr(float* base, long long sz, int slots, int slot) { return base + (long long)slot * sz; }
+#define AIN(ps, l, slot) slot_ptr((ps).ain[l], (ps).ain_sz[l], (ps).slots, slot)
+#define ZH(ps, l, slot) slot_ptr((ps).zh[l], (ps).zh_sz[l], (ps).slots, slot)
+#define DZ(ps, l, slot) slot_ptr((ps).dz[l], (ps).dz_sz[l], (ps).slots, slot)
+#define DP(ps, l, slot) slot_ptr((ps).dp[l], (ps).dp_sz[l], (ps).slots, slot)
+#define STRIDE(ps, what, l) ((ps).what##_sz[l] * (ps).slots)
+
+// primal forward of one pass: conv -> stats -> BN/leaky/pool for every block
+static void forward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const float* theta, const float* meta, int bn_step,
+                         int stat_kind, int T, cudaStream_t st) {
+  for (int l = 0; l < h->L; ++l) {
+    const LayerGeom& g = h->geo[l];
+    if (l == 0) {
+      Conv0Args a{};
+      a.X = ps.xg; a.x_stride = ps.xg_stride;
+      a.W = theta + h->pl.w_off[0]; a.w_stride = h->Ppad;
+      a.bias = theta + h->pl.b_off[0]; a.bias_stride = h->Ppad;
+      a.out = ZH(ps, 0, slot); a.out_stride = STRIDE(ps, zh, 0);
+      a.rows = ps.n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.c0 = h->C; a.ncols = h->F; a.mode = CONV_FWD_STATS;
+      a.stats = stat_at(h, stat_kind, bn_step, 0); a.stats_stride = h->stats_task_stride; a.tasks = T;
+      launch_conv0(a, st);
+    } else {
+      ConvArgs a{};
+      a.nsrc = 1;
+      a.src[0].A = AIN(ps, l, slot); a.src[0].a_stride = STRIDE(ps, ain, l);
+      a.src[0].W = theta + h->pl.w_off[l]; a.src[0].w_stride = h->Ppad; a.src[0].kc = h->F; a.src[0].wt = 0; a.src[0].sign = 1;
+      a.bias = theta + h->pl.b_off[l]; a.bias_stride = h->Ppad;
+      a.out = ZH(ps, l, slot); a.out_stride = STRIDE(ps, zh, l);
+      a.rows = ps.n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.ncols = h->F; a.mode = CONV_FWD_STATS;
+      a.stats = stat_at(h, stat_kind, bn_step, l); a.stats_stride = h->stats_task_stride; a.tasks = T;
+      launch_conv_rows(a, st);
+    }
+    BnActArgs b{};
+    b.z = ZH(ps, l, slot); b.z_stride = STRIDE(ps, zh, l);
+    b.stats = stat_at(h, stat_kind, bn_step, l); b.stats_stride = h->stats_task_stride;
+    b.gamma = gamma_at(h, meta, l, bn_step); b.beta = beta_at(h, meta, l, bn_step);
+    b.p = AIN(ps, l + 1, slot); b.p_stride = STRIDE(ps, ain, l + 1);
+    b.g = bn_geom(h, l, ps.n); b.tasks = T;
+    launch_bnact(b, st);
+  }
+}
+
+// primal backward of one pass (dp[L-1] already written by the head): BN backward, wgrad, dgrad
+static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const float* theta, const float* meta, int bn_step,
+                          int kind_fwd, int kind_bwd, float* partial, const ChunkPlan& cp, int T, cudaStream_t st) {
+  for (int l = h->L - 1; l >= 0; --l) {
+    const LayerGeom& g = h->geo[l];
+    BnBwdArgs b{};
+    b.dp = DP(ps, l, slot); b.dp_stride = STRIDE(ps, dp, l);
+    b.zh = ZH(ps, l, slot); b.zh_stride = STRIDE(ps, zh, l);
+    b.stats_fwd = stat_at(h, kind_fwd, bn_step, l); b.stats_fwd_stride = h->stats_task_stride;
+    b.stats_bwd = stat_at(h, kind_bwd, bn_step, l); b.stats_bwd_stride = h->stats_task_stride;
+    b.gamma = gamma_at(h, meta, l, bn_step); b.beta = beta_at(h, meta, l, bn_step);
+    b.dz = DZ(ps, l, slot); b.dz_stride = STRIDE(ps, dz, l);
+    b.g = bn_geom(h, l, ps.n); b.tasks = T;
+    launch_bnbwd_reduce(b, st);
+    launch_bnbwd_apply(b, st);
+
+    WgradArgs w{};
+    w.nsrc = 1;
+    w.D[0] = DZ(ps, l, slot); w.d_stride[0] = STRIDE(ps, dz, l);
+    w.ncols = h->F; w.rows = ps.n * g.G; w.gw = g.gw;
+    w.rows_per_chunk = cp.rows_per_chunk[l]; w.nchunks = cp.nchunks[l];
+    w.partial = partial + cp.pd.off[2 * l]; w.partial_task_stride = cp.pd.task_stride; w.chunk_stride = cp.pd.cstride[2 * l];
+    w.tasks = T;
+    if (l == 0) {
+      w.A[0] = ps.xg; w.a_stride[0] = ps.xg_stride; w.kc = h->C;
+      launch_wgrad0(w, st);
+    } else {
+      w.A[0] = AIN(ps, l, slot); w.a_stride[0] = STRIDE(ps, ain, l); w.kc = h->F;
+      launch_wgrad(w, st);
+      ConvArgs a{};
+      a.nsrc = 1;
+      a.src[0].A = DZ(ps, l, slot); a.src[0].a_stride = STRIDE(ps, dz, l);
+      a.src[0].W = theta + h->pl.w_off[l]; a.src[0].w_stride = h->Ppad; a.src[0].kc = h->F; a.src[0].wt = 1; a.src[0].sign = -1;
+      a.out = DP(ps, l - 1, slot); a.out_stride = STRIDE(ps, dp, l - 1);
+      a.rows = ps.n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.ncols = h->F; a.mode = CONV_PLAIN; a.tasks = T;
+      launch_conv_rows(a, st);
+    }
+  }
+}
+
+// forward-mode tangent of (support forward + support backward) at step s in direction u  =>  H u into `partial`
+static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const float* u, const float* meta,
+                         const long long* y_support, int T, cudaStream_t st) {
+  const PassSet& sp = h->sup; const PassSet& tn = h->tan;
+  for (int l = 0; l < h->L; ++l) {
+    const LayerGeom& g = h->geo[l];
+    if (l == 0) {
+      Conv0Args a{};
+      a.X = sp.xg; a.x_stride = sp.xg_stride;
+      a.W = u + h->pl.w_off[0]; a.w_stride = h->Ppad;
+      a.bias = u + h->pl.b_off[0]; a.bias_stride = h->Ppad;
+      a.out = ZH(tn, 0, 0); a.out_stride = STRIDE(tn, zh, 0);
+      a.rows = sp.n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.c0 = h->C; a.ncols = h->F; a.mode = CONV_TAN_STATS;
+      a.zh = ZH(sp, 0, s); a.zh_stride = STRIDE(sp, zh, 0);
+      a.stats = stat_at(h, PASS_TAN_FWD, s, 0); a.stats_stride = h->stats_task_stride; a.tasks = T;
+      launch_conv0(a, st);
+    } else {
+      ConvArgs a{};
+      a.nsrc = 2;
+      a.src[0].A = AIN(sp, l, s); a.src[0].a_stride = STRIDE(sp, ain, l);
+      a.src[0].W = u + h->pl.w_off[l]; a.src[0].w_stride = h->Ppad; a.src[0].kc = h->F; a.src[0].wt = 0; a.src[0].sign = 1;
+      a.src[1].A = AIN(tn, l, 0); a.src[1].a_stride = STRIDE(tn, ain, l);
+      a.src[1].W = theta + h->pl.w_off[l]; a.src[1].w_stride = h->Ppad; a.src[1].kc = h->F; a.src[1].wt = 0; a.src[1].sign = 1;
+      a.bias = u + h->pl.b_off[l]; a.bias_stride = h->Ppad;
+      a.out = ZH(tn, l, 0); a.out_stride = STRIDE(tn, zh, l);
+      a.rows = sp.n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.ncols = h->F; a.mode = CONV_TAN_STATS;
+      a.zh = ZH(sp, l, s); a.zh_stride = STRIDE(sp, zh, l);
+      a.stats = stat_at(h, PASS_TAN_FWD, s, l); a.stats_stride = h->stats_task_stride; a.tasks = T;
+      launch_conv_rows(a, st);
+    }
+    BnActTanArgs b{};
+    b.zdot = ZH(tn, l, 0); b.zdot_stride = STRIDE(tn, zh, l);
+    b.zh = ZH(sp, l, s); b.zh_stride = STRIDE(sp, zh, l);
+    b.stats_fwd = stat_at(h, PASS_SUP_FWD, s, l); b.stats_fwd_stride = h->stats_task_stride;
+    b.stats_tan = stat_at(h, PASS_TAN_FWD, s, l); b.stats_tan_stride = h->stats_task_stride;
+    b.gamma = gamma_at(h, meta, l, s); b.beta = beta_at(h, meta, l, s);
+    b.pdot = AIN(tn, l + 1, 0); b.pdot_stride = STRIDE(tn, ain, l + 1);
+    b.g = bn_geom(h, l, sp.n); b.tasks = T;
+    launch_bnact_tan(b, st);
+  }
+  const ChunkPlan& cp = h->plan_sup;
+  {
+    HeadArgs a{};
+    a.mode = HEAD_TANGENT; a.n = h->n_s; a.N = h->N; a.D = h->D;
+    a.f = AIN(sp, h->L, s); a.f_stride = STRIDE(sp, ain, h->L);
+    a.fdot = AIN(tn, h->L, 0); a.fdot_stride = STRIDE(tn, ain, h->L);
+    a.Wfc = theta + h->pl.fcw_off; a.bfc = theta + h->pl.fcb_off; a.theta_stride = h->Ppad;
+    a.uW = u + h->pl.fcw_off; a.ub = u + h->pl.fcb_off; a.u_stride = h->Ppad;
+    a.y = y_support; a.y_stride = h->n_s;
+    a.gW = h->sup_partial + cp.pd.off[2 * h->L]; a.gb = h->sup_partial + cp.pd.off[2 * h->L + 1]; a.g_stride = cp.pd.task_stride;
+    a.df = DP(tn, h->L - 1, 0); a.df_stride = STRIDE(tn, dp, h->L - 1);
+    a.tasks = T;
+    launch_head(a, st);
+  }
+  for (int l = h->L - 1; l >= 0; --l) {
+    const LayerGeom& g = h->geo[l];
+    BnBwdTanArgs b{};
+    b.dp = DP(sp, l, s); b.dp_stride = STRIDE(sp, dp, l);
+    b.dpdot = DP(tn, l, 0); b.dpdot_stride = STRIDE(tn, dp, l);
+    b.zh = ZH(sp, l, s); b.zh_stride = STRIDE(sp, zh, l);
+    b.zhdot = ZH(tn, l, 0); b.zhdot_stride = STRIDE(tn, zh, l);
+    b.dz = DZ(sp, l, s); b.dz_stride = STRIDE(sp, dz, l);
+    b.stats_fwd = stat_at(h, PASS_SUP_FWD, s, l); b.stats_fwd_stride = h->stats_task_stride;
+    b.stats_bwd = stat_at(h, PASS_SUP_BWD, s, l); b.stats_bwd_stride = h->stats_task_stride;
+    b.stats_tan = stat_at(h, PASS_TAN_FWD, s, l); b.stats_tan_stride = h->stats_task_stride;
+    b.stats_tbwd = stat_at(h, PASS_TAN_BWD, s, l); b.stats_tbwd_stride = h->stats_task_stride;
+    b.gamma = gamma_at(h, meta, l, s); b.beta = beta_at(h, meta, l, s);
+    b.dzdot = DZ(tn, l, 0); b.dzdot_stride = STRIDE(tn, dz, l);
+    b.g = bn_geom(h, l, sp.n); b.tasks = T;
+    launch_bnbwd_tan_reduce(b, st);
+    launch_bnbwd_tan_apply(b, st);
+
+    WgradArgs w{};
+    w.D[0] = DZ(tn, l, 0); w.d_stride[0] = STRIDE(tn, dz, l);
+    w.ncols = h->F; w.rows = sp.n * g.G; w.gw = g.gw;
+    w.rows_per_chunk = cp.rows_per_chunk[l]; w.nchunks = cp.nchunks[l];
+    w.partial = h->sup_partial + cp.pd.off[2 * l]; w.partial_task_stride = cp.pd.task_stride; w.chunk_stride = cp.pd.cstride[2 * l];
+    w.tasks = T;
+    if (l == 0) {
+      w.nsrc = 1;
+      w.A[0] = sp.xg; w.a_stride[0] = sp.xg_stride; w.kc = h->C;
+      launch_wgrad0(w, st);
+    } else {
+      w.nsrc = 2;
+      w.A[0] = AIN(sp, l, s); w.a_stride[0] = STRIDE(sp, ain, l); w.kc = h->F;
+      w.A[1] = AIN(tn, l, 0); w.a_stride[1] = STRIDE(tn, ain, l);
+      w.D[1] = DZ(sp, l, s); w.d_stride[1] = STRIDE(sp, dz, l);
+      launch_wgrad(w, st);
+      ConvArgs a{};
+      a.nsrc = 2;
+      a.src[0].A = DZ(tn, l, 0); a.src[0].a_stride = STRIDE(tn, dz, l);
+      a.src[0].W = theta + h->pl.w_off[l]; a.src[0].w_stride = h->Ppad; a.src[0].kc = h->F; a.src[0].wt = 1; a.src[0].sign = -1;
+      a.src[1].A = DZ(sp, l, s); a.src[1].a_stride = STRIDE(sp, dz, l);
+      a.src[1].W = u + h->pl.w_off[l]; a.src[1].w_stride = h->Ppad; a.src[1].kc = h->F; a.src[1].wt = 1; a.src[1].sign = -1;
+      a.out = DP(tn, l - 1, 0); a.out_stride = STRIDE(tn, dp, l - 1);
+      a.rows = sp.n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.ncols = h->F; a.mode = CONV_PLAIN; a.tasks = T;
+      launch_conv_rows(a, st);
+    }
+  }
+}
+
+extern "C" int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200_iter_args* it, const float* meta,
+                                            const float* x_support, const int64_t* y_support, const float* x_target,
+                                            const int64_t* y_target, float* result, float* last_logits, void* stream) {
+  if (!h || !it || !meta || !x_support || !y_support || !x_target || !y_target || !result) return fail("null argument");
+  const int T = it->n_tasks;
+  if (T < 1 || T > h->maxT) return fail("n_tasks out of range");
+  if (it->num_steps < 1 || it->num_steps > h->S) return fail("num_steps out of range (must be <= inner_steps)");
+  if (it->tasks_global < T) return fail("tasks_global < n_tasks");
+  const unsigned mask = it->target_mask & ((1u << it->num_steps) - 1u);
+  if (mask == 0) return fail("target_mask selects no target pass");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long launches0 = g_launch_counter;
+  const long long TP = (long long)h->maxT * h->Ppad;
+  const long long* ys = (const long long*)y_support;
+  const long long* yt = (const long long*)y_target;
+  int last_t = 0;
+  for (int s = 0; s < it->num_steps; ++s) if (mask & (1u << s)) last_t = s;
+
+  float* pin = h->pinned + 32 * (h->pin_slot++ & 15);
+  for (int s = 0; s < MAML_MAX_STEPS; ++s) pin[s] = it->target_weight[s];
+  CK(cudaMemcpyAsync(h->weights_dev, pin, MAML_MAX_STEPS * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(h->stats, 0, (size_t)h->stats_count * sizeof(double), st));
+  CK(cudaMemsetAsync(h->abar, 0, (size_t)h->maxT * h->pl.nseg_inner * MAML_MAX_STEPS * sizeof(float), st));
+  CK(cudaMemsetAsync(h->losses, 0, (size_t)h->maxT * MAML_MAX_STEPS * sizeof(float), st));
+  CK(cudaMemsetAsync(h->correct, 0, (size_t)h->maxT * sizeof(float), st));
+
+  launch_prep_x(x_support, h->sup.xg, h->sup.xg_stride, T, h->n_s, h->C, h->H, h->W, st);
+  launch_prep_x(x_target, h->tgt.xg, h->tgt.xg_stride, T, h->n_t, h->C, h->H, h->W, st);
+  launch_import_theta(h->pl, meta, h->theta, h->Ppad, T, st);
+
+  // ---------------- phase A: unroll the inner loop
+  for (int s = 0; s < it->num_steps; ++s) {
+    const float* th = h->theta + (long long)s * TP;
+    float* th_next = h->theta + (long long)(s + 1) * TP;
+    forward_pass(h, h->sup, s, th, meta, s, PASS_SUP_FWD, T, st);
+    {
+      HeadArgs a{};
+      a.mode = HEAD_SUPPORT; a.n = h->n_s; a.N = h->N; a.D = h->D;
+      a.f = AIN(h->sup, h->L, s); a.f_stride = STRIDE(h->sup, ain, h->L);
+      a.Wfc = th + h->pl.fcw_off; a.bfc = th + h->pl.fcb_off; a.theta_stride = h->Ppad;
+      a.y = ys; a.y_stride = h->n_s;
+      a.gW = h->sup_partial + h->plan_sup.pd.off[2 * h->L]; a.gb = h->sup_partial + h->plan_sup.pd.off[2 * h->L + 1];
+      a.g_stride = h->plan_sup.pd.task_stride;
+      a.df = DP(h->sup, h->L - 1, s); a.df_stride = STRIDE(h->sup, dp, h->L - 1);
+      a.tasks = T;
+      launch_head(a, st);
+    }
+    backward_pass(h, h->sup, s, th, meta, s, PASS_SUP_FWD, PASS_SUP_BWD, h->sup_partial, h->plan_sup, T, st);
+    launch_param_reduce(h->pl, h->plan_sup.pd, h->sup_partial, PR_UPDATE, th, th_next, h->g + (long long)s * TP, nullptr, meta, s,
+                        h->Ppad, T, st);
+    if (mask & (1u << s)) {
+      forward_pass(h, h->tgt, 0, th_next, meta, s, PASS_TGT_FWD, T, st);
+      HeadArgs a{};
+      a.mode = HEAD_TARGET_FWD; a.n = h->n_t; a.N = h->N; a.D = h->D;
+      a.f = AIN(h->tgt, h->L, 0); a.f_stride = STRIDE(h->tgt, ain, h->L);
+      a.Wfc = th_next + h->pl.fcw_off; a.bfc = th_next + h->pl.fcb_off; a.theta_stride = h->Ppad;
+      a.y = yt; a.y_stride = h->n_t;
+      a.loss_out = h->losses + s; a.loss_stride = MAML_MAX_STEPS;
+      if (s == last_t) {
+        a.logits_out = last_logits; a.logits_stride = (long long)h->n_t * h->N;
+        a.correct_out = h->correct; a.correct_stride = 1;
+      }
+      a.tasks = T;
+      launch_head(a, st);
+      if (it->training) {
+        HeadArgs bqa = a;
+        bqa.mode = HEAD_TARGET_BWD; bqa.scale_ptr = h->weights_dev + s;
+        bqa.logits_out = nullptr; bqa.correct_out = nullptr; bqa.loss_out = nullptr;
+        bqa.gW = h->tgt_partial + h->plan_tgt.pd.off[2 * h->L]; bqa.gb = h->tgt_partial + h->plan_tgt.pd.off[2 * h->L + 1];
+        bqa.g_stride = h->plan_tgt.pd.task_stride;
+        bqa.df = DP(h->tgt, h->L - 1, 0); bqa.df_stride = STRIDE(h->tgt, dp, h->L - 1);
+        launch_head(bqa, st);
+        backward_pass(h, h->tgt, 0, th_next, meta, s, PASS_TGT_FWD, PASS_TGT_BWD, h->tgt_partial, h->plan_tgt, T, st);
+        launch_param_reduce(h->pl, h->plan_tgt.pd, h->tgt_partial, PR_STORE, nullptr, nullptr, h->tgrad + (long long)s * TP, nullptr,
+                            meta, s, h->Ppad, T, st);
+      }
+    }
+  }
+
+  // ---------------- phase B: reverse sweep
+  if (it->training) {
+    CK(cudaMemsetAsync(h->tbar, 0, (size_t)TP * sizeof(float), st));
+    for (int s = it->num_steps - 1; s >= 0; --s) {
+      const float* th = h->theta + (long long)s * TP;
+      const float* tg = (mask & (1u << s)) ? h->tgrad + (long long)s * TP : nullptr;
+      launch_dots_u(h->pl, h->tbar, tg, h->g + (long long)s * TP, h->u, h->abar, meta, s, h->Ppad, T, st);
+      if (it->second_order) {
+        tangent_pass(h, s, th, h->u, meta, ys, T, st);
+        launch_param_reduce(h->pl, h->plan_sup.pd, h->sup_partial, PR_SUB, nullptr, nullptr, nullptr, h->tbar, meta, s, h->Ppad, T, st);
+      }
+    }
+  }
+
+  ExportArgs e{};
+  e.pl = h->pl;
+  e.tbar = h->tbar; e.task_stride = h->Ppad;
+  e.abar = h->abar;
+  e.stats = h->stats; e.stats_task_stride = h->stats_task_stride; e.st_pass_stride = h->st_pass_stride; e.st_layer_stride = h->st_layer_stride;
+  e.losses = h->losses; e.correct = h->correct; e.weights = h->weights_dev;
+  e.target_mask = mask; e.num_steps = it->num_steps; e.training = it->training;
+  e.tasks = T; e.task_offset = it->task_offset; e.tasks_global = it->tasks_global;
+  e.n_s = h->n_s; e.n_t = h->n_t;
+  for (int l = 0; l < h->L; ++l) e.hw[l] = h->geo[l].h * h->geo[l].w;
+  e.result = result;
+  launch_export(e, st);
+
+  h->last_launches = g_launch_counter - launches0;
+  h->last_tasks = T;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int maml_b200_adam_step(maml_b200_handle* h, float* meta, const float* grad, float* exp_avg, float* exp_avg_sq,
+                                   float lr, int32_t step, uint32_t trainable_mask, uint32_t clamp_mask, void* stream) {
+  if (!h || !meta || !grad || !exp_avg || !exp_avg_sq) return fail("null argument");
+  if (step < 1) return fail("step must be >= 1");
+  std::vector<long long> ends;
+  for (size_t k = 0; k < h->seg_off.size(); ++k) ends.push_back(h->seg_off[k] + h->seg_size[k]);
+  const float bc1 = (float)(1.0 - pow(0.9, (double)step));
+  const float bc2 = (float)(1.0 - pow(0.999, (double)step));
+  launch_adam(meta, grad, exp_avg, exp_avg_sq, h->pl.meta_size, lr, bc1, bc2, ends.data(), (int)ends.size(), trainable_mask,
+              clamp_mask, (cudaStream_t)stream);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int maml_b200_running_stats_update(maml_b200_handle* h, const float* result, float* running_mean, float* running_var,
+                                              const float* decay_host, void* stream) {
+  if (!h || !result || !running_mean || !running_var || !decay_host) return fail("null argument");
+  if (!h->cfg.per_step_bn) return 0;    // shared-BN mode passes running stats = None in the reference: no update
+  cudaStream_t st = (cudaStream_t)stream;
+  float* pin = h->pinned + 32 * (h->pin_slot++ & 15);
+  for (int s = 0; s < h->S; ++s) pin[s] = decay_host[s];
+  CK(cudaMemcpyAsync(h->decay_dev, pin, h->S * sizeof(float), cudaMemcpyHostToDevice, st));
+  const long long LSF = (long long)h->L * h->S * h->F;
+  launch_running_update(result + h->pl.meta_size + 2, result + h->pl.meta_size + 2 + LSF, running_mean, running_var, h->decay_dev,
+                        h->L, h->S, h->F, st);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// debug taps (tests): raw copy of one internal buffer
+// ---------------------------------------------------------------------------------------------
+extern "C" int64_t maml_b200_debug_read(maml_b200_handle* h, const char* name, int32_t task, int32_t step, int32_t layer,
+                                        float* host_out, int64_t capacity) {
+  if (!h || !name) { fail("null argument"); return -1; }
+  if (task < 0 || task >= h->maxT) { fail("bad task"); return -1; }
+  cudaDeviceSynchronize();
+  const std::string nm(name);
+  const float* src = nullptr; long long count = 0;
+  const long long TP = (long long)h->maxT * h->Ppad;
+  auto pass_buf = [&](const PassSet& ps, const std::string& what, int slot) -> bool {
+    if (slot < 0 || slot >= ps.slots) return false;
+    if (what == "ain") {
+      if (layer < 1 || layer > h->L) return false;
+      count = (layer == h->L) ? (long long)ps.n * h->D : (long long)ps.n * h->geo[layer].G * h->F;
+      src = ps.ain[layer] + ((long long)task * ps.slots + slot) * ps.ain_sz[layer];
+    } else if (what == "zh") {
+      if (layer < 0 || layer >= h->L) return false;
+      count = (long long)ps.n * h->geo[layer].G * h->F;
+      src = ps.zh[layer] + ((long long)task * ps.slots + slot) * ps.zh_sz[layer];
+    } else if (what == "dz") {
+      if (layer < 0 || layer >= h->L) return false;
+      count = (long long)ps.n * h->geo[layer].G * h->F;
+      src = ps.dz[layer] + ((long long)task * ps.slots + slot) * ps.dz_sz[layer];
+    } else if (what == "dp") {
+      if (layer < 0 || layer >= h->L) return false;
+      count = (long long)ps.n * h->geo[layer].pG * h->F;
+      src = ps.dp[layer] + ((long long)task * ps.slots + slot) * ps.dp_sz[layer];
+    } else return false;
+    return true;
+  };
+  bool ok = false;
+  if (nm.rfind("sup_", 0) == 0) ok = pass_buf(h->sup, nm.substr(4), step);
+  else if (nm.rfind("tgt_", 0) == 0) ok = pass_buf(h->tgt, nm.substr(4), 0);
+  else if (nm.rfind("tan_", 0) == 0) ok = pass_buf(h->tan, nm.substr(4), 0);
+  else if (nm == "theta") { if (step >= 0 && step <= h->S) { src = h->theta + (long long)step * TP + (long long)task * h->Ppad; count = h->pl.P; ok = true; } }
+  else if (nm == "g") { if (step >= 0 && step < h->S) { src = h->g + (long long)step * TP + (long long)task * h->Ppad; count = h->pl.P; ok = true; } }
+  else if (nm == "tgrad") { if (step >= 0 && step < h->S) { src = h->tgrad + (long long)step * TP + (long long)task * h->Ppad; count = h->pl.P; ok = true; } }
+  else if (nm == "tbar") { src = h->tbar + (long long)task * h->Ppad; count = h->pl.P; ok = true; }
+  else if (nm == "u") { src = h->u + (long long)task * h->Ppad; count = h->pl.P; ok = true; }
+  else if (nm == "losses") { src = h->losses + (long long)task * MAML_MAX_STEPS; count = MAML_MAX_STEPS; ok = true; }
+  else if (nm == "abar") { src = h->abar + (long long)task * h->pl.nseg_inner * MAML_MAX_STEPS; count = (long long)h->pl.nseg_inner * MAML_MAX_STEPS; ok = true; }
+  if (!ok) { fail("unknown debug tap / bad index: " + nm); return -1; }
+  const long long ncopy = std::min<long long>(count, capacity);
+  if (host_out && ncopy > 0) {
+    cudaError_t e = cudaMemcpy(host_out, src, (size_t)ncopy * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { fail(std::string("debug memcpy: ") + cudaGetErrorString(e)); return -1; }
+  }
+  return count;
+}

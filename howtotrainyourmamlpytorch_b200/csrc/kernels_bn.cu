@@ -1,0 +1,430 @@
+// BatchNorm(batch statistics) + leaky-ReLU(0.01) + 2x2 max-pool: forward, backward and the
+// forward-mode tangents of both (Hessian-vector pass), on the padded pixel-grid layout.
+//
+// Restates reference meta_neural_network_architectures.py:246-247 (F.batch_norm, training=True
+// always), :426 (F.leaky_relu), :651-652 (F.max_pool2d k=2,s=2, floor, first max wins) and their
+// derivatives; equations are SURVEY.md appendix A1-A3 (validated against the reference).
+//
+// Work item = (pooling window, channel quad).  A window is the 2x2 block (2wy+dy, 2wx+dx);
+// windows on the odd last row/column are "partial": they produce no pooled value and receive no
+// pooled gradient, but their positions still take part in BatchNorm.
+#include "common.cuh"
+
+struct Chan4 { float4 mu, r, g, b; };
+
+__device__ __forceinline__ float leaky(float y) { return y > 0.f ? y : LEAKY_SLOPE_F * y; }
+__device__ __forceinline__ float slope_of(float y) { return y > 0.f ? 1.f : LEAKY_SLOPE_F; }
+
+// per-channel constants from the fp64 sums (sum z, sum z^2)
+__device__ __forceinline__ void chan_setup(const double* __restrict__ st, const float* __restrict__ gamma,
+                                           const float* __restrict__ beta, double m, int F, float* s_mu, float* s_r,
+                                           float* s_g, float* s_b) {
+  const int tid = threadIdx.x;
+  if (tid < F) {
+    const double mean = st[tid * 2 + 0] / m;
+    double var = st[tid * 2 + 1] / m - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mu[tid] = (float)mean;
+    s_r[tid] = (float)(1.0 / sqrt(var + BN_EPS_D));
+    s_g[tid] = gamma[tid];
+    s_b[tid] = beta[tid];
+  }
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 ld4s(const float* s, int q) { return make_float4(s[q * 4], s[q * 4 + 1], s[q * 4 + 2], s[q * 4 + 3]); }
+
+#define F4_OP(out, expr) { out.x = expr(x); out.y = expr(y); out.z = expr(z); out.w = expr(w); }
+
+struct WinIter {
+  int hc, wc, NW, F4, WPB, q, lane;
+  __device__ WinIter(const BnGeom& g) {
+    hc = (g.h + 1) >> 1; wc = (g.w + 1) >> 1; NW = g.n * hc * wc; F4 = g.F >> 2;
+    WPB = blockDim.x / F4; q = threadIdx.x % F4; lane = threadIdx.x / F4;
+  }
+};
+
+// ------------------------------------------------------------------------------- forward
+__global__ void __launch_bounds__(256) bnact_kernel(BnActArgs a) {
+  __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64];
+  const BnGeom g = a.g;
+  const int task = blockIdx.y;
+  chan_setup(a.stats + (long long)task * a.stats_stride, a.gamma, a.beta, (double)g.n * g.h * g.w, g.F, s_mu, s_r, s_g, s_b);
+  __syncthreads();
+  WinIter it(g);
+  if (it.lane >= it.WPB) return;
+  const float4 mu = ld4s(s_mu, it.q), r = ld4s(s_r, it.q), ga = ld4s(s_g, it.q), be = ld4s(s_b, it.q);
+  float* z = a.z + (long long)task * a.z_stride;
+  float* p = a.p + (long long)task * a.p_stride;
+  for (int wi = blockIdx.x * it.WPB + it.lane; wi < it.NW; wi += gridDim.x * it.WPB) {
+    const int img = wi / (it.hc * it.wc);
+    const int rem = wi - img * it.hc * it.wc;
+    const int wy = rem / it.wc, wx = rem - wy * it.wc;
+    float4 best = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = 2 * wy + (k >> 1), xx = 2 * wx + (k & 1);
+      if (yy < g.h && xx < g.w) {
+        const long long idx = ((long long)img * g.G + (yy + 1) * g.gw + (xx + 1)) * g.F + it.q * 4;
+        const float4 zv = ld4(z + idx);
+        float4 zh, act;
+        zh.x = (zv.x - mu.x) * r.x; zh.y = (zv.y - mu.y) * r.y; zh.z = (zv.z - mu.z) * r.z; zh.w = (zv.w - mu.w) * r.w;
+        st4(z + idx, zh);
+        act.x = leaky(fmaf(ga.x, zh.x, be.x)); act.y = leaky(fmaf(ga.y, zh.y, be.y));
+        act.z = leaky(fmaf(ga.z, zh.z, be.z)); act.w = leaky(fmaf(ga.w, zh.w, be.w));
+        if (k == 0) best = act;
+        else {
+          if (act.x > best.x) best.x = act.x;
+          if (act.y > best.y) best.y = act.y;
+          if (act.z > best.z) best.z = act.z;
+          if (act.w > best.w) best.w = act.w;
+        }
+      }
+    }
+    if (wy < g.ph && wx < g.pw)
+      st4(p + ((long long)img * g.pG + (wy + g.pb) * g.pgw + (wx + g.pb)) * g.F + it.q * 4, best);
+  }
+}
+
+static inline dim3 bn_grid(const BnGeom& g, int tasks, int* block) {
+  const int F4 = g.F / 4;
+  const int wpb = 256 / F4;
+  *block = wpb * F4;
+  const int NW = g.n * ((g.h + 1) / 2) * ((g.w + 1) / 2);
+  int bx = (NW + wpb - 1) / wpb;
+  if (bx > 592) bx = 592;
+  if (bx < 1) bx = 1;
+  return dim3(bx, tasks);
+}
+
+void launch_bnact(const BnActArgs& a, cudaStream_t st) {
+  int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
+  bnact_kernel<<<grid, block, 0, st>>>(a);
+  CUDA_CHECK_LAUNCH();
+}
+
+// value of one window position: loads zh, recomputes y; used by all backward-type kernels
+struct WinPos { float4 zh; float4 y; bool ok; long long idx; };
+
+__device__ __forceinline__ void argmax_window(const float* __restrict__ zhp, const BnGeom& g, int img, int wy, int wx, int q,
+                                              const float4& ga, const float4& be, float4 (&zh)[4], long long (&idx)[4],
+                                              int4& arg, float4& slope_at) {
+  float4 best = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 ybest = best;
+  arg = make_int4(0, 0, 0, 0);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int yy = 2 * wy + (k >> 1), xx = 2 * wx + (k & 1);
+    idx[k] = ((long long)img * g.G + (yy + 1) * g.gw + (xx + 1)) * g.F + q * 4;
+    zh[k] = ld4(zhp + idx[k]);
+    float4 y, act;
+    y.x = fmaf(ga.x, zh[k].x, be.x); y.y = fmaf(ga.y, zh[k].y, be.y);
+    y.z = fmaf(ga.z, zh[k].z, be.z); y.w = fmaf(ga.w, zh[k].w, be.w);
+    act.x = leaky(y.x); act.y = leaky(y.y); act.z = leaky(y.z); act.w = leaky(y.w);
+    if (k == 0) { best = act; ybest = y; }
+    else {
+      if (act.x > best.x) { best.x = act.x; ybest.x = y.x; arg.x = k; }
+      if (act.y > best.y) { best.y = act.y; ybest.y = y.y; arg.y = k; }
+      if (act.z > best.z) { best.z = act.z; ybest.z = y.z; arg.z = k; }
+      if (act.w > best.w) { best.w = act.w; ybest.w = y.w; arg.w = k; }
+    }
+  }
+  slope_at.x = slope_of(ybest.x); slope_at.y = slope_of(ybest.y); slope_at.z = slope_of(ybest.z); slope_at.w = slope_of(ybest.w);
+}
+
+__device__ __forceinline__ float pick(const float4 (&v)[4], int k, int comp) {
+  const float4 t = v[k];
+  return comp == 0 ? t.x : comp == 1 ? t.y : comp == 2 ? t.z : t.w;
+}
+
+// block-level reduction of per-thread (4 channels x 2 sums) fp64 partials, then one atomic per channel
+__device__ __forceinline__ void block_reduce_stats(double (&s1)[4], double (&s2)[4], const WinIter& it, double* stats, int F) {
+  __shared__ double red[256 * 8];
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { red[tid * 8 + c * 2] = s1[c]; red[tid * 8 + c * 2 + 1] = s2[c]; }
+  __syncthreads();
+  for (int o = tid; o < F * 2; o += blockDim.x) {
+    const int ch = o >> 1, which = o & 1;
+    const int q = ch >> 2, comp = ch & 3;
+    double t = 0.0;
+    for (int l = 0; l < it.WPB; ++l) t += red[(l * it.F4 + q) * 8 + comp * 2 + which];
+    atomicAdd(&stats[ch * 2 + which], t);
+  }
+}
+
+// ------------------------------------------------------------------------------- backward: reduce
+__global__ void __launch_bounds__(256) bnbwd_reduce_kernel(BnBwdArgs a) {
+  __shared__ float s_g[64], s_b[64];
+  const BnGeom g = a.g;
+  const int task = blockIdx.y;
+  if (threadIdx.x < g.F) { s_g[threadIdx.x] = a.gamma[threadIdx.x]; s_b[threadIdx.x] = a.beta[threadIdx.x]; }
+  __syncthreads();
+  WinIter it(g);
+  double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  if (it.lane < it.WPB) {
+    const float4 ga = ld4s(s_g, it.q), be = ld4s(s_b, it.q);
+    const float* zhp = a.zh + (long long)task * a.zh_stride;
+    const float* dp = a.dp + (long long)task * a.dp_stride;
+    for (int wi = blockIdx.x * it.WPB + it.lane; wi < it.NW; wi += gridDim.x * it.WPB) {
+      const int img = wi / (it.hc * it.wc);
+      const int rem = wi - img * it.hc * it.wc;
+      const int wy = rem / it.wc, wx = rem - wy * it.wc;
+      if (wy >= g.ph || wx >= g.pw) continue;
+      float4 zh[4]; long long idx[4]; int4 arg; float4 sl;
+      argmax_window(zhp, g, img, wy, wx, it.q, ga, be, zh, idx, arg, sl);
+      const float4 d = ld4(dp + ((long long)img * g.pG + (wy + g.pb) * g.pgw + (wx + g.pb)) * g.F + it.q * 4);
+      const float dy0 = d.x * sl.x, dy1 = d.y * sl.y, dy2 = d.z * sl.z, dy3 = d.w * sl.w;
+      s1[0] += dy0; s2[0] += (double)dy0 * (double)pick(zh, arg.x, 0);
+      s1[1] += dy1; s2[1] += (double)dy1 * (double)pick(zh, arg.y, 1);
+      s1[2] += dy2; s2[2] += (double)dy2 * (double)pick(zh, arg.z, 2);
+      s1[3] += dy3; s2[3] += (double)dy3 * (double)pick(zh, arg.w, 3);
+    }
+  }
+  block_reduce_stats(s1, s2, it, a.stats_bwd + (long long)task * a.stats_bwd_stride, g.F);
+}
+
+void launch_bnbwd_reduce(const BnBwdArgs& a, cudaStream_t st) {
+  int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
+  if (grid.x > 148) grid.x = 148;
+  bnbwd_reduce_kernel<<<grid, block, 0, st>>>(a);
+  CUDA_CHECK_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------- backward: apply
+// dz = r * gamma * (dy - S1/m - zh * S2/m)   at every valid position (dy != 0 only at the arg-max)
+__global__ void __launch_bounds__(256) bnbwd_apply_kernel(BnBwdArgs a) {
+  __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_c1[64], s_c2[64];
+  const BnGeom g = a.g;
+  const int task = blockIdx.y;
+  const double m = (double)g.n * g.h * g.w;
+  chan_setup(a.stats_fwd + (long long)task * a.stats_fwd_stride, a.gamma, a.beta, m, g.F, s_mu, s_r, s_g, s_b);
+  if (threadIdx.x < g.F) {
+    const double* sb = a.stats_bwd + (long long)task * a.stats_bwd_stride;
+    s_c1[threadIdx.x] = (float)(sb[threadIdx.x * 2] / m);
+    s_c2[threadIdx.x] = (float)(sb[threadIdx.x * 2 + 1] / m);
+  }
+  __syncthreads();
+  WinIter it(g);
+  if (it.lane >= it.WPB) return;
+  const float4 r = ld4s(s_r, it.q), ga = ld4s(s_g, it.q), be = ld4s(s_b, it.q), c1 = ld4s(s_c1, it.q), c2 = ld4s(s_c2, it.q);
+  const float4 rg = make_float4(r.x * ga.x, r.y * ga.y, r.z * ga.z, r.w * ga.w);
+  const float* zhp = a.zh + (long long)task * a.zh_stride;
+  const float* dp = a.dp + (long long)task * a.dp_stride;
+  float* dz = a.dz + (long long)task * a.dz_stride;
+  for (int wi = blockIdx.x * it.WPB + it.lane; wi < it.NW; wi += gridDim.x * it.WPB) {
+    const int img = wi / (it.hc * it.wc);
+    const int rem = wi - img * it.hc * it.wc;
+    const int wy = rem / it.wc, wx = rem - wy * it.wc;
+    const bool full = (wy < g.ph && wx < g.pw);
+    if (full) {
+      float4 zh[4]; long long idx[4]; int4 arg; float4 sl;
+      argmax_window(zhp, g, img, wy, wx, it.q, ga, be, zh, idx, arg, sl);
+      const float4 d = ld4(dp + ((long long)img * g.pG + (wy + g.pb) * g.pgw + (wx + g.pb)) * g.F + it.q * 4);
+      const float4 dyv = make_float4(d.x * sl.x, d.y * sl.y, d.z * sl.z, d.w * sl.w);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float4 o;
+        o.x = rg.x * ((arg.x == k ? dyv.x : 0.f) - c1.x - zh[k].x * c2.x);
+        o.y = rg.y * ((arg.y == k ? dyv.y : 0.f) - c1.y - zh[k].y * c2.y);
+        o.z = rg.z * ((arg.z == k ? dyv.z : 0.f) - c1.z - zh[k].z * c2.z);
+        o.w = rg.w * ((arg.w == k ? dyv.w : 0.f) - c1.w - zh[k].w * c2.w);
+        st4(dz + idx[k], o);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int yy = 2 * wy + (k >> 1), xx = 2 * wx + (k & 1);
+        if (yy < g.h && xx < g.w) {
+          const long long idx = ((long long)img * g.G + (yy + 1) * g.gw + (xx + 1)) * g.F + it.q * 4;
+          const float4 zh = ld4(zhp + idx);
+          float4 o;
+          o.x = rg.x * (-c1.x - zh.x * c2.x); o.y = rg.y * (-c1.y - zh.y * c2.y);
+          o.z = rg.z * (-c1.z - zh.z * c2.z); o.w = rg.w * (-c1.w - zh.w * c2.w);
+          st4(dz + idx, o);
+        }
+      }
+    }
+  }
+}
+
+void launch_bnbwd_apply(const BnBwdArgs& a, cudaStream_t st) {
+  int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
+  bnbwd_apply_kernel<<<grid, block, 0, st>>>(a);
+  CUDA_CHECK_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------- tangent forward
+// zhdot = r * (zdot - mean(zdot) - zh * mean(zh * zdot));  pdot = slope * gamma * zhdot at the arg-max
+__global__ void __launch_bounds__(256) bnact_tan_kernel(BnActTanArgs a) {
+  __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_md[64], s_q[64];
+  const BnGeom g = a.g;
+  const int task = blockIdx.y;
+  const double m = (double)g.n * g.h * g.w;
+  chan_setup(a.stats_fwd + (long long)task * a.stats_fwd_stride, a.gamma, a.beta, m, g.F, s_mu, s_r, s_g, s_b);
+  if (threadIdx.x < g.F) {
+    const double* stt = a.stats_tan + (long long)task * a.stats_tan_stride;
+    s_md[threadIdx.x] = (float)(stt[threadIdx.x * 2] / m);
+    s_q[threadIdx.x] = (float)(stt[threadIdx.x * 2 + 1] / m);
+  }
+  __syncthreads();
+  WinIter it(g);
+  if (it.lane >= it.WPB) return;
+  const float4 r = ld4s(s_r, it.q), ga = ld4s(s_g, it.q), be = ld4s(s_b, it.q), md = ld4s(s_md, it.q), qq = ld4s(s_q, it.q);
+  float* zd = a.zdot + (long long)task * a.zdot_stride;
+  const float* zhp = a.zh + (long long)task * a.zh_stride;
+  float* pd = a.pdot + (long long)task * a.pdot_stride;
+  for (int wi = blockIdx.x * it.WPB + it.lane; wi < it.NW; wi += gridDim.x * it.WPB) {
+    const int img = wi / (it.hc * it.wc);
+    const int rem = wi - img * it.hc * it.wc;
+    const int wy = rem / it.wc, wx = rem - wy * it.wc;
+    float4 best = make_float4(0.f, 0.f, 0.f, 0.f), pbest = best;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = 2 * wy + (k >> 1), xx = 2 * wx + (k & 1);
+      if (yy < g.h && xx < g.w) {
+        const long long idx = ((long long)img * g.G + (yy + 1) * g.gw + (xx + 1)) * g.F + it.q * 4;
+        const float4 zh = ld4(zhp + idx);
+        const float4 zv = ld4(zd + idx);
+        float4 zhd;
+        zhd.x = r.x * (zv.x - md.x - zh.x * qq.x); zhd.y = r.y * (zv.y - md.y - zh.y * qq.y);
+        zhd.z = r.z * (zv.z - md.z - zh.z * qq.z); zhd.w = r.w * (zv.w - md.w - zh.w * qq.w);
+        st4(zd + idx, zhd);
+        float4 y, act, pdv;
+        y.x = fmaf(ga.x, zh.x, be.x); y.y = fmaf(ga.y, zh.y, be.y); y.z = fmaf(ga.z, zh.z, be.z); y.w = fmaf(ga.w, zh.w, be.w);
+        act.x = leaky(y.x); act.y = leaky(y.y); act.z = leaky(y.z); act.w = leaky(y.w);
+        pdv.x = slope_of(y.x) * ga.x * zhd.x; pdv.y = slope_of(y.y) * ga.y * zhd.y;
+        pdv.z = slope_of(y.z) * ga.z * zhd.z; pdv.w = slope_of(y.w) * ga.w * zhd.w;
+        if (k == 0) { best = act; pbest = pdv; }
+        else {
+          if (act.x > best.x) { best.x = act.x; pbest.x = pdv.x; }
+          if (act.y > best.y) { best.y = act.y; pbest.y = pdv.y; }
+          if (act.z > best.z) { best.z = act.z; pbest.z = pdv.z; }
+          if (act.w > best.w) { best.w = act.w; pbest.w = pdv.w; }
+        }
+      }
+    }
+    if (wy < g.ph && wx < g.pw)
+      st4(pd + ((long long)img * g.pG + (wy + g.pb) * g.pgw + (wx + g.pb)) * g.F + it.q * 4, pbest);
+  }
+}
+
+void launch_bnact_tan(const BnActTanArgs& a, cudaStream_t st) {
+  int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
+  bnact_tan_kernel<<<grid, block, 0, st>>>(a);
+  CUDA_CHECK_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------- tangent backward: reduce
+// T1 = sum dydot,  T2 = sum (dydot * zh + dy * zhdot)   (both only at the arg-max position)
+__global__ void __launch_bounds__(256) bnbwd_tan_reduce_kernel(BnBwdTanArgs a) {
+  __shared__ float s_g[64], s_b[64];
+  const BnGeom g = a.g;
+  const int task = blockIdx.y;
+  if (threadIdx.x < g.F) { s_g[threadIdx.x] = a.gamma[threadIdx.x]; s_b[threadIdx.x] = a.beta[threadIdx.x]; }
+  __syncthreads();
+  WinIter it(g);
+  double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  if (it.lane < it.WPB) {
+    const float4 ga = ld4s(s_g, it.q), be = ld4s(s_b, it.q);
+    const float* zhp = a.zh + (long long)task * a.zh_stride;
+    const float* zhd = a.zhdot + (long long)task * a.zhdot_stride;
+    const float* dp = a.dp + (long long)task * a.dp_stride;
+    const float* dpd = a.dpdot + (long long)task * a.dpdot_stride;
+    for (int wi = blockIdx.x * it.WPB + it.lane; wi < it.NW; wi += gridDim.x * it.WPB) {
+      const int img = wi / (it.hc * it.wc);
+      const int rem = wi - img * it.hc * it.wc;
+      const int wy = rem / it.wc, wx = rem - wy * it.wc;
+      if (wy >= g.ph || wx >= g.pw) continue;
+      float4 zh[4]; long long idx[4]; int4 arg; float4 sl;
+      argmax_window(zhp, g, img, wy, wx, it.q, ga, be, zh, idx, arg, sl);
+      const long long pidx = ((long long)img * g.pG + (wy + g.pb) * g.pgw + (wx + g.pb)) * g.F + it.q * 4;
+      const float4 d = ld4(dp + pidx), dd = ld4(dpd + pidx);
+      const int ar[4] = {arg.x, arg.y, arg.z, arg.w};
+      const float slv[4] = {sl.x, sl.y, sl.z, sl.w};
+      const float dv[4] = {d.x, d.y, d.z, d.w};
+      const float ddv[4] = {dd.x, dd.y, dd.z, dd.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float zhk = pick(zh, ar[c], c);
+        const float zhdk = zhd[idx[ar[c]] + c];
+        const float dy = dv[c] * slv[c], dyd = ddv[c] * slv[c];
+        s1[c] += dyd;
+        s2[c] += (double)dyd * (double)zhk + (double)dy * (double)zhdk;
+      }
+    }
+  }
+  block_reduce_stats(s1, s2, it, a.stats_tbwd + (long long)task * a.stats_tbwd_stride, g.F);
+}
+
+void launch_bnbwd_tan_reduce(const BnBwdTanArgs& a, cudaStream_t st) {
+  int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
+  if (grid.x > 148) grid.x = 148;
+  bnbwd_tan_reduce_kernel<<<grid, block, 0, st>>>(a);
+  CUDA_CHECK_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------- tangent backward: apply
+// dzdot = -r*q*dz + r*gamma*(dydot - T1/m - zhdot*S2/m - zh*T2/m)
+__global__ void __launch_bounds__(256) bnbwd_tan_apply_kernel(BnBwdTanArgs a) {
+  __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_q[64], s_c2[64], s_t1[64], s_t2[64];
+  const BnGeom g = a.g;
+  const int task = blockIdx.y;
+  const double m = (double)g.n * g.h * g.w;
+  chan_setup(a.stats_fwd + (long long)task * a.stats_fwd_stride, a.gamma, a.beta, m, g.F, s_mu, s_r, s_g, s_b);
+  if (threadIdx.x < g.F) {
+    const int c = threadIdx.x;
+    s_q[c] = (float)((a.stats_tan + (long long)task * a.stats_tan_stride)[c * 2 + 1] / m);
+    s_c2[c] = (float)((a.stats_bwd + (long long)task * a.stats_bwd_stride)[c * 2 + 1] / m);
+    const double* tb = a.stats_tbwd + (long long)task * a.stats_tbwd_stride;
+    s_t1[c] = (float)(tb[c * 2] / m);
+    s_t2[c] = (float)(tb[c * 2 + 1] / m);
+  }
+  __syncthreads();
+  WinIter it(g);
+  if (it.lane >= it.WPB) return;
+  const float4 r = ld4s(s_r, it.q), ga = ld4s(s_g, it.q), be = ld4s(s_b, it.q);
+  const float4 qq = ld4s(s_q, it.q), c2 = ld4s(s_c2, it.q), t1 = ld4s(s_t1, it.q), t2 = ld4s(s_t2, it.q);
+  const float4 rg = make_float4(r.x * ga.x, r.y * ga.y, r.z * ga.z, r.w * ga.w);
+  const float4 rq = make_float4(-r.x * qq.x, -r.y * qq.y, -r.z * qq.z, -r.w * qq.w);
+  const float* zhp = a.zh + (long long)task * a.zh_stride;
+  const float* zhd = a.zhdot + (long long)task * a.zhdot_stride;
+  const float* dzp = a.dz + (long long)task * a.dz_stride;
+  const float* dpd = a.dpdot + (long long)task * a.dpdot_stride;
+  float* dzd = a.dzdot + (long long)task * a.dzdot_stride;
+  for (int wi = blockIdx.x * it.WPB + it.lane; wi < it.NW; wi += gridDim.x * it.WPB) {
+    const int img = wi / (it.hc * it.wc);
+    const int rem = wi - img * it.hc * it.wc;
+    const int wy = rem / it.wc, wx = rem - wy * it.wc;
+    const bool full = (wy < g.ph && wx < g.pw);
+    int4 arg = make_int4(-1, -1, -1, -1);
+    float4 dyd = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (full) {
+      float4 zh[4]; long long idx[4]; float4 sl;
+      argmax_window(zhp, g, img, wy, wx, it.q, ga, be, zh, idx, arg, sl);
+      const float4 dd = ld4(dpd + ((long long)img * g.pG + (wy + g.pb) * g.pgw + (wx + g.pb)) * g.F + it.q * 4);
+      dyd = make_float4(dd.x * sl.x, dd.y * sl.y, dd.z * sl.z, dd.w * sl.w);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = 2 * wy + (k >> 1), xx = 2 * wx + (k & 1);
+      if (yy < g.h && xx < g.w) {
+        const long long idx = ((long long)img * g.G + (yy + 1) * g.gw + (xx + 1)) * g.F + it.q * 4;
+        const float4 zh = ld4(zhp + idx), zd = ld4(zhd + idx), dzv = ld4(dzp + idx);
+        float4 o;
+        o.x = rq.x * dzv.x + rg.x * ((arg.x == k ? dyd.x : 0.f) - t1.x - zd.x * c2.x - zh.x * t2.x);
+        o.y = rq.y * dzv.y + rg.y * ((arg.y == k ? dyd.y : 0.f) - t1.y - zd.y * c2.y - zh.y * t2.y);
+        o.z = rq.z * dzv.z + rg.z * ((arg.z == k ? dyd.z : 0.f) - t1.z - zd.z * c2.z - zh.z * t2.z);
+        o.w = rq.w * dzv.w + rg.w * ((arg.w == k ? dyd.w : 0.f) - t1.w - zd.w * c2.w - zh.w * t2.w);
+        st4(dzd + idx, o);
+      }
+    }
+  }
+}
+
+void launch_bnbwd_tan_apply(const BnBwdTanArgs& a, cudaStream_t st) {
+  int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
+  bnbwd_tan_apply_kernel<<<grid, block, 0, st>>>(a);
+  CUDA_CHECK_LAUNCH();
+}

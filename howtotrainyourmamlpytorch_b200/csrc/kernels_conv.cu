@@ -1,0 +1,436 @@
+// CUDA-core (fp32 FFMA) shifted-row GEMM kernels for the 3x3 / pad-1 convolutions of the
+// MAML backbone: forward conv, tangent conv (two operand pairs), dgrad, wgrad, and the small-K
+// first-block variants.  Restates (for the conv part) reference
+// meta_neural_network_architectures.py:89-97 (F.conv2d) and its autograd derivatives
+// (convolution_backward / double backward) -- see SURVEY.md appendix A1-A3.
+//
+// These kernels are the exact-fp32 path: used for the first block (K = 9*C_in is 9 or 27) and
+// for shapes the tcgen05 3xTF32 kernels (kernels_tc.cu) do not cover.
+#include "common.cuh"
+
+long long g_launch_counter = 0;
+
+__device__ __forceinline__ int tap_shift(int tap, int gw) { return (tap / 3 - 1) * gw + (tap % 3 - 1); }
+
+__device__ __forceinline__ bool row_valid(int row, int rows, int G, int gw, int h, int w) {
+  if (row >= rows) return false;
+  int rr = row % G;
+  int yy = rr / gw;
+  int xx = rr - yy * gw;
+  return yy >= 1 && yy <= h && xx >= 1 && xx <= w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared epilogue: + bias, store, and (optionally) per-channel batch statistics in fp64
+//   CONV_FWD_STATS: (sum z, sum z^2)            -> BatchNorm batch mean / biased variance
+//   CONV_TAN_STATS: (sum zdot, sum zh * zdot)   -> tangent of the BatchNorm statistics
+// thread (ty, tx) owns rows j0 + ty*4 .. +3 and columns tx*FN .. +FN-1
+// ---------------------------------------------------------------------------------------------
+template <int FN>
+__device__ __forceinline__ void conv_epilogue(float (&acc)[4][FN], int j0, int rows, int gw, int G, int h, int w,
+                                              int mode, const float* __restrict__ bias, float* __restrict__ out,
+                                              const float* __restrict__ zh, double* __restrict__ stats,
+                                              double* sred) {
+  constexpr int NC = 16 * FN;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  float bv[FN];
+#pragma unroll
+  for (int jn = 0; jn < FN; ++jn) bv[jn] = bias ? bias[tx * FN + jn] : 0.f;
+  double s1[FN], s2[FN];
+#pragma unroll
+  for (int jn = 0; jn < FN; ++jn) { s1[jn] = 0.0; s2[jn] = 0.0; }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = j0 + ty * 4 + i;
+    if (row < rows) {
+      const long long base = (long long)row * NC + tx * FN;
+      const bool valid = (mode != CONV_PLAIN) && row_valid(row, rows, G, gw, h, w);
+#pragma unroll
+      for (int jn = 0; jn < FN; ++jn) {
+        const float v = acc[i][jn] + bv[jn];
+        out[base + jn] = v;
+        if (valid) {
+          if (mode == CONV_FWD_STATS) {
+            s1[jn] += (double)v;
+            s2[jn] += (double)v * (double)v;
+          } else {
+            const float zv = zh[base + jn];
+            s1[jn] += (double)v;
+            s2[jn] += (double)zv * (double)v;
+          }
+        }
+      }
+    }
+  }
+  if (mode != CONV_PLAIN) {
+    const int warp = tid >> 5;
+#pragma unroll
+    for (int jn = 0; jn < FN; ++jn) {
+      s1[jn] += __shfl_xor_sync(0xffffffffu, s1[jn], 16);
+      s2[jn] += __shfl_xor_sync(0xffffffffu, s2[jn], 16);
+    }
+    if ((tid & 16) == 0) {
+#pragma unroll
+      for (int jn = 0; jn < FN; ++jn) {
+        sred[(warp * NC + tx * FN + jn) * 2 + 0] = s1[jn];
+        sred[(warp * NC + tx * FN + jn) * 2 + 1] = s2[jn];
+      }
+    }
+    __syncthreads();
+    for (int c = tid; c < NC * 2; c += 256) {
+      double t = 0.0;
+#pragma unroll
+      for (int wq = 0; wq < 8; ++wq) t += sred[wq * NC * 2 + c];
+      atomicAdd(&stats[c], t);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic shifted-row GEMM:  out[j, col] = sum_src sum_tap sum_k A_src[j +/- s_tap, k] * W_src[tap, k, col]
+// CTA tile 64 rows x NC columns, 256 threads, 4 x FN micro-tile, K step 16, register prefetch.
+// ---------------------------------------------------------------------------------------------
+template <int FN>
+__global__ void __launch_bounds__(256) conv_rows_kernel(ConvArgs a) {
+  constexpr int NC = 16 * FN;
+  __shared__ __align__(16) float As[16][68];
+  __shared__ __align__(16) float Ws[16][NC];
+  __shared__ double sred[8 * NC * 2];
+  const int task = blockIdx.y;
+  const int j0 = blockIdx.x * 64;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+
+  float acc[4][FN];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int jn = 0; jn < FN; ++jn) acc[i][jn] = 0.f;
+
+  const int it0 = 9 * (a.src[0].kc >> 4);
+  const int nit = it0 + (a.nsrc > 1 ? 9 * (a.src[1].kc >> 4) : 0);
+
+  float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rw = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cur_wt = 0;
+
+  auto fetch = [&](int it) {
+    const int s = (it < it0) ? 0 : 1;
+    const ConvSrc& src = a.src[s];
+    const int local = (s == 0) ? it : it - it0;
+    const int kch = src.kc >> 4;
+    const int tap = local / kch;
+    const int c0 = (local - tap * kch) << 4;
+    const int sh = src.sign * tap_shift(tap, a.gw);
+    {
+      const int row = tid >> 2, cq = tid & 3;
+      const int jr = j0 + row;
+      if (jr < a.rows) {
+        const float* p = src.A + (long long)task * src.a_stride + (long long)(jr + sh) * src.kc + c0 + cq * 4;
+        ra = *reinterpret_cast<const float4*>(p);
+      } else {
+        ra = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    cur_wt = src.wt;
+    if (tid < 4 * NC) {
+      const float* wb = src.W + (long long)task * src.w_stride;
+      if (src.wt == 0) {
+        rw = *reinterpret_cast<const float4*>(wb + (long long)(tap * src.kc + c0) * NC + tid * 4);
+      } else {
+        const int col = tid >> 2, kq = tid & 3;
+        rw = *reinterpret_cast<const float4*>(wb + (long long)(tap * NC + col) * src.kc + c0 + kq * 4);
+      }
+    }
+  };
+
+  fetch(0);
+  for (int it = 0; it < nit; ++it) {
+    {
+      const int row = tid >> 2, cq = tid & 3;
+      As[cq * 4 + 0][row] = ra.x; As[cq * 4 + 1][row] = ra.y; As[cq * 4 + 2][row] = ra.z; As[cq * 4 + 3][row] = ra.w;
+      if (tid < 4 * NC) {
+        if (cur_wt == 0) {
+          const int k = (tid * 4) / NC, col = (tid * 4) - k * NC;
+          *reinterpret_cast<float4*>(&Ws[k][col]) = rw;
+        } else {
+          const int col = tid >> 2, kq = tid & 3;
+          Ws[kq * 4 + 0][col] = rw.x; Ws[kq * 4 + 1][col] = rw.y; Ws[kq * 4 + 2][col] = rw.z; Ws[kq * 4 + 3][col] = rw.w;
+        }
+      }
+    }
+    __syncthreads();
+    if (it + 1 < nit) fetch(it + 1);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float b[FN];
+#pragma unroll
+      for (int jn = 0; jn < FN; ++jn) b[jn] = Ws[k][tx * FN + jn];
+#pragma unroll
+      for (int jn = 0; jn < FN; ++jn) {
+        acc[0][jn] = fmaf(a4.x, b[jn], acc[0][jn]);
+        acc[1][jn] = fmaf(a4.y, b[jn], acc[1][jn]);
+        acc[2][jn] = fmaf(a4.z, b[jn], acc[2][jn]);
+        acc[3][jn] = fmaf(a4.w, b[jn], acc[3][jn]);
+      }
+    }
+    __syncthreads();
+  }
+
+  conv_epilogue<FN>(acc, j0, a.rows, a.gw, a.G, a.h, a.w, a.mode,
+                    a.bias ? a.bias + (long long)task * a.bias_stride : nullptr,
+                    a.out + (long long)task * a.out_stride,
+                    a.zh ? a.zh + (long long)task * a.zh_stride : nullptr,
+                    a.stats ? a.stats + (long long)task * a.stats_stride : nullptr, sred);
+}
+
+void launch_conv_rows(const ConvArgs& a, cudaStream_t st) {
+  dim3 grid((a.rows + 63) / 64, a.tasks);
+  switch (a.ncols / 16) {
+    case 1: conv_rows_kernel<1><<<grid, 256, 0, st>>>(a); break;
+    case 2: conv_rows_kernel<2><<<grid, 256, 0, st>>>(a); break;
+    case 3: conv_rows_kernel<3><<<grid, 256, 0, st>>>(a); break;
+    default: conv_rows_kernel<4><<<grid, 256, 0, st>>>(a); break;
+  }
+  CUDA_CHECK_LAUNCH();
+}
+
+// ---------------------------------------------------------------------------------------------
+// first block: K = 9 * C0 (9 or 27) -- all weights and the image window live in shared memory
+// ---------------------------------------------------------------------------------------------
+template <int FN>
+__global__ void __launch_bounds__(256) conv0_kernel(Conv0Args a) {
+  constexpr int NC = 16 * FN;
+  extern __shared__ float sm0[];
+  __shared__ double sred[8 * NC * 2];
+  const int task = blockIdx.y;
+  const int j0 = blockIdx.x * 64;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int c0 = a.c0;
+  float* Ws = sm0;                       // [9*c0][NC]
+  float* xs = sm0 + 9 * c0 * NC;         // [(64 + 2*(gw+1))][c0]
+  const int halo = a.gw + 1;
+  const int wrows = 64 + 2 * halo;
+  const float* W = a.W + (long long)task * a.w_stride;
+  for (int i = tid; i < 9 * c0 * NC; i += 256) Ws[i] = W[i];
+  const float* X = a.X + (long long)task * a.x_stride;
+  const int guard = a.gw + 2;
+  for (int i = tid; i < wrows * c0; i += 256) {
+    const int r = j0 - halo + i / c0;
+    float v = 0.f;
+    if (r >= -guard && r < a.rows + guard) v = X[(long long)(j0 - halo) * c0 + i];
+    xs[i] = v;
+  }
+  __syncthreads();
+
+  float acc[4][FN];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int jn = 0; jn < FN; ++jn) acc[i][jn] = 0.f;
+
+  for (int tap = 0; tap < 9; ++tap) {
+    const int sh = tap_shift(tap, a.gw) + halo;
+    for (int c = 0; c < c0; ++c) {
+      float b[FN];
+#pragma unroll
+      for (int jn = 0; jn < FN; ++jn) b[jn] = Ws[(tap * c0 + c) * NC + tx * FN + jn];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float av = xs[(ty * 4 + i + sh) * c0 + c];
+#pragma unroll
+        for (int jn = 0; jn < FN; ++jn) acc[i][jn] = fmaf(av, b[jn], acc[i][jn]);
+      }
+    }
+  }
+  conv_epilogue<FN>(acc, j0, a.rows, a.gw, a.G, a.h, a.w, a.mode,
+                    a.bias ? a.bias + (long long)task * a.bias_stride : nullptr,
+                    a.out + (long long)task * a.out_stride,
+                    a.zh ? a.zh + (long long)task * a.zh_stride : nullptr,
+                    a.stats ? a.stats + (long long)task * a.stats_stride : nullptr, sred);
+}
+
+void launch_conv0(const Conv0Args& a, cudaStream_t st) {
+  dim3 grid((a.rows + 63) / 64, a.tasks);
+  const size_t smem = (size_t)(9 * a.c0 * a.ncols + (64 + 2 * (a.gw + 1)) * a.c0) * sizeof(float);
+  switch (a.ncols / 16) {
+    case 1: conv0_kernel<1><<<grid, 256, smem, st>>>(a); break;
+    case 2: conv0_kernel<2><<<grid, 256, smem, st>>>(a); break;
+    case 3: conv0_kernel<3><<<grid, 256, smem, st>>>(a); break;
+    default: conv0_kernel<4><<<grid, 256, smem, st>>>(a); break;
+  }
+  CUDA_CHECK_LAUNCH();
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad:  partial[chunk][tap][c][f] = sum_{j in chunk} sum_src A_src[j + s_tap, c] * D_src[j, f]
+//         partial[chunk][bias][f]   = sum_{j in chunk} D_0[j, f]                 (tap 4 CTA)
+// grid (nchunks * 9, tasks); chunks are reduced (in fixed order => deterministic) by the
+// parameter-space kernel that consumes the partial buffer.
+// ---------------------------------------------------------------------------------------------
+template <int CN, int FN>
+__global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
+  constexpr int KC = 16 * CN, NC = 16 * FN;
+  __shared__ __align__(16) float As[16][KC];
+  __shared__ __align__(16) float Ds[16][NC];
+  const int task = blockIdx.y;
+  const int chunk = blockIdx.x / 9, tap = blockIdx.x - chunk * 9;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int sh = tap_shift(tap, a.gw);
+  const int r_begin = chunk * a.rows_per_chunk;
+  const int r_end = min(a.rows, r_begin + a.rows_per_chunk);
+
+  float acc[CN][FN];
+#pragma unroll
+  for (int i = 0; i < CN; ++i)
+#pragma unroll
+    for (int jn = 0; jn < FN; ++jn) acc[i][jn] = 0.f;
+  float bacc = 0.f;
+
+  const int steps = (r_end > r_begin) ? (r_end - r_begin + 15) / 16 : 0;
+  const int nit = steps * a.nsrc;
+  float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rd = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto fetch = [&](int it) {
+    const int s = it / steps;
+    const int r0 = r_begin + (it - s * steps) * 16;
+    if (tid < 4 * KC) {
+      const int r = tid / (KC / 4), c4 = tid - r * (KC / 4);
+      const int jr = r0 + r;
+      if (jr < r_end)
+        ra = *reinterpret_cast<const float4*>(a.A[s] + (long long)task * a.a_stride[s] + (long long)(jr + sh) * KC + c4 * 4);
+      else
+        ra = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (tid < 4 * NC) {
+      const int r = tid / (NC / 4), f4 = tid - r * (NC / 4);
+      const int jr = r0 + r;
+      if (jr < r_end)
+        rd = *reinterpret_cast<const float4*>(a.D[s] + (long long)task * a.d_stride[s] + (long long)jr * NC + f4 * 4);
+      else
+        rd = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+
+  if (nit > 0) fetch(0);
+  for (int it = 0; it < nit; ++it) {
+    if (tid < 4 * KC) {
+      const int r = tid / (KC / 4), c4 = tid - r * (KC / 4);
+      *reinterpret_cast<float4*>(&As[r][c4 * 4]) = ra;
+    }
+    if (tid < 4 * NC) {
+      const int r = tid / (NC / 4), f4 = tid - r * (NC / 4);
+      *reinterpret_cast<float4*>(&Ds[r][f4 * 4]) = rd;
+    }
+    __syncthreads();
+    const bool bias_src = (it / steps) == 0;
+    if (it + 1 < nit) fetch(it + 1);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      float av[CN], b[FN];
+#pragma unroll
+      for (int i = 0; i < CN; ++i) av[i] = As[r][ty * CN + i];
+#pragma unroll
+      for (int jn = 0; jn < FN; ++jn) b[jn] = Ds[r][tx * FN + jn];
+#pragma unroll
+      for (int i = 0; i < CN; ++i)
+#pragma unroll
+        for (int jn = 0; jn < FN; ++jn) acc[i][jn] = fmaf(av[i], b[jn], acc[i][jn]);
+    }
+    if (tap == 4 && bias_src && tid < NC) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) bacc += Ds[r][tid];
+    }
+    __syncthreads();
+  }
+
+  float* P = a.partial + (long long)task * a.partial_task_stride + (long long)chunk * a.chunk_stride;
+#pragma unroll
+  for (int i = 0; i < CN; ++i)
+#pragma unroll
+    for (int jn = 0; jn < FN; ++jn) P[(long long)(tap * KC + ty * CN + i) * NC + tx * FN + jn] = acc[i][jn];
+  if (tap == 4 && tid < NC) P[(long long)9 * KC * NC + tid] = bacc;
+}
+
+void launch_wgrad(const WgradArgs& a, cudaStream_t st) {
+  dim3 grid(a.nchunks * 9, a.tasks);
+  const int cn = a.kc / 16, fn = a.ncols / 16;
+#define WG_CASE(C, F_) if (cn == C && fn == F_) { wgrad_kernel<C, F_><<<grid, 256, 0, st>>>(a); CUDA_CHECK_LAUNCH(); return; }
+  WG_CASE(1, 1) WG_CASE(2, 2) WG_CASE(3, 3) WG_CASE(4, 4)
+#undef WG_CASE
+}
+
+// first block wgrad: A = image matrix [rows][c0] (c0 <= 4), D = dz [rows][F]
+__global__ void __launch_bounds__(256) wgrad0_kernel(WgradArgs a) {
+  const int task = blockIdx.y, chunk = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int Fc = a.ncols, c0 = a.kc;
+  const int NG = 256 / Fc;
+  const int grp = tid / Fc, f = tid - grp * Fc;
+  const bool active = grp < NG;
+  const int ncombo = 9 * c0;
+  constexpr int MAXQ = 9;
+  float acc[MAXQ];
+  int off[MAXQ];
+#pragma unroll
+  for (int i = 0; i < MAXQ; ++i) {
+    acc[i] = 0.f;
+    const int q = grp + i * NG;
+    off[i] = (q < ncombo) ? tap_shift(q / c0, a.gw) * c0 + (q % c0) : 0;
+  }
+  float bacc = 0.f;
+  const int r_begin = chunk * a.rows_per_chunk;
+  const int r_end = min(a.rows, r_begin + a.rows_per_chunk);
+  const float* A = a.A[0] + (long long)task * a.a_stride[0];
+  const float* D = a.D[0] + (long long)task * a.d_stride[0];
+  if (active) {
+    for (int jr = r_begin; jr < r_end; ++jr) {
+      const float d = D[(long long)jr * Fc + f];
+      const float* ar = A + (long long)jr * c0;
+#pragma unroll
+      for (int i = 0; i < MAXQ; ++i) {
+        const int q = grp + i * NG;
+        if (q < ncombo) acc[i] = fmaf(ar[off[i]], d, acc[i]);
+      }
+      bacc += d;
+    }
+    float* P = a.partial + (long long)task * a.partial_task_stride + (long long)chunk * a.chunk_stride;
+#pragma unroll
+    for (int i = 0; i < MAXQ; ++i) {
+      const int q = grp + i * NG;
+      if (q < ncombo) P[(long long)q * Fc + f] = acc[i];
+    }
+    if (grp == 0) P[(long long)ncombo * Fc + f] = bacc;
+  }
+}
+
+void launch_wgrad0(const WgradArgs& a, cudaStream_t st) {
+  dim3 grid(a.nchunks, a.tasks);
+  wgrad0_kernel<<<grid, 256, 0, st>>>(a);
+  CUDA_CHECK_LAUNCH();
+}
+
+// ---------------------------------------------------------------------------------------------
+// image NCHW [tasks][n][C][H][W] -> padded-grid matrix [tasks][n*G][C] (valid positions only)
+// ---------------------------------------------------------------------------------------------
+__global__ void prep_x_kernel(const float* __restrict__ x, float* __restrict__ xg, long long xg_task_stride, int n,
+                              int C, int H, int W) {
+  const int task = blockIdx.y;
+  const long long total = (long long)n * H * W;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int xx = (int)(i % W);
+  const int yy = (int)((i / W) % H);
+  const int img = (int)(i / ((long long)W * H));
+  const int gw = W + 2, G = (H + 2) * (W + 2);
+  const float* src = x + ((long long)task * n + img) * C * H * W + (long long)yy * W + xx;
+  float* dst = xg + (long long)task * xg_task_stride + ((long long)img * G + (yy + 1) * gw + (xx + 1)) * C;
+  for (int c = 0; c < C; ++c) dst[c] = src[(long long)c * H * W];
+}
+
+void launch_prep_x(const float* x, float* xg, long long xg_task_stride, int tasks, int n, int C, int H, int W,
+                   cudaStream_t st) {
+  const long long total = (long long)n * H * W;
+  dim3 grid((unsigned)((total + 255) / 256), tasks);
+  prep_x_kernel<<<grid, 256, 0, st>>>(x, xg, xg_task_stride, n, C, H, W);
+  CUDA_CHECK_LAUNCH();
+}

@@ -1,0 +1,136 @@
+// Classifier head: flatten + linear + mean softmax cross-entropy, its gradient, and the forward-mode
+// tangent of both.  One CTA per task (n <= ~100 rows, N <= 32 classes, D <= a few thousand).
+// Restates reference meta_neural_network_architectures.py:657-658 / :141 (view + F.linear) and
+// few_shot_learning_system.py:284 (F.cross_entropy, mean reduction); tangent: SURVEY.md appendix A3.
+//
+// Feature order: f[i][d] with d = pixel * F + channel (grid order).  The fast weights keep W_fc in
+// the same internal order; import / export kernels permute from / to the reference's
+// channel-major flatten (NCHW .view(n, -1)).
+#include "common.cuh"
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
+  extern __shared__ float smh[];
+  __shared__ float s_rowloss[128];
+  __shared__ float s_rowcorrect[128];
+  const int task = blockIdx.x;
+  const int n = a.n, N = a.N, D = a.D;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* logits = smh;
+  float* prob = smh + n * N;
+  float* dl = smh + 2 * n * N;
+  float* ldot = smh + 3 * n * N;
+  float* dldot = smh + 4 * n * N;
+  const bool tan = (a.mode == HEAD_TANGENT);
+
+  const float* f = a.f + (long long)task * a.f_stride;
+  const float* W = a.Wfc + (long long)task * a.theta_stride;
+  const float* b = a.bfc + (long long)task * a.theta_stride;
+  const float* fd = tan ? a.fdot + (long long)task * a.fdot_stride : nullptr;
+  const float* uW = tan ? a.uW + (long long)task * a.u_stride : nullptr;
+  const float* ub = tan ? a.ub + (long long)task * a.u_stride : nullptr;
+  const long long* y = a.y + (long long)task * a.y_stride;
+
+  for (int o = warp; o < n * N; o += 8) {
+    const int i = o / N, k = o - i * N;
+    float s = 0.f, sd = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float fv = f[(long long)i * D + d], wv = W[(long long)k * D + d];
+      s = fmaf(fv, wv, s);
+      if (tan) sd += fd[(long long)i * D + d] * wv + fv * uW[(long long)k * D + d];
+    }
+    s = warp_sum(s);
+    if (tan) sd = warp_sum(sd);
+    if (lane == 0) {
+      logits[o] = s + b[k];
+      if (tan) ldot[o] = sd + ub[k];
+    }
+  }
+  __syncthreads();
+
+  const float wscale = (a.scale_ptr ? *a.scale_ptr : 1.f);
+  const float inv_n = 1.f / (float)n;
+  for (int i = tid; i < n; i += 256) {
+    float mx = logits[i * N];
+    int am = 0;
+    for (int k = 1; k < N; ++k) {
+      const float v = logits[i * N + k];
+      if (v > mx) { mx = v; am = k; }
+    }
+    float se = 0.f;
+    for (int k = 0; k < N; ++k) se += expf(logits[i * N + k] - mx);
+    const float lse = mx + logf(se);
+    const int yi = (int)y[i];
+    float pd = 0.f;
+    for (int k = 0; k < N; ++k) {
+      const float p = expf(logits[i * N + k] - mx) / se;
+      prob[i * N + k] = p;
+      dl[i * N + k] = (p - (k == yi ? 1.f : 0.f)) * (wscale * inv_n);
+      if (tan) pd += p * ldot[i * N + k];
+    }
+    if (tan)
+      for (int k = 0; k < N; ++k) {
+        const float p = prob[i * N + k];
+        dldot[i * N + k] = (p * ldot[i * N + k] - p * pd) * inv_n;
+      }
+    if (i < 128) { s_rowloss[i] = lse - logits[i * N + yi]; s_rowcorrect[i] = (am == yi) ? 1.f : 0.f; }
+  }
+  __syncthreads();
+
+  if (a.mode == HEAD_TARGET_FWD) {
+    if (tid == 0) {
+      float ls = 0.f, cs = 0.f;
+      for (int i = 0; i < n; ++i) { ls += s_rowloss[i]; cs += s_rowcorrect[i]; }
+      a.loss_out[(long long)task * a.loss_stride] = ls * inv_n;
+      if (a.correct_out) a.correct_out[(long long)task * a.correct_stride] = cs;
+    }
+    if (a.logits_out) {
+      float* lo = a.logits_out + (long long)task * a.logits_stride;
+      for (int o = tid; o < n * N; o += 256) lo[o] = logits[o];
+    }
+    return;
+  }
+
+  float* gW = a.gW + (long long)task * a.g_stride;
+  float* gb = a.gb + (long long)task * a.g_stride;
+  for (int o = tid; o < N * D; o += 256) {
+    const int k = o / D, d = o - k * D;
+    float s = 0.f;
+    if (!tan) {
+      for (int i = 0; i < n; ++i) s = fmaf(dl[i * N + k], f[(long long)i * D + d], s);
+    } else {
+      for (int i = 0; i < n; ++i)
+        s += dldot[i * N + k] * f[(long long)i * D + d] + dl[i * N + k] * fd[(long long)i * D + d];
+    }
+    gW[o] = s;
+  }
+  if (tid < N) {
+    float s = 0.f;
+    const float* src = tan ? dldot : dl;
+    for (int i = 0; i < n; ++i) s += src[i * N + tid];
+    gb[tid] = s;
+  }
+  float* df = a.df + (long long)task * a.df_stride;
+  for (int o = tid; o < n * D; o += 256) {
+    const int i = o / D, d = o - i * D;
+    float s = 0.f;
+    if (!tan) {
+      for (int k = 0; k < N; ++k) s = fmaf(dl[i * N + k], W[(long long)k * D + d], s);
+    } else {
+      for (int k = 0; k < N; ++k)
+        s += dldot[i * N + k] * W[(long long)k * D + d] + dl[i * N + k] * uW[(long long)k * D + d];
+    }
+    df[o] = s;
+  }
+}
+
+void launch_head(const HeadArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)5 * a.n * a.N * sizeof(float);
+  head_kernel<<<a.tasks, 256, smem, st>>>(a);
+  CUDA_CHECK_LAUNCH();
+}

@@ -1,0 +1,307 @@
+// Parameter-space kernels: import of the meta-parameters into the per-task fast-weight layout, the
+// LSLR fast-weight update fused with the deterministic reduction of the wgrad partials, the reverse
+// sweep bookkeeping (alpha-bar, u = alpha * theta-bar), export of the meta-gradient in the
+// reference's layout, fused clamp + Adam, running-statistic EMA.
+//
+// Restates reference inner_loop_optimizers.py:99-113 (theta' = theta - alpha[name][step] * g),
+// few_shot_learning_system.py:105-120 (which tensors adapt), :325-336 (clamp + Adam),
+// meta_neural_network_architectures.py:226-247 (running-stat EMA side effect) and SURVEY.md A4.
+#include "common.cuh"
+
+// internal index (per-task fast-weight vector) -> index in the reference-layout flat meta vector
+__device__ __forceinline__ long long internal_to_meta(const ParamLayout& pl, long long i, int* seg_out) {
+  for (int l = 0; l < pl.L; ++l) {
+    const long long wsz = 9LL * pl.cin[l] * pl.F;
+    if (i >= pl.w_off[l] && i < pl.w_off[l] + wsz) {
+      const long long rel = i - pl.w_off[l];
+      const int f = (int)(rel % pl.F);
+      const int c = (int)((rel / pl.F) % pl.cin[l]);
+      const int tap = (int)(rel / ((long long)pl.F * pl.cin[l]));
+      *seg_out = 2 * l;
+      return pl.m_w[l] + ((long long)f * pl.cin[l] + c) * 9 + tap;
+    }
+    if (i >= pl.b_off[l] && i < pl.b_off[l] + pl.F) {
+      *seg_out = 2 * l + 1;
+      return pl.m_b[l] + (i - pl.b_off[l]);
+    }
+  }
+  const long long D = (long long)pl.pix * pl.F;
+  if (i >= pl.fcw_off && i < pl.fcw_off + (long long)pl.N * D) {
+    const long long rel = i - pl.fcw_off;
+    const int k = (int)(rel / D);
+    const int r2 = (int)(rel % D);
+    const int pix = r2 / pl.F, c = r2 % pl.F;
+    *seg_out = 2 * pl.L;
+    return pl.m_fcw + (long long)k * D + (long long)c * pl.pix + pix;
+  }
+  *seg_out = 2 * pl.L + 1;
+  return pl.m_fcb + (i - pl.fcb_off);
+}
+
+__global__ void import_theta_kernel(ParamLayout pl, const float* __restrict__ meta, float* __restrict__ theta0,
+                                    long long stride, int tasks) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pl.P) return;
+  int seg;
+  const float v = meta[internal_to_meta(pl, i, &seg)];
+  for (int t = 0; t < tasks; ++t) theta0[(long long)t * stride + i] = v;
+}
+
+void launch_import_theta(const ParamLayout& pl, const float* meta, float* theta0, long long stride, int tasks,
+                         cudaStream_t st) {
+  import_theta_kernel<<<(unsigned)((pl.P + 255) / 256), 256, 0, st>>>(pl, meta, theta0, stride, tasks);
+  CUDA_CHECK_LAUNCH();
+}
+
+__device__ __forceinline__ int seg_of(const ParamLayout& pl, long long i) {
+  int s = 0;
+  for (int k = 1; k < pl.nseg_inner; ++k)
+    if (i >= pl.seg_off[k]) s = k;
+  return s;
+}
+
+// reduce the gradient chunks of every inner tensor (fixed order) and
+//   PR_UPDATE: g_out = sum; theta_out = theta_in - alpha[seg][step] * sum     (LSLR step)
+//   PR_STORE : g_out = sum
+//   PR_SUB   : tbar -= sum
+__global__ void param_reduce_kernel(ParamLayout pl, PartialDesc pd, const float* __restrict__ partial, int mode,
+                                    const float* __restrict__ theta_in, float* __restrict__ theta_out,
+                                    float* __restrict__ g_out, float* __restrict__ tbar,
+                                    const float* __restrict__ meta, int step, long long task_stride) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pl.P) return;
+  const int task = blockIdx.y;
+  const int seg = seg_of(pl, i);
+  const float* p = partial + (long long)task * pd.task_stride + pd.off[seg] + (i - pl.seg_off[seg]);
+  float s = 0.f;
+  for (int c = 0; c < pd.nchunks[seg]; ++c) s += p[(long long)c * pd.cstride[seg]];
+  const long long o = (long long)task * task_stride + i;
+  if (mode == PR_UPDATE) {
+    const float alpha = meta[pl.m_lslr + (long long)seg * (pl.S + 1) + step];
+    g_out[o] = s;
+    theta_out[o] = theta_in[o] - alpha * s;
+  } else if (mode == PR_STORE) {
+    g_out[o] = s;
+  } else {
+    tbar[o] -= s;
+  }
+}
+
+void launch_param_reduce(const ParamLayout& pl, const PartialDesc& pd, const float* partial, int mode,
+                         const float* theta_in, float* theta_out, float* g_out, float* tbar, const float* meta, int step,
+                         long long task_stride, int tasks, cudaStream_t st) {
+  dim3 grid((unsigned)((pl.P + 255) / 256), tasks);
+  param_reduce_kernel<<<grid, 256, 0, st>>>(pl, pd, partial, mode, theta_in, theta_out, g_out, tbar, meta, step, task_stride);
+  CUDA_CHECK_LAUNCH();
+}
+
+// per (task, inner tensor):  tbar += tgrad (optional);  abar[seg][step] = -<tbar, g>;  u = alpha[seg][step] * tbar
+__global__ void __launch_bounds__(256) dots_u_kernel(ParamLayout pl, float* __restrict__ tbar, const float* __restrict__ tgrad,
+                                                     const float* __restrict__ g, float* __restrict__ u,
+                                                     float* __restrict__ abar, const float* __restrict__ meta, int step,
+                                                     long long task_stride) {
+  __shared__ double red[8];
+  const int seg = blockIdx.x, task = blockIdx.y;
+  const long long base = (long long)task * task_stride + pl.seg_off[seg];
+  const float alpha = meta[pl.m_lslr + (long long)seg * (pl.S + 1) + step];
+  double dot = 0.0;
+  for (long long i = threadIdx.x; i < pl.seg_size[seg]; i += 256) {
+    float tb = tbar[base + i];
+    if (tgrad) { tb += tgrad[base + i]; tbar[base + i] = tb; }
+    dot += (double)tb * (double)g[base + i];
+    u[base + i] = alpha * tb;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    abar[((long long)task * pl.nseg_inner + seg) * MAML_MAX_STEPS + step] = (float)(-t);
+  }
+}
+
+void launch_dots_u(const ParamLayout& pl, float* tbar, const float* tgrad, const float* g, float* u, float* abar,
+                   const float* meta, int step, long long task_stride, int tasks, cudaStream_t st) {
+  dim3 grid(pl.nseg_inner, tasks);
+  dots_u_kernel<<<grid, 256, 0, st>>>(pl, tbar, tgrad, g, u, abar, meta, step, task_stride);
+  CUDA_CHECK_LAUNCH();
+}
+
+// ---------------------------------------------------------------------------------------------
+// export: result = [meta-gradient (reference layout) | loss | n_correct | running-mean parts | running-var parts]
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ const double* stat_ptr(const ExportArgs& a, int task, int kind, int step, int layer) {
+  return a.stats + (long long)task * a.stats_task_stride + ((long long)kind * MAML_MAX_STEPS + step) * a.st_pass_stride +
+         (long long)layer * a.st_layer_stride;
+}
+
+__global__ void export_kernel(ExportArgs a) {
+  const ParamLayout& pl = a.pl;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long LSF = (long long)pl.L * pl.S * pl.F;
+  const long long total = pl.meta_size + 2 + (pl.per_step_bn ? 2 * LSF : 0);
+  if (i >= total) return;
+  const double invB = 1.0 / (double)a.tasks_global;
+  double val = 0.0;
+  if (i < pl.meta_size) {
+    if (!a.training) { a.result[i] = 0.f; return; }
+    // which meta segment?
+    bool done = false;
+    for (int l = 0; l < pl.L && !done; ++l) {
+      const long long wsz = 9LL * pl.cin[l] * pl.F;
+      const long long bnsz = (long long)(pl.per_step_bn ? pl.S : 1) * pl.F;
+      if (i >= pl.m_w[l] && i < pl.m_w[l] + wsz) {
+        const long long rel = i - pl.m_w[l];
+        const int tap = (int)(rel % 9);
+        const int c = (int)((rel / 9) % pl.cin[l]);
+        const int f = (int)(rel / (9LL * pl.cin[l]));
+        const long long ii = pl.w_off[l] + ((long long)tap * pl.cin[l] + c) * pl.F + f;
+        for (int t = 0; t < a.tasks; ++t) val += (double)a.tbar[(long long)t * a.task_stride + ii];
+        done = true;
+      } else if (i >= pl.m_b[l] && i < pl.m_b[l] + pl.F) {
+        const long long ii = pl.b_off[l] + (i - pl.m_b[l]);
+        for (int t = 0; t < a.tasks; ++t) val += (double)a.tbar[(long long)t * a.task_stride + ii];
+        done = true;
+      } else if ((i >= pl.m_beta[l] && i < pl.m_beta[l] + bnsz) || (i >= pl.m_gamma[l] && i < pl.m_gamma[l] + bnsz)) {
+        const bool is_gamma = (i >= pl.m_gamma[l] && i < pl.m_gamma[l] + bnsz);
+        const long long rel = i - (is_gamma ? pl.m_gamma[l] : pl.m_beta[l]);
+        const int f = (int)(rel % pl.F);
+        const int s_sel = (int)(rel / pl.F);
+        const int which = is_gamma ? 1 : 0;
+        for (int s = 0; s < a.num_steps; ++s) {
+          if (pl.per_step_bn && s != s_sel) continue;
+          for (int t = 0; t < a.tasks; ++t) {
+            val += stat_ptr(a, t, PASS_TGT_BWD, s, l)[f * 2 + which];
+            val -= stat_ptr(a, t, PASS_TAN_BWD, s, l)[f * 2 + which];
+          }
+        }
+        done = true;
+      }
+    }
+    if (!done) {
+      const long long D = (long long)pl.pix * pl.F;
+      if (i >= pl.m_fcw && i < pl.m_fcw + (long long)pl.N * D) {
+        const long long rel = i - pl.m_fcw;
+        const int k = (int)(rel / D);
+        const int r2 = (int)(rel % D);
+        const int c = r2 / pl.pix, pix = r2 % pl.pix;
+        const long long ii = pl.fcw_off + (long long)k * D + (long long)pix * pl.F + c;
+        for (int t = 0; t < a.tasks; ++t) val += (double)a.tbar[(long long)t * a.task_stride + ii];
+      } else if (i >= pl.m_fcb && i < pl.m_fcb + pl.N) {
+        const long long ii = pl.fcb_off + (i - pl.m_fcb);
+        for (int t = 0; t < a.tasks; ++t) val += (double)a.tbar[(long long)t * a.task_stride + ii];
+      } else {
+        const long long rel = i - pl.m_lslr;
+        const int seg = (int)(rel / (pl.S + 1));
+        const int s = (int)(rel % (pl.S + 1));
+        if (s < a.num_steps)
+          for (int t = 0; t < a.tasks; ++t)
+            val += (double)a.abar[((long long)t * pl.nseg_inner + seg) * MAML_MAX_STEPS + s];
+      }
+    }
+    a.result[i] = (float)(val * invB);
+    return;
+  }
+  if (i == pl.meta_size) {
+    for (int t = 0; t < a.tasks; ++t)
+      for (int s = 0; s < a.num_steps; ++s)
+        if (a.target_mask & (1u << s)) val += (double)a.weights[s] * (double)a.losses[(long long)t * MAML_MAX_STEPS + s];
+    a.result[i] = (float)(val * invB);
+    return;
+  }
+  if (i == pl.meta_size + 1) {
+    for (int t = 0; t < a.tasks; ++t) val += (double)a.correct[t];
+    a.result[i] = (float)val;
+    return;
+  }
+  // running-statistic partial sums (per-step BN only).  For block l, step s the reference applies, for
+  // global task g = 0..B-1 in order: support update, then (if a target pass runs at s) target update;
+  // r <- 0.9 r + 0.1 stat.  Unrolled: r_new = 0.9^U r_old + sum_k 0.1 * 0.9^(U-1-k) stat_k.
+  long long rel = i - (pl.meta_size + 2);
+  const int which = (int)(rel / LSF);           // 0: mean, 1: var
+  rel -= (long long)which * LSF;
+  const int l = (int)(rel / ((long long)pl.S * pl.F));
+  const int s = (int)((rel / pl.F) % pl.S);
+  const int f = (int)(rel % pl.F);
+  if (!a.training || s >= a.num_steps) { a.result[i] = 0.f; return; }
+  const bool has_t = (a.target_mask >> s) & 1u;
+  const int c = has_t ? 2 : 1;
+  const int U = c * a.tasks_global;
+  for (int t = 0; t < a.tasks; ++t) {
+    const int gidx = a.task_offset + t;
+    for (int j = 0; j < c; ++j) {
+      const int k = c * gidx + j;
+      const double wgt = 0.1 * pow(0.9, (double)(U - 1 - k));
+      const double* sp = stat_ptr(a, t, j == 0 ? PASS_SUP_FWD : PASS_TGT_FWD, s, l);
+      const double m = (double)(j == 0 ? a.n_s : a.n_t) * (double)a.hw[l];
+      const double mean = sp[f * 2] / m;
+      if (which == 0) val += wgt * mean;
+      else {
+        double var = sp[f * 2 + 1] / m - mean * mean;
+        if (var < 0.0) var = 0.0;
+        val += wgt * var * (m / (m > 1.0 ? m - 1.0 : 1.0));
+      }
+    }
+  }
+  a.result[i] = (float)val;
+}
+
+void launch_export(const ExportArgs& a, cudaStream_t st) {
+  const long long total = a.pl.meta_size + 2 + (a.pl.per_step_bn ? 2LL * a.pl.L * a.pl.S * a.pl.F : 0);
+  export_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+  CUDA_CHECK_LAUNCH();
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused clamp + Adam over the flat vectors
+// ---------------------------------------------------------------------------------------------
+struct SegEnds { long long e[32]; int n; };
+
+__global__ void adam_kernel(float* __restrict__ meta, const float* __restrict__ grad, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float bc1, float bc2, SegEnds se,
+                            unsigned trainable_mask, unsigned clamp_mask) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int seg = 0;
+  for (int k = 0; k < se.n; ++k)
+    if (i >= se.e[k]) seg = k + 1;
+  if (!((trainable_mask >> seg) & 1u)) return;
+  float g = grad[i];
+  if ((clamp_mask >> seg) & 1u) g = fminf(fmaxf(g, -10.f), 10.f);
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+  // torch.optim.Adam (single-tensor path): exp_avg.lerp_(grad, 1-beta1); exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
+  const float mi = m[i] + (g - m[i]) * (1.f - b1);
+  const float vi = v[i] * b2 + (1.f - b2) * g * g;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+  meta[i] = meta[i] - (lr / bc1) * (mi / denom);
+}
+
+void launch_adam(float* meta, const float* grad, float* m, float* v, long long n, float lr, float bc1, float bc2,
+                 const long long* seg_end_host, int nseg, unsigned trainable_mask, unsigned clamp_mask, cudaStream_t st) {
+  SegEnds se;
+  se.n = nseg - 1;
+  for (int k = 0; k < nseg - 1 && k < 32; ++k) se.e[k] = seg_end_host[k];
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(meta, grad, m, v, n, lr, bc1, bc2, se, trainable_mask, clamp_mask);
+  CUDA_CHECK_LAUNCH();
+}
+
+__global__ void running_update_kernel(const float* __restrict__ pm, const float* __restrict__ pv, float* __restrict__ rm,
+                                      float* __restrict__ rv, const float* __restrict__ decay, int L, int S, int F) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L * S * F) return;
+  const int s = (i / F) % S;
+  const float d = decay[s];
+  rm[i] = d * rm[i] + pm[i];
+  rv[i] = d * rv[i] + pv[i];
+}
+
+void launch_running_update(const float* part_mean, const float* part_var, float* rm, float* rv, const float* decay_dev,
+                           int L, int S, int F, cudaStream_t st) {
+  const int n = L * S * F;
+  running_update_kernel<<<(n + 255) / 256, 256, 0, st>>>(part_mean, part_var, rm, rv, decay_dev, L, S, F);
+  CUDA_CHECK_LAUNCH();
+}

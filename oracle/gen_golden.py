@@ -1,0 +1,191 @@
+"""ORACLE TOOLING -- TEST INFRASTRUCTURE ONLY.
+
+Generates the golden vectors under ``tests/golden/`` by importing the UNMODIFIED reference
+from ``/root/reference`` (a pure-Python/PyTorch program; it runs on CPU in the authoring
+container) and running ``MAMLFewShotClassifier.run_train_iter`` on seeded synthetic episodes.
+
+  python oracle/gen_golden.py            # regenerates every case
+  python oracle/gen_golden.py tiny_pp    # one case
+
+Each ``tests/golden/<case>.npz`` holds: the args (JSON string), the initial ``state_dict``,
+the fp32 reference outputs (loss, accuracy, last-step logits, every outer gradient captured
+just before ``optimizer.step``, the post-Adam ``state_dict`` incl. running statistics, the
+logged ``learning_rate``), and the fp64 reference loss / gradients (noise-floor anchor for
+the tolerance policy).  Inputs are stored only for the tiny cases; the
+full-size ones are regenerated from their seed by ``oracle.maml_oracle.synthetic_batch``.
+
+The reference cannot travel to the GPU box (``/root/reference`` does not exist there), so
+nothing under ``tests/`` reads it at run time: tests read these fixtures.
+"""
+import contextlib
+import io
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from howtotrainyourmamlpytorch_b200.configs import CONFIGS  # noqa: E402
+from howtotrainyourmamlpytorch_b200.utils.parser_utils import args_from_json  # noqa: E402
+from oracle import maml_oracle as O  # noqa: E402
+
+REF = "/root/reference"
+
+_TINY = dict(image_height=20, image_width=20, image_channels=3, cnn_num_filters=16,
+             num_classes_per_set=3, num_samples_per_class=2, num_target_samples=2,
+             number_of_training_steps_per_iter=3, number_of_evaluation_steps_per_iter=3,
+             batch_size=3, total_epochs=100, multi_step_loss_num_epochs=10,
+             dataset_name="mini_imagenet_tiny")
+
+# case name -> (base config, overrides, list of (epoch, iteration-seed) train iterations)
+# Inputs are N(0,1) for every case: Bernoulli "Omniglot-like" images give exact max-pool ties
+# whose resolution is rounding noise, so the reference's own fp32-vs-fp64 gradients differ by
+# 10-100 % there (measured; see DESIGN.md "noise floor") and a parity test would be vacuous.
+KIND = "normal"
+CASES = {
+    "tiny_pp":        ("mini_imagenet_mamlpp_5w1s", dict(_TINY), [(0, 0), (0, 1)]),
+    "tiny_pp_late":   ("mini_imagenet_mamlpp_5w1s", dict(_TINY), [(12, 0)]),
+    "tiny_pp_first":  ("mini_imagenet_mamlpp_5w1s", dict(_TINY, second_order=False), [(3, 0)]),
+    "tiny_maml":      ("omniglot_maml_5w1s", dict(_TINY, image_channels=1, image_height=16, image_width=16,
+                                                  dataset_name="omniglot_tiny"), [(0, 0), (1, 1)]),
+    "tiny_odd":       ("omniglot_mamlpp_5w1s", dict(_TINY, image_channels=1, image_height=28, image_width=28,
+                                                    cnn_num_filters=32, batch_size=2,
+                                                    dataset_name="omniglot_tiny"), [(2, 0)]),
+    "omniglot_mamlpp_5w1s": ("omniglot_mamlpp_5w1s", dict(batch_size=2), [(0, 0)]),
+    "omniglot_maml_5w1s":   ("omniglot_maml_5w1s", dict(batch_size=2), [(0, 0)]),
+    "mini_imagenet_mamlpp_5w1s": ("mini_imagenet_mamlpp_5w1s", dict(batch_size=1), [(0, 0)]),
+    "omniglot_mamlpp_20w5s": ("omniglot_mamlpp_20w5s", dict(batch_size=1), [(0, 0)]),
+}
+
+
+def make_args(case):
+    base, over, iters = CASES[case]
+    d = dict(CONFIGS[base])
+    d.update(over)
+    d["experiment_name"] = case
+    return args_from_json(None, **d), d, iters
+
+
+def build_reference(args, dtype):
+    sys.path.insert(0, REF)
+    import few_shot_learning_system as ref_sys  # noqa: the reference, unmodified
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = ref_sys.MAMLFewShotClassifier(
+            im_shape=(2, args.image_channels, args.image_height, args.image_width),
+            device=torch.device("cpu"), args=args)
+    if dtype == torch.float64:
+        model.double()
+    return model
+
+
+def run_reference_fp32(args, iters, store_inputs):
+    import warnings
+    warnings.filterwarnings("ignore")
+    model = build_reference(args, torch.float32)
+    out = {}
+    for k, v in model.state_dict().items():
+        out["state/" + k] = v.detach().numpy().copy()
+    for it, (epoch, seed_it) in enumerate(iters):
+        batch = O.synthetic_batch(args, iteration=seed_it, kind=KIND)
+        if store_inputs:
+            for nm, t in zip(("xs", "xt", "ys", "yt"), batch):
+                out["it%d/%s" % (it, nm)] = t.numpy().copy()
+        captured = {}
+        orig_step = model.optimizer.step
+
+        def step_and_capture(*a, **kw):
+            for n, p in model.named_parameters():
+                if p.requires_grad:
+                    captured[n] = (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p))
+            return orig_step(*a, **kw)
+
+        model.optimizer.step = step_and_capture
+        with contextlib.redirect_stdout(io.StringIO()):
+            losses, preds = model.run_train_iter(data_batch=batch, epoch=epoch)
+        model.optimizer.step = orig_step
+        out["it%d/loss" % it] = np.float64(float(losses["loss"]))
+        out["it%d/accuracy" % it] = np.float64(float(losses["accuracy"]))
+        out["it%d/learning_rate" % it] = np.float64(float(losses["learning_rate"]))
+        S = args.number_of_training_steps_per_iter
+        out["it%d/msl" % it] = np.array([float(losses["loss_importance_vector_%d" % i]) for i in range(S)])
+        out["it%d/logits" % it] = np.stack(preds).astype(np.float32)
+        for n, g in captured.items():
+            out["it%d/grad/%s" % (it, n)] = g.numpy().copy()
+        for k, v in model.state_dict().items():
+            out["it%d/post/%s" % (it, k)] = v.detach().numpy().copy()
+    return out
+
+
+def run_reference_fp64(args, iters, state32, big):
+    """fp64 reference gradients at the SAME parameters as each fp32 iteration started from
+    (iteration 0 only -- later iterations start from fp32-updated parameters)."""
+    model = build_reference(args, torch.float64)
+    sd = {k: torch.from_numpy(v).double() for k, v in state32.items()}
+    model.load_state_dict(sd)
+    epoch, seed_it = iters[0]
+    batch = O.synthetic_batch(args, iteration=seed_it, kind=KIND)
+    xs, xt, ys, yt = batch
+    model.current_epoch = int(epoch)
+    data = (xs.double(), xt.double(), ys.long(), yt.long())
+    with contextlib.redirect_stdout(io.StringIO()):
+        losses, _ = model.train_forward_prop(data_batch=data, epoch=int(epoch))
+        model.optimizer.zero_grad()
+        losses["loss"].backward()
+    out = {"it0/loss64": np.float64(float(losses["loss"]))}
+    for n, p in model.named_parameters():
+        if p.requires_grad:
+            g = p.grad.detach() if p.grad is not None else torch.zeros_like(p)
+            out["it0/grad64/" + n] = g.numpy().astype(np.float32 if big else np.float64)
+    return out
+
+
+def check_against_oracle(args, blob, iters):
+    """Immediately validate both restatements against what was just generated."""
+    state = {k[len("state/"):]: torch.from_numpy(v) for k, v in blob.items() if k.startswith("state/")}
+    epoch, seed_it = iters[0]
+    batch = O.synthetic_batch(args, iteration=seed_it, kind=KIND)
+    worst = {}
+    for nm, fn in (("autograd", O.autograd_train_iter), ("manual", O.manual_train_iter)):
+        for dt, suffix in ((torch.float32, ""), (torch.float64, "64")):
+            st = {k: v.to(dt) for k, v in state.items()}
+            res = fn(st, args, batch, epoch)
+            ref_loss = float(blob["it0/loss" + suffix])
+            err = abs(float(res["loss"]) - ref_loss) / max(abs(ref_loss), 1e-30)
+            gerr = 0.0
+            for n, g in res["grads"].items():
+                ref = torch.from_numpy(blob["it0/grad%s/%s" % (suffix, n)]).to(torch.float64)
+                denom = float(ref.abs().max())
+                if denom < 1e-6:
+                    continue  # dead conv-bias gradients: pure noise in the reference
+                gerr = max(gerr, float((g.double() - ref).abs().max()) / denom)
+            worst[nm + suffix] = (err, gerr)
+    return worst
+
+
+def main():
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    which = sys.argv[1:] or list(CASES.keys())
+    torch.set_num_threads(8)
+    for case in which:
+        args, argdict, iters = make_args(case)
+        big = case not in ("tiny_pp", "tiny_pp_late", "tiny_pp_first", "tiny_maml", "tiny_odd")
+        blob = run_reference_fp32(args, iters, store_inputs=not big)
+        state32 = {k[len("state/"):]: v for k, v in blob.items() if k.startswith("state/")}
+        blob.update(run_reference_fp64(args, iters, state32, big))
+        blob["args_json"] = np.array(json.dumps(argdict))
+        blob["iters_json"] = np.array(json.dumps(iters))
+        blob["kind"] = np.array(KIND)
+        path = os.path.join(ROOT, "tests", "golden", case + ".npz")
+        np.savez_compressed(path, **blob)
+        worst = check_against_oracle(args, blob, iters)
+        print(case, "%.1f KB" % (os.path.getsize(path) / 1024.0),
+              {k: ("%.1e" % a, "%.1e" % b) for k, (a, b) in worst.items()}, flush=True)
+
+
+if __name__ == "__main__":
+    main()
