@@ -25,6 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import _native
+from . import sharding
 from .inner_loop_optimizers import LSLRGradientDescentLearningRule
 from .meta_neural_network_architectures import VGGReLUNormNetwork
 
@@ -223,8 +224,8 @@ class MAMLFewShotClassifier(nn.Module):
         the recursive form applied to the already-updated lr (a logging quirk, reproduced as is)."""
         base, eta_min, T = float(self.args.meta_learning_rate), float(self.args.min_learning_rate), int(self.args.total_epochs)
         lr = self._cosine_lr(epoch)
-        if epoch == 0:
-            return lr
+        # torch 2.11 CosineAnnealingLR.get_lr: the `_is_initial` shortcut only holds inside the constructor, so
+        # even at epoch 0 the recursive (chainable) form is evaluated on the closed-form lr.
         if (epoch - 1 - T) % (2 * T) == 0:
             return lr + (base - eta_min) * (1 - math.cos(math.pi / T)) / 2
         return (1 + math.cos(math.pi * epoch / T)) / (1 + math.cos(math.pi * (epoch - 1) / T)) * (lr - eta_min) + eta_min
@@ -299,6 +300,9 @@ class MAMLFewShotClassifier(nn.Module):
 
     def _run(self, data_batch, epoch, training_phase, apply_update):
         x_support, x_target, y_support, y_target = data_batch
+        if self.device.type != "cuda":
+            raise _native.NativeLibraryError(
+                "MAMLFewShotClassifier needs a CUDA (sm_100a) device: the hot path has no CPU fallback")
         xs = self._stage("xs", x_support, torch.float32)
         xt = self._stage("xt", x_target, torch.float32)
         ys = self._stage("ys", y_support, torch.float32).long()      # float -> long like the reference
@@ -308,10 +312,10 @@ class MAMLFewShotClassifier(nn.Module):
         N = int(self.args.num_classes_per_set)
         eng = self._ensure_engine(B)
         num_steps, second, mask, weights, w_msl = self._schedule(epoch, training_phase)
-        B_global = B * self.world_size
+        task_offset, B_global = sharding.shard_of(self.rank, self.world_size, B)
         logits = torch.empty(B, n_t, N, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            eng.fwd_bwd(n_tasks=B, task_offset=self.rank * B, tasks_global=B_global, num_steps=num_steps,
+            eng.fwd_bwd(n_tasks=B, task_offset=task_offset, tasks_global=B_global, num_steps=num_steps,
                         second_order=second, training=training_phase, target_mask=mask, target_weight=weights,
                         meta=self._flat, xs=xs, ys=ys, xt=xt, yt=yt, result=self._result, last_logits=logits)
             if self.world_size > 1:
@@ -325,7 +329,7 @@ class MAMLFewShotClassifier(nn.Module):
                               clamp_mask=self._clamp_mask)
                 if self.args.per_step_bn_statistics:
                     S = int(self.args.number_of_training_steps_per_iter)
-                    decay = [0.9 ** (((2 if (mask >> s) & 1 else 1) * B_global) if s < num_steps else 0) for s in range(S)]
+                    decay = sharding.decay_vector(mask, num_steps, S, B_global)
                     eng.running_stats_update(self._result, self._running[0], self._running[1], decay)
         return head, logits, w_msl, B_global, n_t
 

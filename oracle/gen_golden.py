@@ -84,9 +84,18 @@ def build_reference(args, dtype):
 
 
 def run_reference_fp32(args, iters, store_inputs):
+    """fp32 reference run.  The true model gives the losses / logits / post-Adam state.  The outer
+    gradients are captured on a twin model whose ``dataset_name`` lacks 'imagenet' -- the reference clamps
+    ``param.grad`` in place between ``backward`` and ``optimizer.step`` (:332-335), so the twin is the only
+    way to see the UNCLAMPED gradients without editing the reference.  The twin is reloaded from the true
+    model's parameters before every iteration."""
+    import copy
     import warnings
     warnings.filterwarnings("ignore")
     model = build_reference(args, torch.float32)
+    args_nc = copy.copy(args)
+    args_nc.dataset_name = args.dataset_name.replace("imagenet", "imgnet")
+    twin = build_reference(args_nc, torch.float32)
     out = {}
     for k, v in model.state_dict().items():
         out["state/" + k] = v.detach().numpy().copy()
@@ -95,19 +104,22 @@ def run_reference_fp32(args, iters, store_inputs):
         if store_inputs:
             for nm, t in zip(("xs", "xt", "ys", "yt"), batch):
                 out["it%d/%s" % (it, nm)] = t.numpy().copy()
+        twin.load_state_dict(copy.deepcopy(model.state_dict()))
         captured = {}
-        orig_step = model.optimizer.step
+        orig_step = twin.optimizer.step
 
         def step_and_capture(*a, **kw):
-            for n, p in model.named_parameters():
+            for n, p in twin.named_parameters():
                 if p.requires_grad:
                     captured[n] = (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p))
-            return orig_step(*a, **kw)
+            return None          # the twin never updates
 
-        model.optimizer.step = step_and_capture
+        twin.optimizer.step = step_and_capture
+        with contextlib.redirect_stdout(io.StringIO()):
+            twin.run_train_iter(data_batch=batch, epoch=epoch)
+        twin.optimizer.step = orig_step
         with contextlib.redirect_stdout(io.StringIO()):
             losses, preds = model.run_train_iter(data_batch=batch, epoch=epoch)
-        model.optimizer.step = orig_step
         out["it%d/loss" % it] = np.float64(float(losses["loss"]))
         out["it%d/accuracy" % it] = np.float64(float(losses["accuracy"]))
         out["it%d/learning_rate" % it] = np.float64(float(losses["learning_rate"]))

@@ -1,0 +1,127 @@
+"""CPU: host-side logic of the drop-in surface against the golden vectors, and the C-ABI library."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ALL_CASES, ROOT, load_golden
+from oracle import maml_oracle as O
+
+
+def _model(g):
+    from howtotrainyourmamlpytorch_b200 import MAMLFewShotClassifier
+    a = g.args
+    return MAMLFewShotClassifier(im_shape=(2, a.image_channels, a.image_height, a.image_width),
+                                 device=torch.device("cpu"), args=a)
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_state_dict_and_init_match_reference(case):
+    g = load_golden(case)
+    m = _model(g)
+    sd = m.state_dict()
+    ref = g.state()
+    assert list(sd.keys()) == list(ref.keys())
+    for k in ref:
+        assert sd[k].shape == ref[k].shape and torch.equal(sd[k], ref[k]), k
+    assert [n for n, p in m.named_parameters() if p.requires_grad] == list(g.grads(0).keys())
+    st = O.init_state(g.args)
+    for k in ref:
+        assert torch.equal(st[k], ref[k]), k
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_schedules_match_reference(case):
+    g = load_golden(case)
+    m = _model(g)
+    for it, (epoch, _) in enumerate(g.iters):
+        m.current_epoch = int(epoch)
+        w = m.get_per_step_loss_importance_vector().numpy()
+        assert np.array_equal(w.astype(np.float64), g.array("msl", it)), (epoch, w, g.array("msl", it))
+        assert np.array_equal(w, O.msl_weights(g.args, int(epoch)))
+        assert abs(m._logged_lr(int(epoch)) - g.scalar("learning_rate", it)) < 1e-12
+        assert abs(m._cosine_lr(int(epoch)) - O.cosine_lr(g.args, int(epoch))) < 1e-15
+
+
+def test_schedule_masks():
+    g = load_golden("tiny_pp")       # MAML++: MSL for epoch < 10, S = 3
+    m = _model(g)
+    m.current_epoch = 0
+    steps, second, mask, weights, _ = m._schedule(0, True)
+    assert (steps, second, mask) == (3, True, 0b111) and abs(sum(weights) - 1.0) < 1e-6
+    steps, second, mask, weights, _ = m._schedule(12, True)
+    assert (steps, second, mask) == (3, True, 0b100) and weights[2] == 1.0
+    steps, second, mask, weights, _ = m._schedule(0, False)
+    assert (steps, second, mask) == (3, False, 0b100)
+    g = load_golden("tiny_pp_first")
+    m = _model(g)
+    assert m._schedule(3, True)[1] is False
+    sched = O.target_pass_schedule(g.args, 3, True, 3)
+    assert sched == ["msl", "msl", "msl"]
+
+
+def test_no_cpu_fallback():
+    from howtotrainyourmamlpytorch_b200 import _native
+    g = load_golden("tiny_pp")
+    m = _model(g)
+    with pytest.raises(_native.NativeLibraryError):
+        m.run_train_iter(g.batch(0), 0)
+    with pytest.raises(NotImplementedError):
+        m.classifier.forward(torch.zeros(1, 3, 20, 20), num_step=0)
+
+
+def test_lslr_update_rule_is_the_reference_formula():
+    from howtotrainyourmamlpytorch_b200 import LSLRGradientDescentLearningRule
+    rule = LSLRGradientDescentLearningRule(torch.device("cpu"), 5, True, 0.1)
+    w = {"layer_dict.conv0.conv.weight": torch.randn(4, 3, 3, 3), "layer_dict.linear.bias": torch.randn(5)}
+    rule.initialise(w)
+    assert list(rule.names_learning_rates_dict.keys()) == ["layer_dict-conv0-conv-weight", "layer_dict-linear-bias"]
+    assert rule.names_learning_rates_dict["layer_dict-linear-bias"].shape == (6,)
+    gr = {k: torch.randn_like(v) for k, v in w.items()}
+    out = rule.update_params(w, gr, num_step=2)
+    for k in w:
+        assert torch.allclose(out[k], w[k] - 0.1 * gr[k])
+
+
+def test_optimizer_state_dict_roundtrip_format():
+    g = load_golden("tiny_pp")
+    m = _model(g)
+    sd = m.optimizer.state_dict()
+    ref = torch.optim.Adam([torch.nn.Parameter(p.detach().clone()) for p in m.trainable_parameters()], lr=1e-3)
+    assert set(sd["param_groups"][0].keys()) >= {"lr", "betas", "eps", "weight_decay", "amsgrad", "params"}
+    assert sd["param_groups"][0]["params"] == ref.state_dict()["param_groups"][0]["params"]
+    m.optimizer.step_count = 3
+    m._exp_avg.normal_()
+    sd = m.optimizer.state_dict()
+    ref.load_state_dict(sd)            # torch's own Adam accepts it
+    m2 = _model(g)
+    m2.optimizer.load_state_dict(sd)
+    assert m2.optimizer.step_count == 3 and torch.equal(m2._exp_avg, m._exp_avg)
+
+
+def test_checkpoint_save_load(tmp_path):
+    g = load_golden("tiny_maml")
+    m = _model(g)
+    with torch.no_grad():
+        m._flat.add_(0.25)
+    m.save_model(os.path.join(str(tmp_path), "train_model_latest"), {"current_iter": 7, "best_val_acc": np.float64(0.5)})
+    m2 = _model(g)
+    state = m2.load_model(str(tmp_path), "train_model", "latest")
+    assert state["current_iter"] == 7
+    assert torch.equal(m2._flat, m._flat) and m2._views_intact()
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    from howtotrainyourmamlpytorch_b200 import _native
+    ge.build()
+    header = open(os.path.join(ROOT, "include", "maml_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(maml_b200_[a-z_0-9]+)\s*\(", header)))
+    assert declared, "no declarations parsed"
+    lib = _native.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(_native.EXPORTED_SYMBOLS) == declared
+    assert lib.maml_b200_abi_version() == _native.ABI_VERSION
