@@ -19,7 +19,9 @@ EXPORTED_SYMBOLS = [
     "maml_b200_workspace_bytes", "maml_b200_num_segments", "maml_b200_segment", "maml_b200_meta_size",
     "maml_b200_result_size", "maml_b200_meta_batch_fwd_bwd", "maml_b200_adam_step",
     "maml_b200_running_stats_update", "maml_b200_debug_read", "maml_b200_last_launch_count",
+    "maml_b200_profile", "maml_b200_profile_read",
 ]
+PROF_CATS = ["conv_igemm", "conv_first_block", "wgrad", "wgrad_first_block", "bn_act_pool", "head", "param"]
 
 
 class Config(ctypes.Structure):
@@ -78,6 +80,11 @@ def load_library():
     lib.maml_b200_debug_read.restype = i64
     lib.maml_b200_last_launch_count.argtypes = [vp]
     lib.maml_b200_last_launch_count.restype = i64
+    lib.maml_b200_profile.argtypes = [vp, i32]
+    lib.maml_b200_profile.restype = ctypes.c_int
+    lib.maml_b200_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                           ctypes.POINTER(i64), i32]
+    lib.maml_b200_profile_read.restype = ctypes.c_int
     if lib.maml_b200_abi_version() != ABI_VERSION:
         raise NativeLibraryError("libmaml_b200.so ABI version mismatch: rebuild the library")
     _lib = lib
@@ -93,14 +100,15 @@ class Engine(object):
     """Owns one ``maml_b200_handle`` (one static task shape on the current CUDA device)."""
 
     def __init__(self, n_way, k_shot, t_target, channels, height, width, filters, num_stages, inner_steps,
-                 per_step_bn, max_tasks):
+                 per_step_bn, max_tasks, keep_target_passes=False):
         import torch
         if not torch.cuda.is_available():
             raise NativeLibraryError("the MAML engine needs a CUDA (sm_100a) device; there is no CPU fallback")
         self.lib = load_library()
         self.cfg = Config(n_way=n_way, k_shot=k_shot, t_target=t_target, channels=channels, height=height, width=width,
                           filters=filters, num_stages=num_stages, inner_steps=inner_steps,
-                          per_step_bn=int(bool(per_step_bn)), max_tasks=max_tasks, reserved=0)
+                          per_step_bn=int(bool(per_step_bn)), max_tasks=max_tasks,
+                          reserved=1 if keep_target_passes else 0)
         h = ctypes.c_void_p()
         _check(self.lib, self.lib.maml_b200_create(ctypes.byref(self.cfg), ctypes.byref(h)), "maml_b200_create")
         self.h = h
@@ -151,6 +159,16 @@ class Engine(object):
         rc = self.lib.maml_b200_running_stats_update(self.h, result.data_ptr(), running_mean.data_ptr(),
                                                      running_var.data_ptr(), arr, self._stream())
         _check(self.lib, rc, "maml_b200_running_stats_update")
+
+    def profile(self, enable):
+        _check(self.lib, self.lib.maml_b200_profile(self.h, int(bool(enable))), "maml_b200_profile")
+
+    def profile_read(self):
+        """{category: (ms, algorithmic_flops, launches)} since profile(True); synchronises."""
+        n = len(PROF_CATS)
+        ms, fl, ln = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_int64 * n)()
+        _check(self.lib, self.lib.maml_b200_profile_read(self.h, ms, fl, ln, n), "maml_b200_profile_read")
+        return {PROF_CATS[i]: (ms[i], fl[i], ln[i]) for i in range(n)}
 
     def last_launch_count(self):
         return int(self.lib.maml_b200_last_launch_count(self.h))

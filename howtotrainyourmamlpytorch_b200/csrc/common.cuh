@@ -50,6 +50,7 @@ struct ConvArgs {
   const float* zh; long long zh_stride;        // CONV_TAN_STATS: normalised activations of the primal pass
   double* stats; long long stats_stride;       // [task][ncols][2]
   int tasks;
+  double alg_flops;                            // algorithmic FLOPs of this launch (valid pixels only; profiling)
 };
 
 struct Conv0Args {                             // first block: K = 9 * C0 is tiny, direct conv
@@ -61,6 +62,7 @@ struct Conv0Args {                             // first block: K = 9 * C0 is tin
   const float* zh; long long zh_stride;
   double* stats; long long stats_stride;
   int tasks;
+  double alg_flops;
 };
 
 struct WgradArgs {
@@ -71,6 +73,7 @@ struct WgradArgs {
   int rows_per_chunk, nchunks;
   float* partial; long long partial_task_stride; long long chunk_stride;  // [task][chunk][9*kc*ncols + ncols]
   int tasks;
+  double alg_flops;
 };
 
 struct BnGeom { int n, h, w, gw, G, ph, pw, pgw, pG, pb, F; };
@@ -219,3 +222,18 @@ enum { PASS_SUP_FWD = 0, PASS_SUP_BWD = 1, PASS_TGT_FWD = 2, PASS_TGT_BWD = 3, P
 extern long long g_launch_counter;   // bumped by every launcher
 
 #define CUDA_CHECK_LAUNCH() do { g_launch_counter++; } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// optional per-launch profiling with CUDA events on the launching stream (bench.py roofline leg)
+// ---------------------------------------------------------------------------------------------
+enum { PROF_CONV = 0, PROF_CONV0 = 1, PROF_WGRAD = 2, PROF_WGRAD0 = 3, PROF_BN = 4, PROF_HEAD = 5, PROF_PARAM = 6,
+       PROF_CATS = 7 };
+struct Profiler;
+extern Profiler* g_prof;                       // non-null while profiling is on
+void prof_begin(int cat, double flops, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st; bool on;
+  ProfScope(int cat, double flops, cudaStream_t s) : st(s), on(g_prof != nullptr) { if (on) prof_begin(cat, flops, st); }
+  ~ProfScope() { if (on) prof_end(st); }
+};

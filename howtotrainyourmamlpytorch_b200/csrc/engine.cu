@@ -27,6 +27,29 @@ static int fail(const std::string& m) { g_err = m; return 1; }
 
 static inline long long rup(long long x, long long m) { return (x + m - 1) / m * m; }
 
+// ---------------------------------------------------------------------------------------------
+// per-launch profiler (CUDA events on the launching stream); off unless maml_b200_profile(h, 1)
+// ---------------------------------------------------------------------------------------------
+struct Profiler {
+  struct Rec { int cat; double flops; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  cudaEvent_t get() {
+    if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    return pool[used++];
+  }
+  void reset() { recs.clear(); used = 0; }
+  ~Profiler() { for (auto e : pool) cudaEventDestroy(e); }
+};
+Profiler* g_prof = nullptr;
+void prof_begin(int cat, double flops, cudaStream_t st) {
+  Profiler::Rec r; r.cat = cat; r.flops = flops; r.a = g_prof->get(); r.b = g_prof->get();
+  cudaEventRecord(r.a, st);
+  g_prof->recs.push_back(r);
+}
+void prof_end(cudaStream_t st) { cudaEventRecord(g_prof->recs.back().b, st); }
+
 struct PassSet {            // activation buffers of one kind of pass (support: S slots, target / tangent: 1)
   int n = 0, slots = 0;
   float* xg = nullptr; long long xg_stride = 0;                       // block-0 input grid (row 0), per task
@@ -58,6 +81,7 @@ struct maml_b200_handle {
   int pin_slot = 0;
   long long last_launches = 0;
   int last_tasks = 0;
+  Profiler prof;
 };
 
 extern "C" int maml_b200_abi_version(void) { return MAML_B200_ABI_VERSION; }
@@ -179,7 +203,7 @@ static void carve_pass(maml_b200_handle* h, Bump& b, PassSet& ps, int n, int slo
 static void carve(maml_b200_handle* h, Bump& b) {
   const long long T = h->maxT;
   carve_pass(h, b, h->sup, h->n_s, h->S, true, true);
-  carve_pass(h, b, h->tgt, h->n_t, 1, true, true);
+  carve_pass(h, b, h->tgt, h->n_t, (h->cfg.reserved & 1) ? h->S : 1, true, true);   // reserved bit 0: keep every target pass (tests)
   carve_pass(h, b, h->tan, h->n_s, 1, false, true);
   h->theta = b.f((long long)(h->S + 1) * T * h->Ppad);
   h->g = b.f((long long)h->S * T * h->Ppad);
@@ -267,6 +291,11 @@ static BnGeom bn_geom(const maml_b200_handle* h, int l, int n) {
   BnGeom b; b.n = n; b.h = g.h; b.w = g.w; b.gw = g.gw; b.G = g.G; b.ph = g.ph; b.pw = g.pw; b.pgw = g.pgw; b.pG = g.pG; b.pb = g.pb; b.F = h->F;
   return b;
 }
+static double conv_flops(const maml_b200_handle* h, int l, int n, int T, int nsrc) {
+  // algorithmic FLOPs: 2 * valid pixels * C_in * 9 * F per operand pair, per task
+  const LayerGeom& g = h->geo[l];
+  return 2.0 * (double)n * g.h * g.w * (double)g.cin * 9.0 * (double)h->F * (double)nsrc * (double)T;
+}
 static double* stat_at(const maml_b200_handle* h, int kind, int step, int layer) {
   return h->stats + ((long long)kind * MAML_MAX_STEPS + step) * h->st_pass_stride + (long long)layer * h->st_layer_stride;
 }
@@ -298,6 +327,7 @@ static void forward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const
       a.out = ZH(ps, 0, slot); a.out_stride = STRIDE(ps, zh, 0);
       a.rows = ps.n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.c0 = h->C; a.ncols = h->F; a.mode = CONV_FWD_STATS;
       a.stats = stat_at(h, stat_kind, bn_step, 0); a.stats_stride = h->stats_task_stride; a.tasks = T;
+      a.alg_flops = conv_flops(h, 0, ps.n, T, 1);
       launch_conv0(a, st);
     } else {
       ConvArgs a{};
@@ -308,6 +338,7 @@ static void forward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const
       a.out = ZH(ps, l, slot); a.out_stride = STRIDE(ps, zh, l);
       a.rows = ps.n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.ncols = h->F; a.mode = CONV_FWD_STATS;
       a.stats = stat_at(h, stat_kind, bn_step, l); a.stats_stride = h->stats_task_stride; a.tasks = T;
+      a.alg_flops = conv_flops(h, l, ps.n, T, 1);
       launch_conv_rows(a, st);
     }
     BnActArgs b{};
@@ -345,9 +376,11 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
     w.tasks = T;
     if (l == 0) {
       w.A[0] = ps.xg; w.a_stride[0] = ps.xg_stride; w.kc = h->C;
+      w.alg_flops = conv_flops(h, 0, ps.n, T, 1);
       launch_wgrad0(w, st);
     } else {
       w.A[0] = AIN(ps, l, slot); w.a_stride[0] = STRIDE(ps, ain, l); w.kc = h->F;
+      w.alg_flops = conv_flops(h, l, ps.n, T, 1);
       launch_wgrad(w, st);
       ConvArgs a{};
       a.nsrc = 1;
@@ -355,6 +388,7 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
       a.src[0].W = theta + h->pl.w_off[l]; a.src[0].w_stride = h->Ppad; a.src[0].kc = h->F; a.src[0].wt = 1; a.src[0].sign = -1;
       a.out = DP(ps, l - 1, slot); a.out_stride = STRIDE(ps, dp, l - 1);
       a.rows = ps.n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.ncols = h->F; a.mode = CONV_PLAIN; a.tasks = T;
+      a.alg_flops = conv_flops(h, l, ps.n, T, 1);
       launch_conv_rows(a, st);
     }
   }
@@ -375,6 +409,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
       a.rows = sp.n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.c0 = h->C; a.ncols = h->F; a.mode = CONV_TAN_STATS;
       a.zh = ZH(sp, 0, s); a.zh_stride = STRIDE(sp, zh, 0);
       a.stats = stat_at(h, PASS_TAN_FWD, s, 0); a.stats_stride = h->stats_task_stride; a.tasks = T;
+      a.alg_flops = conv_flops(h, 0, sp.n, T, 1);
       launch_conv0(a, st);
     } else {
       ConvArgs a{};
@@ -388,6 +423,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
       a.rows = sp.n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.ncols = h->F; a.mode = CONV_TAN_STATS;
       a.zh = ZH(sp, l, s); a.zh_stride = STRIDE(sp, zh, l);
       a.stats = stat_at(h, PASS_TAN_FWD, s, l); a.stats_stride = h->stats_task_stride; a.tasks = T;
+      a.alg_flops = conv_flops(h, l, sp.n, T, 2);
       launch_conv_rows(a, st);
     }
     BnActTanArgs b{};
@@ -441,12 +477,14 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
     if (l == 0) {
       w.nsrc = 1;
       w.A[0] = sp.xg; w.a_stride[0] = sp.xg_stride; w.kc = h->C;
+      w.alg_flops = conv_flops(h, 0, sp.n, T, 1);
       launch_wgrad0(w, st);
     } else {
       w.nsrc = 2;
       w.A[0] = AIN(sp, l, s); w.a_stride[0] = STRIDE(sp, ain, l); w.kc = h->F;
       w.A[1] = AIN(tn, l, 0); w.a_stride[1] = STRIDE(tn, ain, l);
       w.D[1] = DZ(sp, l, s); w.d_stride[1] = STRIDE(sp, dz, l);
+      w.alg_flops = conv_flops(h, l, sp.n, T, 2);
       launch_wgrad(w, st);
       ConvArgs a{};
       a.nsrc = 2;
@@ -456,6 +494,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
       a.src[1].W = u + h->pl.w_off[l]; a.src[1].w_stride = h->Ppad; a.src[1].kc = h->F; a.src[1].wt = 1; a.src[1].sign = -1;
       a.out = DP(tn, l - 1, 0); a.out_stride = STRIDE(tn, dp, l - 1);
       a.rows = sp.n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.ncols = h->F; a.mode = CONV_PLAIN; a.tasks = T;
+      a.alg_flops = conv_flops(h, l, sp.n, T, 2);
       launch_conv_rows(a, st);
     }
   }
@@ -512,10 +551,11 @@ extern "C" int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200
     launch_param_reduce(h->pl, h->plan_sup.pd, h->sup_partial, PR_UPDATE, th, th_next, h->g + (long long)s * TP, nullptr, meta, s,
                         h->Ppad, T, st);
     if (mask & (1u << s)) {
-      forward_pass(h, h->tgt, 0, th_next, meta, s, PASS_TGT_FWD, T, st);
+      const int ts = (h->cfg.reserved & 1) ? s : 0;
+      forward_pass(h, h->tgt, ts, th_next, meta, s, PASS_TGT_FWD, T, st);
       HeadArgs a{};
       a.mode = HEAD_TARGET_FWD; a.n = h->n_t; a.N = h->N; a.D = h->D;
-      a.f = AIN(h->tgt, h->L, 0); a.f_stride = STRIDE(h->tgt, ain, h->L);
+      a.f = AIN(h->tgt, h->L, ts); a.f_stride = STRIDE(h->tgt, ain, h->L);
       a.Wfc = th_next + h->pl.fcw_off; a.bfc = th_next + h->pl.fcb_off; a.theta_stride = h->Ppad;
       a.y = yt; a.y_stride = h->n_t;
       a.loss_out = h->losses + s; a.loss_stride = MAML_MAX_STEPS;
@@ -531,9 +571,9 @@ extern "C" int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200
         bqa.logits_out = nullptr; bqa.correct_out = nullptr; bqa.loss_out = nullptr;
         bqa.gW = h->tgt_partial + h->plan_tgt.pd.off[2 * h->L]; bqa.gb = h->tgt_partial + h->plan_tgt.pd.off[2 * h->L + 1];
         bqa.g_stride = h->plan_tgt.pd.task_stride;
-        bqa.df = DP(h->tgt, h->L - 1, 0); bqa.df_stride = STRIDE(h->tgt, dp, h->L - 1);
+        bqa.df = DP(h->tgt, h->L - 1, ts); bqa.df_stride = STRIDE(h->tgt, dp, h->L - 1);
         launch_head(bqa, st);
-        backward_pass(h, h->tgt, 0, th_next, meta, s, PASS_TGT_FWD, PASS_TGT_BWD, h->tgt_partial, h->plan_tgt, T, st);
+        backward_pass(h, h->tgt, ts, th_next, meta, s, PASS_TGT_FWD, PASS_TGT_BWD, h->tgt_partial, h->plan_tgt, T, st);
         launch_param_reduce(h->pl, h->plan_tgt.pd, h->tgt_partial, PR_STORE, nullptr, nullptr, h->tgrad + (long long)s * TP, nullptr,
                             meta, s, h->Ppad, T, st);
       }
@@ -602,6 +642,27 @@ extern "C" int maml_b200_running_stats_update(maml_b200_handle* h, const float* 
   return 0;
 }
 
+extern "C" int maml_b200_profile(maml_b200_handle* h, int32_t enable) {
+  if (!h) return fail("null argument");
+  if (enable) { h->prof.reset(); g_prof = &h->prof; } else { g_prof = nullptr; }
+  return 0;
+}
+
+extern "C" int maml_b200_profile_read(maml_b200_handle* h, double* ms_by_cat, double* flops_by_cat, int64_t* launches_by_cat,
+                                      int32_t ncat) {
+  if (!h || !ms_by_cat || !flops_by_cat || !launches_by_cat) return fail("null argument");
+  CK(cudaDeviceSynchronize());
+  for (int c = 0; c < ncat; ++c) { ms_by_cat[c] = 0; flops_by_cat[c] = 0; launches_by_cat[c] = 0; }
+  for (auto& r : h->prof.recs) {
+    if (r.cat < 0 || r.cat >= ncat) continue;
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_by_cat[r.cat] += ms; flops_by_cat[r.cat] += r.flops; launches_by_cat[r.cat] += 1;
+  }
+  h->prof.reset();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // debug taps (tests): raw copy of one internal buffer
 // ---------------------------------------------------------------------------------------------
@@ -636,7 +697,7 @@ extern "C" int64_t maml_b200_debug_read(maml_b200_handle* h, const char* name, i
   };
   bool ok = false;
   if (nm.rfind("sup_", 0) == 0) ok = pass_buf(h->sup, nm.substr(4), step);
-  else if (nm.rfind("tgt_", 0) == 0) ok = pass_buf(h->tgt, nm.substr(4), 0);
+  else if (nm.rfind("tgt_", 0) == 0) ok = pass_buf(h->tgt, nm.substr(4), (h->cfg.reserved & 1) ? step : 0);
   else if (nm.rfind("tan_", 0) == 0) ok = pass_buf(h->tan, nm.substr(4), 0);
   else if (nm == "theta") { if (step >= 0 && step <= h->S) { src = h->theta + (long long)step * TP + (long long)task * h->Ppad; count = h->pl.P; ok = true; } }
   else if (nm == "g") { if (step >= 0 && step < h->S) { src = h->g + (long long)step * TP + (long long)task * h->Ppad; count = h->pl.P; ok = true; } }

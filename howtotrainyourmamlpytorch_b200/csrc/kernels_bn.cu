@@ -99,6 +99,7 @@ static inline dim3 bn_grid(const BnGeom& g, int tasks, int* block) {
 }
 
 void launch_bnact(const BnActArgs& a, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
   bnact_kernel<<<grid, block, 0, st>>>(a);
   CUDA_CHECK_LAUNCH();
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(256) bnbwd_reduce_kernel(BnBwdArgs a) {
 }
 
 void launch_bnbwd_reduce(const BnBwdArgs& a, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
   if (grid.x > 148) grid.x = 148;
   bnbwd_reduce_kernel<<<grid, block, 0, st>>>(a);
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(256) bnbwd_apply_kernel(BnBwdArgs a) {
 }
 
 void launch_bnbwd_apply(const BnBwdArgs& a, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
   bnbwd_apply_kernel<<<grid, block, 0, st>>>(a);
   CUDA_CHECK_LAUNCH();
@@ -311,6 +314,7 @@ __global__ void __launch_bounds__(256) bnact_tan_kernel(BnActTanArgs a) {
 }
 
 void launch_bnact_tan(const BnActTanArgs& a, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
   bnact_tan_kernel<<<grid, block, 0, st>>>(a);
   CUDA_CHECK_LAUNCH();
@@ -359,6 +363,7 @@ __global__ void __launch_bounds__(256) bnbwd_tan_reduce_kernel(BnBwdTanArgs a) {
 }
 
 void launch_bnbwd_tan_reduce(const BnBwdTanArgs& a, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
   if (grid.x > 148) grid.x = 148;
   bnbwd_tan_reduce_kernel<<<grid, block, 0, st>>>(a);
@@ -424,6 +429,7 @@ __global__ void __launch_bounds__(256) bnbwd_tan_apply_kernel(BnBwdTanArgs a) {
 }
 
 void launch_bnbwd_tan_apply(const BnBwdTanArgs& a, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
   bnbwd_tan_apply_kernel<<<grid, block, 0, st>>>(a);
   CUDA_CHECK_LAUNCH();

@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(256) conv_rows_kernel(ConvArgs a) {
 }
 
 void launch_conv_rows(const ConvArgs& a, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_CONV, a.alg_flops, st);
   dim3 grid((a.rows + 63) / 64, a.tasks);
   switch (a.ncols / 16) {
     case 1: conv_rows_kernel<1><<<grid, 256, 0, st>>>(a); break;
@@ -250,6 +251,7 @@ __global__ void __launch_bounds__(256) conv0_kernel(Conv0Args a) {
 }
 
 void launch_conv0(const Conv0Args& a, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_CONV0, a.alg_flops, st);
   dim3 grid((a.rows + 63) / 64, a.tasks);
   const size_t smem = (size_t)(9 * a.c0 * a.ncols + (64 + 2 * (a.gw + 1)) * a.c0) * sizeof(float);
   switch (a.ncols / 16) {
@@ -352,6 +354,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
 }
 
 void launch_wgrad(const WgradArgs& a, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_WGRAD, a.alg_flops, st);
   dim3 grid(a.nchunks * 9, a.tasks);
   const int cn = a.kc / 16, fn = a.ncols / 16;
 #define WG_CASE(C, F_) if (cn == C && fn == F_) { wgrad_kernel<C, F_><<<grid, 256, 0, st>>>(a); CUDA_CHECK_LAUNCH(); return; }
@@ -404,6 +407,7 @@ __global__ void __launch_bounds__(256) wgrad0_kernel(WgradArgs a) {
 }
 
 void launch_wgrad0(const WgradArgs& a, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_WGRAD0, a.alg_flops, st);
   dim3 grid(a.nchunks, a.tasks);
   wgrad0_kernel<<<grid, 256, 0, st>>>(a);
   CUDA_CHECK_LAUNCH();
@@ -429,6 +433,7 @@ __global__ void prep_x_kernel(const float* __restrict__ x, float* __restrict__ x
 
 void launch_prep_x(const float* x, float* xg, long long xg_task_stride, int tasks, int n, int C, int H, int W,
                    cudaStream_t st) {
+  ProfScope prof_scope__(PROF_PARAM, 0.0, st);
   const long long total = (long long)n * H * W;
   dim3 grid((unsigned)((total + 255) / 256), tasks);
   prep_x_kernel<<<grid, 256, 0, st>>>(x, xg, xg_task_stride, n, C, H, W);

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
 }
 
 void launch_head(const HeadArgs& a, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_HEAD, 0.0, st);
   const size_t smem = (size_t)5 * a.n * a.N * sizeof(float);
   head_kernel<<<a.tasks, 256, smem, st>>>(a);
   CUDA_CHECK_LAUNCH();

@@ -49,6 +49,7 @@ __global__ void import_theta_kernel(ParamLayout pl, const float* __restrict__ me
 
 void launch_import_theta(const ParamLayout& pl, const float* meta, float* theta0, long long stride, int tasks,
                          cudaStream_t st) {
+  ProfScope prof_scope__(PROF_PARAM, 0.0, st);
   import_theta_kernel<<<(unsigned)((pl.P + 255) / 256), 256, 0, st>>>(pl, meta, theta0, stride, tasks);
   CUDA_CHECK_LAUNCH();
 }
@@ -90,6 +91,7 @@ __global__ void param_reduce_kernel(ParamLayout pl, PartialDesc pd, const float*
 void launch_param_reduce(const ParamLayout& pl, const PartialDesc& pd, const float* partial, int mode,
                          const float* theta_in, float* theta_out, float* g_out, float* tbar, const float* meta, int step,
                          long long task_stride, int tasks, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_PARAM, 0.0, st);
   dim3 grid((unsigned)((pl.P + 255) / 256), tasks);
   param_reduce_kernel<<<grid, 256, 0, st>>>(pl, pd, partial, mode, theta_in, theta_out, g_out, tbar, meta, step, task_stride);
   CUDA_CHECK_LAUNCH();
@@ -124,6 +126,7 @@ __global__ void __launch_bounds__(256) dots_u_kernel(ParamLayout pl, float* __re
 
 void launch_dots_u(const ParamLayout& pl, float* tbar, const float* tgrad, const float* g, float* u, float* abar,
                    const float* meta, int step, long long task_stride, int tasks, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_PARAM, 0.0, st);
   dim3 grid(pl.nseg_inner, tasks);
   dots_u_kernel<<<grid, 256, 0, st>>>(pl, tbar, tgrad, g, u, abar, meta, step, task_stride);
   CUDA_CHECK_LAUNCH();
@@ -249,6 +252,7 @@ __global__ void export_kernel(ExportArgs a) {
 }
 
 void launch_export(const ExportArgs& a, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_PARAM, 0.0, st);
   const long long total = a.pl.meta_size + 2 + (a.pl.per_step_bn ? 2LL * a.pl.L * a.pl.S * a.pl.F : 0);
   export_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
   CUDA_CHECK_LAUNCH();
@@ -282,6 +286,7 @@ __global__ void adam_kernel(float* __restrict__ meta, const float* __restrict__ 
 
 void launch_adam(float* meta, const float* grad, float* m, float* v, long long n, float lr, float bc1, float bc2,
                  const long long* seg_end_host, int nseg, unsigned trainable_mask, unsigned clamp_mask, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_PARAM, 0.0, st);
   SegEnds se;
   se.n = nseg - 1;
   for (int k = 0; k < nseg - 1 && k < 32; ++k) se.e[k] = seg_end_host[k];
@@ -301,6 +306,7 @@ __global__ void running_update_kernel(const float* __restrict__ pm, const float*
 
 void launch_running_update(const float* part_mean, const float* part_var, float* rm, float* rv, const float* decay_dev,
                            int L, int S, int F, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_PARAM, 0.0, st);
   const int n = L * S * F;
   running_update_kernel<<<(n + 255) / 256, 256, 0, st>>>(part_mean, part_var, rm, rv, decay_dev, L, S, F);
   CUDA_CHECK_LAUNCH();

