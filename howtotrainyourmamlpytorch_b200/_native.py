@@ -100,7 +100,7 @@ class Engine(object):
     """Owns one ``maml_b200_handle`` (one static task shape on the current CUDA device)."""
 
     def __init__(self, n_way, k_shot, t_target, channels, height, width, filters, num_stages, inner_steps,
-                 per_step_bn, max_tasks, keep_target_passes=False):
+                 per_step_bn, max_tasks, keep_target_passes=False, force_fp32_convs=False):
         import torch
         if not torch.cuda.is_available():
             raise NativeLibraryError("the MAML engine needs a CUDA (sm_100a) device; there is no CPU fallback")
@@ -108,7 +108,7 @@ class Engine(object):
         self.cfg = Config(n_way=n_way, k_shot=k_shot, t_target=t_target, channels=channels, height=height, width=width,
                           filters=filters, num_stages=num_stages, inner_steps=inner_steps,
                           per_step_bn=int(bool(per_step_bn)), max_tasks=max_tasks,
-                          reserved=1 if keep_target_passes else 0)
+                          reserved=(1 if keep_target_passes else 0) | (2 if force_fp32_convs else 0))
         h = ctypes.c_void_p()
         _check(self.lib, self.lib.maml_b200_create(ctypes.byref(self.cfg), ctypes.byref(h)), "maml_b200_create")
         self.h = h

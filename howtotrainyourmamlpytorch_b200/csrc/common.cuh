@@ -83,6 +83,7 @@ struct BnActArgs {                // forward: z -> zh (in place), pooled activat
   const double* stats; long long stats_stride;     // (sum z, sum z^2)
   const float* gamma; const float* beta;
   float* p; long long p_stride;
+  float* p_hi; float* p_lo;                         // nullable: TF32 hi/lo planes of p (same stride)
   BnGeom g; int tasks;
 };
 
@@ -93,6 +94,7 @@ struct BnActTanArgs {             // tangent forward: zdot -> zhdot (in place), 
   const double* stats_tan; long long stats_tan_stride;   // (sum zdot, sum zh*zdot)
   const float* gamma; const float* beta;
   float* pdot; long long pdot_stride;
+  float* pdot_hi; float* pdot_lo;
   BnGeom g; int tasks;
 };
 
@@ -103,6 +105,7 @@ struct BnBwdArgs {                // backward reduce / apply (primal)
   double* stats_bwd; long long stats_bwd_stride;          // (S1 = sum dy, S2 = sum dy*zh)
   const float* gamma; const float* beta;
   float* dz; long long dz_stride;
+  float* dz_hi; float* dz_lo;
   BnGeom g; int tasks;
 };
 
@@ -118,6 +121,7 @@ struct BnBwdTanArgs {             // backward reduce / apply (tangent)
   double* stats_tbwd; long long stats_tbwd_stride;        // (T1, T2)
   const float* gamma; const float* beta;
   float* dzdot; long long dzdot_stride;
+  float* dzdot_hi; float* dzdot_lo;
   BnGeom g; int tasks;
 };
 

@@ -18,6 +18,7 @@
 
 #include "../../include/maml_b200.h"
 #include "common.cuh"
+#include "tc_common.cuh"
 
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return 1; }
@@ -57,6 +58,12 @@ struct PassSet {            // activation buffers of one kind of pass (support: 
   float* zh[MAML_MAX_LAYERS] = {}; long long zh_sz[MAML_MAX_LAYERS] = {};
   float* dz[MAML_MAX_LAYERS] = {}; long long dz_sz[MAML_MAX_LAYERS] = {};
   float* dp[MAML_MAX_LAYERS] = {}; long long dp_sz[MAML_MAX_LAYERS] = {};
+  // conv inputs of blocks l >= 1 (ain) and output gradients (dz) are stored as three planes: fp32, TF32-hi, TF32-lo
+  // (the hi/lo planes feed the tcgen05 kernels through TMA; same geometry incl. guards)
+  float* ain_base[MAML_MAX_LAYERS + 1] = {}; long long ain_plane[MAML_MAX_LAYERS + 1] = {};
+  float* dz_base[MAML_MAX_LAYERS] = {}; long long dz_plane[MAML_MAX_LAYERS] = {};
+  CUtensorMap ain_map[MAML_MAX_LAYERS][2];   // [layer][hi/lo]
+  CUtensorMap dz_map[MAML_MAX_LAYERS][2];
 };
 
 struct ChunkPlan { int rows_per_chunk[MAML_MAX_LAYERS]; int nchunks[MAML_MAX_LAYERS]; PartialDesc pd; long long size; };
@@ -82,6 +89,11 @@ struct maml_b200_handle {
   long long last_launches = 0;
   int last_tasks = 0;
   Profiler prof;
+  // tensor-core path (blocks l >= 1 when F % 32 == 0)
+  bool use_tc = false;
+  float *pack_theta = nullptr, *pack_u = nullptr;       // [4 planes][steps][T][(L-1)*9*F*F]
+  long long pack_theta_plane = 0, pack_u_plane = 0, pack_task = 0;
+  CUtensorMap theta_map[4], u_map[4];                   // planes: W hi, W lo, WT hi, WT lo
 };
 
 extern "C" int maml_b200_abi_version(void) { return MAML_B200_ABI_VERSION; }
@@ -167,6 +179,52 @@ struct Bump {
   double* d(long long count) { double* p = base ? (double*)(base + off) : nullptr; off += rup(count * 8, 256); return p; }
 };
 
+// 2-D fp32 tensor map [rows][cols] with a [box_rows][32] box, SWIZZLE_128B, zero fill out of bounds
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+static int make_map(CUtensorMap* m, const float* base, long long rows, int cols, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cols * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return 0;
+}
+static int make_pass_maps(maml_b200_handle* h, PassSet& ps, bool has_dz) {
+  for (int l = 1; l < h->L; ++l) {
+    for (int pl = 0; pl < 2; ++pl) {
+      if (make_map(&ps.ain_map[l][pl], ps.ain_base[l] + (pl + 1) * ps.ain_plane[l], ps.ain_plane[l] / h->F, h->F, 128)) return 1;
+      if (has_dz && make_map(&ps.dz_map[l][pl], ps.dz_base[l] + (pl + 1) * ps.dz_plane[l], ps.dz_plane[l] / h->F, h->F, 128)) return 1;
+    }
+  }
+  return 0;
+}
+static int make_all_maps(maml_b200_handle* h) {
+  if (!h->use_tc) return 0;
+  if (make_pass_maps(h, h->sup, true) || make_pass_maps(h, h->tgt, true) || make_pass_maps(h, h->tan, true)) return 1;
+  for (int pl = 0; pl < 4; ++pl) {
+    if (make_map(&h->theta_map[pl], h->pack_theta + pl * h->pack_theta_plane, h->pack_theta_plane / h->F, h->F, h->F)) return 1;
+    if (make_map(&h->u_map[pl], h->pack_u + pl * h->pack_u_plane, h->pack_u_plane / h->F, h->F, h->F)) return 1;
+  }
+  if (tc_conv_prepare()) return fail("cudaFuncSetAttribute(max dynamic shared memory) failed for the tcgen05 conv kernel");
+  return 0;
+}
+
 static void carve_pass(maml_b200_handle* h, Bump& b, PassSet& ps, int n, int slots, bool need_x, bool need_bwd) {
   ps.n = n; ps.slots = slots;
   const long long T = h->maxT;
@@ -180,8 +238,10 @@ static void carve_pass(maml_b200_handle* h, Bump& b, PassSet& ps, int n, int slo
   for (int l = 1; l < h->L; ++l) {
     const long long gr = (long long)h->geo[l].guard * h->F;
     const long long body = (long long)n * h->geo[l].G * h->F;
-    ps.ain_sz[l] = rup(body + 2 * gr, 64);
-    float* p = b.f(ps.ain_sz[l] * T * slots);
+    ps.ain_sz[l] = rup(body + 2 * gr, 192);
+    ps.ain_plane[l] = ps.ain_sz[l] * T * slots;
+    float* p = b.f(ps.ain_plane[l] * 3);
+    ps.ain_base[l] = p;
     ps.ain[l] = p ? p + gr : nullptr;
   }
   ps.ain_sz[h->L] = rup((long long)n * h->D, 64);
@@ -191,8 +251,10 @@ static void carve_pass(maml_b200_handle* h, Bump& b, PassSet& ps, int n, int slo
     ps.zh[l] = b.f(ps.zh_sz[l] * T * slots);
     if (need_bwd) {
       const long long gr = (long long)h->geo[l].guard * h->F;
-      ps.dz_sz[l] = rup((long long)n * h->geo[l].G * h->F + 2 * gr, 64);
-      float* p = b.f(ps.dz_sz[l] * T * slots);
+      ps.dz_sz[l] = rup((long long)n * h->geo[l].G * h->F + 2 * gr, 192);
+      ps.dz_plane[l] = ps.dz_sz[l] * T * slots;
+      float* p = b.f(ps.dz_plane[l] * 3);
+      ps.dz_base[l] = p;
       ps.dz[l] = p ? p + gr : nullptr;
       ps.dp_sz[l] = rup((long long)n * h->geo[l].pG * h->F, 64);
       ps.dp[l] = b.f(ps.dp_sz[l] * T * slots);
@@ -210,6 +272,13 @@ static void carve(maml_b200_handle* h, Bump& b) {
   h->tgrad = b.f((long long)h->S * T * h->Ppad);
   h->tbar = b.f(T * h->Ppad);
   h->u = b.f(T * h->Ppad);
+  h->pack_task = (long long)(h->L - 1) * 9 * h->F * h->F;
+  h->pack_theta_plane = (long long)(h->S + 1) * T * h->pack_task;
+  h->pack_u_plane = T * h->pack_task;
+  if (h->use_tc && h->L > 1) {
+    h->pack_theta = b.f(4 * h->pack_theta_plane);
+    h->pack_u = b.f(4 * h->pack_u_plane);
+  }
   h->sup_partial = b.f(T * h->plan_sup.size);
   h->tgt_partial = b.f(T * h->plan_tgt.size);
   h->st_layer_stride = (long long)h->F * 2;
@@ -245,6 +314,8 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   h->C = cfg->channels; h->H = cfg->height; h->W = cfg->width; h->n_s = n_s; h->n_t = n_t; h->maxT = cfg->max_tasks;
   build_geometry(h);
   build_layout(h);
+  // tensor-core (tcgen05 / TMA, 3xTF32) convolutions for blocks l >= 1; reserved bit 1 forces the fp32 FFMA kernels (tests)
+  h->use_tc = (h->F % 32 == 0) && (h->L > 1) && !(cfg->reserved & 2);
   plan_chunks(h, h->n_s, &h->plan_sup);
   plan_chunks(h, h->n_t, &h->plan_tgt);
   Bump sz{nullptr, 0};
@@ -256,6 +327,7 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   if (e != cudaSuccess) { cudaFree(h->ws); delete h; return fail(std::string("cudaMemset: ") + cudaGetErrorString(e)); }
   Bump as{h->ws, 0};
   carve(h, as);
+  if (make_all_maps(h)) { cudaFree(h->ws); delete h; return 1; }
   e = cudaMallocHost((void**)&h->pinned, 16 * 32 * sizeof(float));
   if (e != cudaSuccess) { cudaFree(h->ws); delete h; return fail(std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
   *out = h;
@@ -314,9 +386,62 @@ static float* slot_ptr(float* base, long long sz, int slots, int slot) { return 
 #define DP(ps, l, slot) slot_ptr((ps).dp[l], (ps).dp_sz[l], (ps).slots, slot)
 #define STRIDE(ps, what, l) ((ps).what##_sz[l] * (ps).slots)
 
+#define AIN_HI(ps, l, slot) (AIN(ps, l, slot) + (ps).ain_plane[l])
+#define AIN_LO(ps, l, slot) (AIN(ps, l, slot) + 2 * (ps).ain_plane[l])
+#define DZ_HI(ps, l, slot) (DZ(ps, l, slot) + (ps).dz_plane[l])
+#define DZ_LO(ps, l, slot) (DZ(ps, l, slot) + 2 * (ps).dz_plane[l])
+
+// one operand pair of a tensor-core conv launch
+struct TcOp {
+  const CUtensorMap* a_maps;   // [hi, lo]
+  int a_row_base, a_task_rows, sign;
+  const CUtensorMap* b_maps;   // 4 planes: W hi, W lo, WT hi, WT lo
+  int b_pair;                  // 0: W planes (dgrad), 2: WT planes (conv)
+  int b_row_base, b_task_rows;
+};
+
+static int a_row_base_of(const maml_b200_handle* h, long long sz, int l, int slot) {
+  return (int)(slot * (sz / h->F) + h->geo[l].guard);
+}
+static TcOp tc_op_ain(const maml_b200_handle* h, const PassSet& ps, int l, int slot, const CUtensorMap* bmaps, int b_step, int sign, int b_pair) {
+  TcOp o;
+  o.a_maps = ps.ain_map[l]; o.a_row_base = a_row_base_of(h, ps.ain_sz[l], l, slot);
+  o.a_task_rows = (int)(ps.ain_sz[l] * ps.slots / h->F); o.sign = sign;
+  o.b_maps = bmaps; o.b_pair = b_pair;
+  o.b_row_base = (int)(((long long)b_step * h->maxT * (h->L - 1) + (l - 1)) * 9 * h->F);
+  o.b_task_rows = (h->L - 1) * 9 * h->F;
+  return o;
+}
+static TcOp tc_op_dz(const maml_b200_handle* h, const PassSet& ps, int l, int slot, const CUtensorMap* bmaps, int b_step, int sign, int b_pair) {
+  TcOp o = tc_op_ain(h, ps, l, slot, bmaps, b_step, sign, b_pair);
+  o.a_maps = ps.dz_map[l]; o.a_row_base = a_row_base_of(h, ps.dz_sz[l], l, slot);
+  o.a_task_rows = (int)(ps.dz_sz[l] * ps.slots / h->F);
+  return o;
+}
+
+static void tc_conv(maml_b200_handle* h, int l, int n, int nsrc, const TcOp* ops, const float* bias, long long bias_stride,
+                    float* out, long long out_stride, int mode, const float* zh, long long zh_stride, double* stats, int T,
+                    cudaStream_t st) {
+  const LayerGeom& g = h->geo[l];
+  TcMaps maps;
+  TcConvArgs a{};
+  a.nsrc = nsrc; a.kc = h->F; a.rows = n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.ncols = h->F; a.mode = mode; a.tasks = T;
+  for (int s = 0; s < nsrc; ++s) {
+    maps.m[s * 4 + 0] = ops[s].a_maps[0]; maps.m[s * 4 + 1] = ops[s].a_maps[1];
+    maps.m[s * 4 + 2] = ops[s].b_maps[ops[s].b_pair]; maps.m[s * 4 + 3] = ops[s].b_maps[ops[s].b_pair + 1];
+    a.a_row_base[s] = ops[s].a_row_base; a.a_task_rows[s] = ops[s].a_task_rows; a.sign[s] = ops[s].sign;
+    a.b_row_base[s] = ops[s].b_row_base; a.b_task_rows[s] = ops[s].b_task_rows;
+  }
+  if (nsrc == 1) for (int k = 4; k < 8; ++k) maps.m[k] = maps.m[k - 4];
+  a.bias = bias; a.bias_stride = bias_stride; a.out = out; a.out_stride = out_stride;
+  a.zh = zh; a.zh_stride = zh_stride; a.stats = stats; a.stats_stride = h->stats_task_stride;
+  a.alg_flops = conv_flops(h, l, n, T, nsrc);
+  launch_conv_tc(maps, a, st);
+}
+
 // primal forward of one pass: conv -> stats -> BN/leaky/pool for every block
-static void forward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const float* theta, const float* meta, int bn_step,
-                         int stat_kind, int T, cudaStream_t st) {
+static void forward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const float* theta, int th_step, const float* meta,
+                         int bn_step, int stat_kind, int T, cudaStream_t st) {
   for (int l = 0; l < h->L; ++l) {
     const LayerGeom& g = h->geo[l];
     if (l == 0) {
@@ -329,6 +454,10 @@ static void forward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const
       a.stats = stat_at(h, stat_kind, bn_step, 0); a.stats_stride = h->stats_task_stride; a.tasks = T;
       a.alg_flops = conv_flops(h, 0, ps.n, T, 1);
       launch_conv0(a, st);
+    } else if (h->use_tc) {
+      TcOp op = tc_op_ain(h, ps, l, slot, h->theta_map, th_step, +1, 2);
+      tc_conv(h, l, ps.n, 1, &op, theta + h->pl.b_off[l], h->Ppad, ZH(ps, l, slot), STRIDE(ps, zh, l), CONV_FWD_STATS, nullptr, 0,
+              stat_at(h, stat_kind, bn_step, l), T, st);
     } else {
       ConvArgs a{};
       a.nsrc = 1;
@@ -346,14 +475,15 @@ static void forward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const
     b.stats = stat_at(h, stat_kind, bn_step, l); b.stats_stride = h->stats_task_stride;
     b.gamma = gamma_at(h, meta, l, bn_step); b.beta = beta_at(h, meta, l, bn_step);
     b.p = AIN(ps, l + 1, slot); b.p_stride = STRIDE(ps, ain, l + 1);
+    if (h->use_tc && l + 1 < h->L) { b.p_hi = AIN_HI(ps, l + 1, slot); b.p_lo = AIN_LO(ps, l + 1, slot); }
     b.g = bn_geom(h, l, ps.n); b.tasks = T;
     launch_bnact(b, st);
   }
 }
 
 // primal backward of one pass (dp[L-1] already written by the head): BN backward, wgrad, dgrad
-static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const float* theta, const float* meta, int bn_step,
-                          int kind_fwd, int kind_bwd, float* partial, const ChunkPlan& cp, int T, cudaStream_t st) {
+static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const float* theta, int th_step, const float* meta,
+                          int bn_step, int kind_fwd, int kind_bwd, float* partial, const ChunkPlan& cp, int T, cudaStream_t st) {
   for (int l = h->L - 1; l >= 0; --l) {
     const LayerGeom& g = h->geo[l];
     BnBwdArgs b{};
@@ -363,6 +493,7 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
     b.stats_bwd = stat_at(h, kind_bwd, bn_step, l); b.stats_bwd_stride = h->stats_task_stride;
     b.gamma = gamma_at(h, meta, l, bn_step); b.beta = beta_at(h, meta, l, bn_step);
     b.dz = DZ(ps, l, slot); b.dz_stride = STRIDE(ps, dz, l);
+    if (h->use_tc && l >= 1) { b.dz_hi = DZ_HI(ps, l, slot); b.dz_lo = DZ_LO(ps, l, slot); }
     b.g = bn_geom(h, l, ps.n); b.tasks = T;
     launch_bnbwd_reduce(b, st);
     launch_bnbwd_apply(b, st);
@@ -382,14 +513,19 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
       w.A[0] = AIN(ps, l, slot); w.a_stride[0] = STRIDE(ps, ain, l); w.kc = h->F;
       w.alg_flops = conv_flops(h, l, ps.n, T, 1);
       launch_wgrad(w, st);
-      ConvArgs a{};
-      a.nsrc = 1;
-      a.src[0].A = DZ(ps, l, slot); a.src[0].a_stride = STRIDE(ps, dz, l);
-      a.src[0].W = theta + h->pl.w_off[l]; a.src[0].w_stride = h->Ppad; a.src[0].kc = h->F; a.src[0].wt = 1; a.src[0].sign = -1;
-      a.out = DP(ps, l - 1, slot); a.out_stride = STRIDE(ps, dp, l - 1);
-      a.rows = ps.n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.ncols = h->F; a.mode = CONV_PLAIN; a.tasks = T;
-      a.alg_flops = conv_flops(h, l, ps.n, T, 1);
-      launch_conv_rows(a, st);
+      if (h->use_tc) {
+        TcOp op = tc_op_dz(h, ps, l, slot, h->theta_map, th_step, -1, 0);
+        tc_conv(h, l, ps.n, 1, &op, nullptr, 0, DP(ps, l - 1, slot), STRIDE(ps, dp, l - 1), CONV_PLAIN, nullptr, 0, nullptr, T, st);
+      } else {
+        ConvArgs a{};
+        a.nsrc = 1;
+        a.src[0].A = DZ(ps, l, slot); a.src[0].a_stride = STRIDE(ps, dz, l);
+        a.src[0].W = theta + h->pl.w_off[l]; a.src[0].w_stride = h->Ppad; a.src[0].kc = h->F; a.src[0].wt = 1; a.src[0].sign = -1;
+        a.out = DP(ps, l - 1, slot); a.out_stride = STRIDE(ps, dp, l - 1);
+        a.rows = ps.n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.ncols = h->F; a.mode = CONV_PLAIN; a.tasks = T;
+        a.alg_flops = conv_flops(h, l, ps.n, T, 1);
+        launch_conv_rows(a, st);
+      }
     }
   }
 }
@@ -411,6 +547,12 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
       a.stats = stat_at(h, PASS_TAN_FWD, s, 0); a.stats_stride = h->stats_task_stride; a.tasks = T;
       a.alg_flops = conv_flops(h, 0, sp.n, T, 1);
       launch_conv0(a, st);
+    } else if (h->use_tc) {
+      TcOp ops[2];
+      ops[0] = tc_op_ain(h, sp, l, s, h->u_map, 0, +1, 2);          // conv(a_in, u_W)
+      ops[1] = tc_op_ain(h, tn, l, 0, h->theta_map, s, +1, 2);      // conv(a_in_dot, W)
+      tc_conv(h, l, sp.n, 2, ops, u + h->pl.b_off[l], h->Ppad, ZH(tn, l, 0), STRIDE(tn, zh, l), CONV_TAN_STATS, ZH(sp, l, s),
+              STRIDE(sp, zh, l), stat_at(h, PASS_TAN_FWD, s, l), T, st);
     } else {
       ConvArgs a{};
       a.nsrc = 2;
@@ -433,6 +575,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
     b.stats_tan = stat_at(h, PASS_TAN_FWD, s, l); b.stats_tan_stride = h->stats_task_stride;
     b.gamma = gamma_at(h, meta, l, s); b.beta = beta_at(h, meta, l, s);
     b.pdot = AIN(tn, l + 1, 0); b.pdot_stride = STRIDE(tn, ain, l + 1);
+    if (h->use_tc && l + 1 < h->L) { b.pdot_hi = AIN_HI(tn, l + 1, 0); b.pdot_lo = AIN_LO(tn, l + 1, 0); }
     b.g = bn_geom(h, l, sp.n); b.tasks = T;
     launch_bnact_tan(b, st);
   }
@@ -464,6 +607,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
     b.stats_tbwd = stat_at(h, PASS_TAN_BWD, s, l); b.stats_tbwd_stride = h->stats_task_stride;
     b.gamma = gamma_at(h, meta, l, s); b.beta = beta_at(h, meta, l, s);
     b.dzdot = DZ(tn, l, 0); b.dzdot_stride = STRIDE(tn, dz, l);
+    if (h->use_tc && l >= 1) { b.dzdot_hi = DZ_HI(tn, l, 0); b.dzdot_lo = DZ_LO(tn, l, 0); }
     b.g = bn_geom(h, l, sp.n); b.tasks = T;
     launch_bnbwd_tan_reduce(b, st);
     launch_bnbwd_tan_apply(b, st);
@@ -486,18 +630,36 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
       w.D[1] = DZ(sp, l, s); w.d_stride[1] = STRIDE(sp, dz, l);
       w.alg_flops = conv_flops(h, l, sp.n, T, 2);
       launch_wgrad(w, st);
-      ConvArgs a{};
-      a.nsrc = 2;
-      a.src[0].A = DZ(tn, l, 0); a.src[0].a_stride = STRIDE(tn, dz, l);
-      a.src[0].W = theta + h->pl.w_off[l]; a.src[0].w_stride = h->Ppad; a.src[0].kc = h->F; a.src[0].wt = 1; a.src[0].sign = -1;
-      a.src[1].A = DZ(sp, l, s); a.src[1].a_stride = STRIDE(sp, dz, l);
-      a.src[1].W = u + h->pl.w_off[l]; a.src[1].w_stride = h->Ppad; a.src[1].kc = h->F; a.src[1].wt = 1; a.src[1].sign = -1;
-      a.out = DP(tn, l - 1, 0); a.out_stride = STRIDE(tn, dp, l - 1);
-      a.rows = sp.n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.ncols = h->F; a.mode = CONV_PLAIN; a.tasks = T;
-      a.alg_flops = conv_flops(h, l, sp.n, T, 2);
-      launch_conv_rows(a, st);
+      if (h->use_tc) {
+        TcOp ops[2];
+        ops[0] = tc_op_dz(h, tn, l, 0, h->theta_map, s, -1, 0);     // dgrad(W, dz_dot)
+        ops[1] = tc_op_dz(h, sp, l, s, h->u_map, 0, -1, 0);         // dgrad(u_W, dz)
+        tc_conv(h, l, sp.n, 2, ops, nullptr, 0, DP(tn, l - 1, 0), STRIDE(tn, dp, l - 1), CONV_PLAIN, nullptr, 0, nullptr, T, st);
+      } else {
+        ConvArgs a{};
+        a.nsrc = 2;
+        a.src[0].A = DZ(tn, l, 0); a.src[0].a_stride = STRIDE(tn, dz, l);
+        a.src[0].W = theta + h->pl.w_off[l]; a.src[0].w_stride = h->Ppad; a.src[0].kc = h->F; a.src[0].wt = 1; a.src[0].sign = -1;
+        a.src[1].A = DZ(sp, l, s); a.src[1].a_stride = STRIDE(sp, dz, l);
+        a.src[1].W = u + h->pl.w_off[l]; a.src[1].w_stride = h->Ppad; a.src[1].kc = h->F; a.src[1].wt = 1; a.src[1].sign = -1;
+        a.out = DP(tn, l - 1, 0); a.out_stride = STRIDE(tn, dp, l - 1);
+        a.rows = sp.n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.ncols = h->F; a.mode = CONV_PLAIN; a.tasks = T;
+        a.alg_flops = conv_flops(h, l, sp.n, T, 2);
+        launch_conv_rows(a, st);
+      }
     }
   }
+}
+
+static void pack_theta_step(maml_b200_handle* h, int step, int T, cudaStream_t st) {
+  if (!h->use_tc) return;
+  const long long TP = (long long)h->maxT * h->Ppad;
+  launch_pack_weights(h->pl, h->theta + (long long)step * TP, h->Ppad, h->pack_theta + (long long)step * h->maxT * h->pack_task,
+                      h->pack_task, h->pack_theta_plane, T, st);
+}
+static void pack_u(maml_b200_handle* h, int T, cudaStream_t st) {
+  if (!h->use_tc) return;
+  launch_pack_weights(h->pl, h->u, h->Ppad, h->pack_u, h->pack_task, h->pack_u_plane, T, st);
 }
 
 extern "C" int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200_iter_args* it, const float* meta,
@@ -529,12 +691,13 @@ extern "C" int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200
   launch_prep_x(x_support, h->sup.xg, h->sup.xg_stride, T, h->n_s, h->C, h->H, h->W, st);
   launch_prep_x(x_target, h->tgt.xg, h->tgt.xg_stride, T, h->n_t, h->C, h->H, h->W, st);
   launch_import_theta(h->pl, meta, h->theta, h->Ppad, T, st);
+  pack_theta_step(h, 0, T, st);
 
   // ---------------- phase A: unroll the inner loop
   for (int s = 0; s < it->num_steps; ++s) {
     const float* th = h->theta + (long long)s * TP;
     float* th_next = h->theta + (long long)(s + 1) * TP;
-    forward_pass(h, h->sup, s, th, meta, s, PASS_SUP_FWD, T, st);
+    forward_pass(h, h->sup, s, th, s, meta, s, PASS_SUP_FWD, T, st);
     {
       HeadArgs a{};
       a.mode = HEAD_SUPPORT; a.n = h->n_s; a.N = h->N; a.D = h->D;
@@ -547,12 +710,13 @@ extern "C" int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200
       a.tasks = T;
       launch_head(a, st);
     }
-    backward_pass(h, h->sup, s, th, meta, s, PASS_SUP_FWD, PASS_SUP_BWD, h->sup_partial, h->plan_sup, T, st);
+    backward_pass(h, h->sup, s, th, s, meta, s, PASS_SUP_FWD, PASS_SUP_BWD, h->sup_partial, h->plan_sup, T, st);
     launch_param_reduce(h->pl, h->plan_sup.pd, h->sup_partial, PR_UPDATE, th, th_next, h->g + (long long)s * TP, nullptr, meta, s,
                         h->Ppad, T, st);
+    pack_theta_step(h, s + 1, T, st);
     if (mask & (1u << s)) {
       const int ts = (h->cfg.reserved & 1) ? s : 0;
-      forward_pass(h, h->tgt, ts, th_next, meta, s, PASS_TGT_FWD, T, st);
+      forward_pass(h, h->tgt, ts, th_next, s + 1, meta, s, PASS_TGT_FWD, T, st);
       HeadArgs a{};
       a.mode = HEAD_TARGET_FWD; a.n = h->n_t; a.N = h->N; a.D = h->D;
       a.f = AIN(h->tgt, h->L, ts); a.f_stride = STRIDE(h->tgt, ain, h->L);
@@ -573,7 +737,7 @@ extern "C" int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200
         bqa.g_stride = h->plan_tgt.pd.task_stride;
         bqa.df = DP(h->tgt, h->L - 1, ts); bqa.df_stride = STRIDE(h->tgt, dp, h->L - 1);
         launch_head(bqa, st);
-        backward_pass(h, h->tgt, ts, th_next, meta, s, PASS_TGT_FWD, PASS_TGT_BWD, h->tgt_partial, h->plan_tgt, T, st);
+        backward_pass(h, h->tgt, ts, th_next, s + 1, meta, s, PASS_TGT_FWD, PASS_TGT_BWD, h->tgt_partial, h->plan_tgt, T, st);
         launch_param_reduce(h->pl, h->plan_tgt.pd, h->tgt_partial, PR_STORE, nullptr, nullptr, h->tgrad + (long long)s * TP, nullptr,
                             meta, s, h->Ppad, T, st);
       }
@@ -588,6 +752,7 @@ extern "C" int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200
       const float* tg = (mask & (1u << s)) ? h->tgrad + (long long)s * TP : nullptr;
       launch_dots_u(h->pl, h->tbar, tg, h->g + (long long)s * TP, h->u, h->abar, meta, s, h->Ppad, T, st);
       if (it->second_order) {
+        pack_u(h, T, st);
         tangent_pass(h, s, th, h->u, meta, ys, T, st);
         launch_param_reduce(h->pl, h->plan_sup.pd, h->sup_partial, PR_SUB, nullptr, nullptr, nullptr, h->tbar, meta, s, h->Ppad, T, st);
       }

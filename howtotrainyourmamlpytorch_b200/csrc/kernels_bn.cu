@@ -33,6 +33,19 @@ __device__ __forceinline__ void chan_setup(const double* __restrict__ st, const 
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// TF32 operand split for the tensor-core kernels: x ~= hi + lo, hi = rna_tf32(x), lo = rna_tf32(x - hi)
+__device__ __forceinline__ float tf32_rna_bn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void st4_split(float* hi, float* lo, long long idx, float4 v) {
+  float4 h, l;
+  h.x = tf32_rna_bn(v.x); h.y = tf32_rna_bn(v.y); h.z = tf32_rna_bn(v.z); h.w = tf32_rna_bn(v.w);
+  l.x = tf32_rna_bn(v.x - h.x); l.y = tf32_rna_bn(v.y - h.y); l.z = tf32_rna_bn(v.z - h.z); l.w = tf32_rna_bn(v.w - h.w);
+  st4(hi + idx, h);
+  st4(lo + idx, l);
+}
 __device__ __forceinline__ float4 ld4s(const float* s, int q) { return make_float4(s[q * 4], s[q * 4 + 1], s[q * 4 + 2], s[q * 4 + 3]); }
 
 #define F4_OP(out, expr) { out.x = expr(x); out.y = expr(y); out.z = expr(z); out.w = expr(w); }
@@ -82,8 +95,11 @@ __global__ void __launch_bounds__(256) bnact_kernel(BnActArgs a) {
         }
       }
     }
-    if (wy < g.ph && wx < g.pw)
-      st4(p + ((long long)img * g.pG + (wy + g.pb) * g.pgw + (wx + g.pb)) * g.F + it.q * 4, best);
+    if (wy < g.ph && wx < g.pw) {
+      const long long pidx = ((long long)img * g.pG + (wy + g.pb) * g.pgw + (wx + g.pb)) * g.F + it.q * 4;
+      st4(p + pidx, best);
+      if (a.p_hi) st4_split(a.p_hi + (long long)task * a.p_stride, a.p_lo + (long long)task * a.p_stride, pidx, best);
+    }
   }
 }
 
@@ -233,6 +249,7 @@ __global__ void __launch_bounds__(256) bnbwd_apply_kernel(BnBwdArgs a) {
         o.z = rg.z * ((arg.z == k ? dyv.z : 0.f) - c1.z - zh[k].z * c2.z);
         o.w = rg.w * ((arg.w == k ? dyv.w : 0.f) - c1.w - zh[k].w * c2.w);
         st4(dz + idx[k], o);
+        if (a.dz_hi) st4_split(a.dz_hi + (long long)task * a.dz_stride, a.dz_lo + (long long)task * a.dz_stride, idx[k], o);
       }
     } else {
 #pragma unroll
@@ -245,6 +262,7 @@ __global__ void __launch_bounds__(256) bnbwd_apply_kernel(BnBwdArgs a) {
           o.x = rg.x * (-c1.x - zh.x * c2.x); o.y = rg.y * (-c1.y - zh.y * c2.y);
           o.z = rg.z * (-c1.z - zh.z * c2.z); o.w = rg.w * (-c1.w - zh.w * c2.w);
           st4(dz + idx, o);
+          if (a.dz_hi) st4_split(a.dz_hi + (long long)task * a.dz_stride, a.dz_lo + (long long)task * a.dz_stride, idx, o);
         }
       }
     }
@@ -308,8 +326,11 @@ __global__ void __launch_bounds__(256) bnact_tan_kernel(BnActTanArgs a) {
         }
       }
     }
-    if (wy < g.ph && wx < g.pw)
-      st4(pd + ((long long)img * g.pG + (wy + g.pb) * g.pgw + (wx + g.pb)) * g.F + it.q * 4, pbest);
+    if (wy < g.ph && wx < g.pw) {
+      const long long pidx = ((long long)img * g.pG + (wy + g.pb) * g.pgw + (wx + g.pb)) * g.F + it.q * 4;
+      st4(pd + pidx, pbest);
+      if (a.pdot_hi) st4_split(a.pdot_hi + (long long)task * a.pdot_stride, a.pdot_lo + (long long)task * a.pdot_stride, pidx, pbest);
+    }
   }
 }
 
@@ -423,6 +444,7 @@ __global__ void __launch_bounds__(256) bnbwd_tan_apply_kernel(BnBwdTanArgs a) {
         o.z = rq.z * dzv.z + rg.z * ((arg.z == k ? dyd.z : 0.f) - t1.z - zd.z * c2.z - zh.z * t2.z);
         o.w = rq.w * dzv.w + rg.w * ((arg.w == k ? dyd.w : 0.f) - t1.w - zd.w * c2.w - zh.w * t2.w);
         st4(dzd + idx, o);
+        if (a.dzdot_hi) st4_split(a.dzdot_hi + (long long)task * a.dzdot_stride, a.dzdot_lo + (long long)task * a.dzdot_stride, idx, o);
       }
     }
   }

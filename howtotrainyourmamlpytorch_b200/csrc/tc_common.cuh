@@ -1,0 +1,26 @@
+// Declarations shared by the tcgen05 kernels (kernels_tc.cu) and the engine.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+struct alignas(64) TcMaps { CUtensorMap m[8]; };   // per source: A_hi, A_lo, B_hi, B_lo
+
+struct TcConvArgs {
+  int nsrc, kc, rows, gw, G, h, w, ncols, mode, tasks;
+  int a_row_base[2];     // row (in the A tensor map) of grid row 0 of task 0 for this pass slot (includes the guard)
+  int a_task_rows[2];    // rows per task in the A tensor map
+  int sign[2];           // +1 conv, -1 dgrad
+  int b_row_base[2];     // row (in the B tensor map) of (task 0, tap 0, n 0)
+  int b_task_rows[2];    // rows per task in the B tensor map
+  const float* bias; long long bias_stride;
+  float* out; long long out_stride;
+  const float* zh; long long zh_stride;
+  double* stats; long long stats_stride;
+  double alg_flops;
+};
+
+size_t tc_conv_smem_bytes(int ncols);
+int tc_conv_prepare();
+void launch_conv_tc(const TcMaps& maps, const TcConvArgs& a, cudaStream_t st);
+void launch_pack_weights(const ParamLayout& pl, const float* theta, long long theta_task_stride, float* pack,
+                         long long pack_task_stride, long long plane_stride, int tasks, cudaStream_t st);

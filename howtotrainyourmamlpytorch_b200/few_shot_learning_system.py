@@ -270,7 +270,8 @@ class MAMLFewShotClassifier(nn.Module):
                     t_target=int(a.num_target_samples), channels=int(self.im_shape[1]), height=int(self.im_shape[2]),
                     width=int(self.im_shape[3]), filters=int(a.cnn_num_filters), num_stages=int(a.num_stages),
                     inner_steps=int(a.number_of_training_steps_per_iter), per_step_bn=bool(a.per_step_bn_statistics),
-                    max_tasks=int(n_tasks), keep_target_passes=bool(getattr(self, "_debug_keep_target_passes", False)))
+                    max_tasks=int(n_tasks), keep_target_passes=bool(getattr(self, "_debug_keep_target_passes", False)),
+                    force_fp32_convs=bool(getattr(self, "_debug_force_fp32_convs", False)))
             self._engine_tasks = int(n_tasks)
             if self._engine.meta_size != self._flat.numel():
                 raise RuntimeError("engine / module parameter layout mismatch (%d vs %d floats)" %

@@ -45,7 +45,8 @@ typedef struct maml_b200_config {
   int32_t inner_steps;  /* S  number_of_training_steps_per_iter, <= 8  */
   int32_t per_step_bn;  /* per_step_bn_statistics (MAML++) 0/1         */
   int32_t max_tasks;    /* max tasks per call on this GPU (workspace)  */
-  int32_t reserved;     /* bit 0 (tests): keep the activations of EVERY target pass for debug_read */
+  int32_t reserved;     /* test switches. bit 0: keep the activations of EVERY target pass for debug_read;
+                           bit 1: run blocks l >= 1 on the fp32 FFMA kernels instead of tcgen05 3xTF32 */
 } maml_b200_config;
 
 /* Per-call schedule: what reference forward(...) derives from epoch / phase (:232-244,:304-305). */
