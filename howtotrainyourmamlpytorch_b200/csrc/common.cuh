@@ -193,13 +193,13 @@ void launch_import_theta(const ParamLayout& pl, const float* meta, float* theta0
 void launch_param_reduce(const ParamLayout& pl, const PartialDesc& pd, const float* partial, int mode,
                          const float* theta_in, float* theta_out, float* g_out, float* tbar,
                          const float* meta, int step, long long task_stride, int tasks, cudaStream_t st);
-void launch_dots_u(const ParamLayout& pl, float* tbar, const float* tgrad, const float* g, float* u, float* abar,
+void launch_dots_u(const ParamLayout& pl, float* tbar, const float* tgrad, const float* g, float* u, double* abar,
                    const float* meta, int step, long long task_stride, int tasks, cudaStream_t st);
 
 struct ExportArgs {
   ParamLayout pl;
   const float* tbar; long long task_stride;          // [tasks][P]
-  const float* abar;                                 // [tasks][nseg_inner][MAML_MAX_STEPS]
+  const double* abar;                                // [tasks][nseg_inner][MAML_MAX_STEPS] (fp64 dot products)
   const double* stats; long long stats_task_stride;  // stats arena
   long long st_pass_stride, st_layer_stride;         // arena strides (doubles)
   const float* losses;                               // [tasks][MAML_MAX_STEPS] target losses

@@ -83,7 +83,8 @@ struct maml_b200_handle {
   float *sup_partial = nullptr, *tgt_partial = nullptr;
   ChunkPlan plan_sup, plan_tgt;
   double* stats = nullptr; long long stats_task_stride = 0, st_pass_stride = 0, st_layer_stride = 0, stats_count = 0;
-  float *losses = nullptr, *correct = nullptr, *abar = nullptr, *weights_dev = nullptr, *decay_dev = nullptr;
+  float *losses = nullptr, *correct = nullptr, *weights_dev = nullptr, *decay_dev = nullptr;
+  double* abar = nullptr;
   float* pinned = nullptr;            // host staging ring for small per-call scalars (16 slots x 32 floats)
   int pin_slot = 0;
   long long last_launches = 0;
@@ -288,7 +289,7 @@ static void carve(maml_b200_handle* h, Bump& b) {
   h->stats = b.d(h->stats_count);
   h->losses = b.f(T * MAML_MAX_STEPS);
   h->correct = b.f(T);
-  h->abar = b.f(T * h->pl.nseg_inner * MAML_MAX_STEPS);
+  h->abar = b.d(T * h->pl.nseg_inner * MAML_MAX_STEPS);
   h->weights_dev = b.f(MAML_MAX_STEPS);
   h->decay_dev = b.f(MAML_MAX_STEPS);
 }
@@ -684,7 +685,7 @@ extern "C" int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200
   for (int s = 0; s < MAML_MAX_STEPS; ++s) pin[s] = it->target_weight[s];
   CK(cudaMemcpyAsync(h->weights_dev, pin, MAML_MAX_STEPS * sizeof(float), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(h->stats, 0, (size_t)h->stats_count * sizeof(double), st));
-  CK(cudaMemsetAsync(h->abar, 0, (size_t)h->maxT * h->pl.nseg_inner * MAML_MAX_STEPS * sizeof(float), st));
+  CK(cudaMemsetAsync(h->abar, 0, (size_t)h->maxT * h->pl.nseg_inner * MAML_MAX_STEPS * sizeof(double), st));
   CK(cudaMemsetAsync(h->losses, 0, (size_t)h->maxT * MAML_MAX_STEPS * sizeof(float), st));
   CK(cudaMemsetAsync(h->correct, 0, (size_t)h->maxT * sizeof(float), st));
 
@@ -870,7 +871,6 @@ extern "C" int64_t maml_b200_debug_read(maml_b200_handle* h, const char* name, i
   else if (nm == "tbar") { src = h->tbar + (long long)task * h->Ppad; count = h->pl.P; ok = true; }
   else if (nm == "u") { src = h->u + (long long)task * h->Ppad; count = h->pl.P; ok = true; }
   else if (nm == "losses") { src = h->losses + (long long)task * MAML_MAX_STEPS; count = MAML_MAX_STEPS; ok = true; }
-  else if (nm == "abar") { src = h->abar + (long long)task * h->pl.nseg_inner * MAML_MAX_STEPS; count = (long long)h->pl.nseg_inner * MAML_MAX_STEPS; ok = true; }
   if (!ok) { fail("unknown debug tap / bad index: " + nm); return -1; }
   const long long ncopy = std::min<long long>(count, capacity);
   if (host_out && ncopy > 0) {

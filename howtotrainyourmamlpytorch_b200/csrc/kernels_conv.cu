@@ -362,8 +362,11 @@ void launch_wgrad(const WgradArgs& a, cudaStream_t st) {
 #undef WG_CASE
 }
 
-// first block wgrad: A = image matrix [rows][c0] (c0 <= 4), D = dz [rows][F]
+// first block wgrad: A = image matrix [rows][c0] (c0 <= 4), D = dz [rows][F].
+// Per 64-row sub-tile the dz rows and the image window (rows +/- halo) are staged in shared memory; thread
+// (grp, f) accumulates the (tap, c) combinations q = grp, grp + NG, ... for output channel f.
 __global__ void __launch_bounds__(256) wgrad0_kernel(WgradArgs a) {
+  extern __shared__ float smw[];
   const int task = blockIdx.y, chunk = blockIdx.x;
   const int tid = threadIdx.x;
   const int Fc = a.ncols, c0 = a.kc;
@@ -372,30 +375,54 @@ __global__ void __launch_bounds__(256) wgrad0_kernel(WgradArgs a) {
   const bool active = grp < NG;
   const int ncombo = 9 * c0;
   constexpr int MAXQ = 9;
+  constexpr int RT = 64;
+  const int halo = a.gw + 1;
+  float* Ds = smw;                       // [RT][Fc]
+  float* Xs = smw + RT * Fc;             // [(RT + 2*halo)][c0]
   float acc[MAXQ];
   int off[MAXQ];
 #pragma unroll
   for (int i = 0; i < MAXQ; ++i) {
     acc[i] = 0.f;
     const int q = grp + i * NG;
-    off[i] = (q < ncombo) ? tap_shift(q / c0, a.gw) * c0 + (q % c0) : 0;
+    off[i] = (q < ncombo) ? (tap_shift(q / c0, a.gw) + halo) * c0 + (q % c0) : 0;
   }
   float bacc = 0.f;
   const int r_begin = chunk * a.rows_per_chunk;
   const int r_end = min(a.rows, r_begin + a.rows_per_chunk);
   const float* A = a.A[0] + (long long)task * a.a_stride[0];
   const float* D = a.D[0] + (long long)task * a.d_stride[0];
-  if (active) {
-    for (int jr = r_begin; jr < r_end; ++jr) {
-      const float d = D[(long long)jr * Fc + f];
-      const float* ar = A + (long long)jr * c0;
-#pragma unroll
-      for (int i = 0; i < MAXQ; ++i) {
-        const int q = grp + i * NG;
-        if (q < ncombo) acc[i] = fmaf(ar[off[i]], d, acc[i]);
-      }
-      bacc += d;
+  const int guard = a.gw + 2;
+  for (int r0 = r_begin; r0 < r_end; r0 += RT) {
+    const int nr = min(RT, r_end - r0);
+    for (int i = tid; i < RT * Fc / 4; i += 256) {
+      const int r = (i * 4) / Fc;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nr) v = *reinterpret_cast<const float4*>(D + (long long)r0 * Fc + (long long)i * 4);
+      *reinterpret_cast<float4*>(Ds + i * 4) = v;
     }
+    for (int i = tid; i < (RT + 2 * halo) * c0; i += 256) {
+      const int r = r0 - halo + i / c0;
+      float v = 0.f;
+      if (r >= -guard && r < a.rows + guard) v = A[(long long)(r0 - halo) * c0 + i];
+      Xs[i] = v;
+    }
+    __syncthreads();
+    if (active) {
+      for (int r = 0; r < nr; ++r) {
+        const float d = Ds[r * Fc + f];
+        const float* xr = Xs + r * c0;
+#pragma unroll
+        for (int i = 0; i < MAXQ; ++i) {
+          const int q = grp + i * NG;
+          if (q < ncombo) acc[i] = fmaf(xr[off[i]], d, acc[i]);
+        }
+        bacc += d;
+      }
+    }
+    __syncthreads();
+  }
+  if (active) {
     float* P = a.partial + (long long)task * a.partial_task_stride + (long long)chunk * a.chunk_stride;
 #pragma unroll
     for (int i = 0; i < MAXQ; ++i) {
@@ -409,7 +436,8 @@ __global__ void __launch_bounds__(256) wgrad0_kernel(WgradArgs a) {
 void launch_wgrad0(const WgradArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_WGRAD0, a.alg_flops, st);
   dim3 grid(a.nchunks, a.tasks);
-  wgrad0_kernel<<<grid, 256, 0, st>>>(a);
+  const size_t smem = (size_t)(64 * a.ncols + (64 + 2 * (a.gw + 1)) * a.kc) * sizeof(float);
+  wgrad0_kernel<<<grid, 256, smem, st>>>(a);
   CUDA_CHECK_LAUNCH();
 }
 

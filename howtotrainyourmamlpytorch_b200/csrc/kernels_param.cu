@@ -97,37 +97,44 @@ void launch_param_reduce(const ParamLayout& pl, const PartialDesc& pd, const flo
   CUDA_CHECK_LAUNCH();
 }
 
-// per (task, inner tensor):  tbar += tgrad (optional);  abar[seg][step] = -<tbar, g>;  u = alpha[seg][step] * tbar
+// per task:  tbar += tgrad (optional);  abar[seg][step] = -<tbar_seg, g_seg> (fp64);  u = alpha[seg][step] * tbar
+// grid (P / 2048, tasks): each CTA covers 2048 consecutive elements, which may straddle a few inner tensors.
 __global__ void __launch_bounds__(256) dots_u_kernel(ParamLayout pl, float* __restrict__ tbar, const float* __restrict__ tgrad,
                                                      const float* __restrict__ g, float* __restrict__ u,
-                                                     float* __restrict__ abar, const float* __restrict__ meta, int step,
+                                                     double* __restrict__ abar, const float* __restrict__ meta, int step,
                                                      long long task_stride) {
   __shared__ double red[8];
-  const int seg = blockIdx.x, task = blockIdx.y;
-  const long long base = (long long)task * task_stride + pl.seg_off[seg];
-  const float alpha = meta[pl.m_lslr + (long long)seg * (pl.S + 1) + step];
-  double dot = 0.0;
-  for (long long i = threadIdx.x; i < pl.seg_size[seg]; i += 256) {
-    float tb = tbar[base + i];
-    if (tgrad) { tb += tgrad[base + i]; tbar[base + i] = tb; }
-    dot += (double)tb * (double)g[base + i];
-    u[base + i] = alpha * tb;
-  }
+  const int task = blockIdx.y;
+  const long long lo = (long long)blockIdx.x * 2048, hi = min(pl.P, lo + 2048);
+  const long long base = (long long)task * task_stride;
+  for (int seg = 0; seg < pl.nseg_inner; ++seg) {
+    const long long s0 = max(lo, pl.seg_off[seg]), s1 = min(hi, pl.seg_off[seg] + pl.seg_size[seg]);
+    if (s0 >= s1) continue;                                  // CTA-uniform
+    const float alpha = meta[pl.m_lslr + (long long)seg * (pl.S + 1) + step];
+    double dot = 0.0;
+    for (long long i = s0 + threadIdx.x; i < s1; i += 256) {
+      float tb = tbar[base + i];
+      if (tgrad) { tb += tgrad[base + i]; tbar[base + i] = tb; }
+      dot += (double)tb * (double)g[base + i];
+      u[base + i] = alpha * tb;
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int w = 0; w < 8; ++w) t += red[w];
-    abar[((long long)task * pl.nseg_inner + seg) * MAML_MAX_STEPS + step] = (float)(-t);
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += red[w];
+      atomicAdd(&abar[((long long)task * pl.nseg_inner + seg) * MAML_MAX_STEPS + step], -t);
+    }
   }
 }
 
-void launch_dots_u(const ParamLayout& pl, float* tbar, const float* tgrad, const float* g, float* u, float* abar,
+void launch_dots_u(const ParamLayout& pl, float* tbar, const float* tgrad, const float* g, float* u, double* abar,
                    const float* meta, int step, long long task_stride, int tasks, cudaStream_t st) {
   ProfScope prof_scope__(PROF_PARAM, 0.0, st);
-  dim3 grid(pl.nseg_inner, tasks);
+  dim3 grid((unsigned)((pl.P + 2047) / 2048), tasks);
   dots_u_kernel<<<grid, 256, 0, st>>>(pl, tbar, tgrad, g, u, abar, meta, step, task_stride);
   CUDA_CHECK_LAUNCH();
 }
@@ -201,7 +208,7 @@ __global__ void export_kernel(ExportArgs a) {
         const int s = (int)(rel % (pl.S + 1));
         if (s < a.num_steps)
           for (int t = 0; t < a.tasks; ++t)
-            val += (double)a.abar[((long long)t * pl.nseg_inner + seg) * MAML_MAX_STEPS + s];
+            val += a.abar[((long long)t * pl.nseg_inner + seg) * MAML_MAX_STEPS + s];
       }
     }
     a.result[i] = (float)(val * invB);

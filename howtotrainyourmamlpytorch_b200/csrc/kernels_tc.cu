@@ -11,7 +11,12 @@
 //
 // Precision: single-pass TF32 is not acceptable for this path (40-130 % meta-gradient
 // error).  Every operand x is pre-split by its producer kernel into hi = rna_tf32(x), lo = rna_tf32(x - hi);
-// the kernel accumulates  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  in the fp32 TMEM accumulator (error ~2^-22).
+// the kernel accumulates A_hi*B_hi and (A_lo*B_hi + A_hi*B_lo) in SEPARATE fp32 TMEM accumulators.
+// The tensor core's fp32 accumulation truncates when it aligns addends, so error grows with the number of
+// sequential accumulations into one accumulator (measured: one accumulator for all 216 MMAs of a 64-channel
+// layer gave ~5x the fp32-FFMA error).  The big term is therefore spread round-robin over 4 accumulators
+// (18 accumulations each instead of 216), the small terms get a fifth, and the epilogue adds the five with
+// IEEE fp32 adds.
 //
 // CTA = one 128-row M tile x all N (<= 64) columns.  Warp roles: warp 0 = TMA producer (one thread),
 // warp 1 = TMEM allocator + MMA issuer (one thread), warps 2..5 = epilogue (TMEM -> registers -> shared ->
@@ -84,7 +89,8 @@ template <int NCOLS>
 __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvArgs a) {
   constexpr int B_BYTES = NCOLS * 128;
   constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
-  constexpr int TMEM_COLS = NCOLS <= 32 ? 32 : 64;
+  constexpr int NACC = 5;                       // 4 x hi*hi (round-robin over k-steps) + 1 x (lo*hi + hi*lo)
+  constexpr int TMEM_COLS = NCOLS <= 32 ? 256 : 512;   // power of two >= NACC * NCOLS
   constexpr int PITCH = NCOLS + 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -153,9 +159,10 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
           const uint64_t al = make_desc_sw128(st + TC_A_BYTES + k * 32);
           const uint64_t bh = make_desc_sw128(st + 2 * TC_A_BYTES + k * 32);
           const uint64_t bl = make_desc_sw128(st + 2 * TC_A_BYTES + B_BYTES + k * 32);
-          tc_mma_tf32(tmem_base, al, bh, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          tc_mma_tf32(tmem_base, ah, bl, idesc, 1u);
-          tc_mma_tf32(tmem_base, ah, bh, idesc, 1u);
+          const int kstep = it * 4 + k;
+          tc_mma_tf32(tmem_base + 4 * NCOLS, al, bh, idesc, kstep > 0 ? 1u : 0u);
+          tc_mma_tf32(tmem_base + 4 * NCOLS, ah, bl, idesc, 1u);
+          tc_mma_tf32(tmem_base + (uint32_t)(kstep & 3) * NCOLS, ah, bh, idesc, kstep >= 4 ? 1u : 0u);
         }
         tc_commit(&empty_bar[stage]);            // frees this smem stage once the MMAs above have read it
       }
@@ -182,11 +189,19 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     const float* bias = a.bias ? a.bias + (long long)task * a.bias_stride : nullptr;
 #pragma unroll
     for (int c0 = 0; c0 < NCOLS; c0 += 16) {
-      uint32_t v[16];
-      tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      uint32_t v0[16], v1[16], v2[16], v3[16], v4[16];
+      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      tc_ld16(ta, v0);
+      tc_ld16(ta + NCOLS, v1);
+      tc_ld16(ta + 2 * NCOLS, v2);
+      tc_ld16(ta + 3 * NCOLS, v3);
+      tc_ld16(ta + 4 * NCOLS, v4);
       tc_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) tile[r * PITCH + c0 + i] = __uint_as_float(v[i]) + (bias ? bias[c0 + i] : 0.f);
+      for (int i = 0; i < 16; ++i) {
+        const float big = (__uint_as_float(v0[i]) + __uint_as_float(v1[i])) + (__uint_as_float(v2[i]) + __uint_as_float(v3[i]));
+        tile[r * PITCH + c0 + i] = (big + __uint_as_float(v4[i])) + (bias ? bias[c0 + i] : 0.f);
+      }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
     float* out = a.out + (long long)task * a.out_stride;

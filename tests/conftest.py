@@ -78,7 +78,7 @@ def grad_tolerance(name, ref32, ref64, big=False):
         ~1e-4 of its max-norm (measured: the autograd-free fp32 restatement vs the fp64 reference on
         omniglot_mamlpp_5w1s, 3 flips -> 4.6e-4; the GPU path, other flips -> up to 3.6e-3 on one LSLR
         gradient; DESIGN.md "noise floor").  The TIGHT full-size check is
-        tests/test_gpu_parity.py::test_decision_forced_parity_full_size, which pins the discrete decisions
+        tests/test_gpu_parity.py::test_decision_forced_parity, which pins the discrete decisions
         and then demands 1e-4; stage-level tests stay at 1e-5.
     Conv biases are mathematically dead (BatchNorm removes them): absolute tolerance only."""
     r64 = ref64.double()

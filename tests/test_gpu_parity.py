@@ -108,7 +108,11 @@ def test_golden_reference_parity(case, cuda_device):
     g = load_golden(case)
     m = _model(g, cuda_device)
     losses, preds, grads = m.meta_gradient(g.batch(0), g.iters[0][0])
-    big = case in BIG_CASES
+    # Tie-breaking chaos (conftest.grad_tolerance) can hit ANY case whose pre-activations land within an ulp of
+    # a branch point under this implementation's rounding (observed on tiny_odd with the tensor-core convs: one
+    # flip -> 1e-4), so the direct comparison always uses the loose bound; the tight statement is
+    # test_decision_forced_parity, which runs on every case.
+    big = True
     ref_loss32, ref_loss64 = g.scalar("loss"), g.scalar("loss64")
     ltol = max(3 * abs(ref_loss32 - ref_loss64), (5e-3 if big else 2e-5) * abs(ref_loss64))
     assert abs(float(losses["loss"]) - ref_loss64) <= ltol, (float(losses["loss"]), ref_loss32, ref_loss64)
@@ -129,8 +133,7 @@ def test_golden_reference_parity(case, cuda_device):
             bad.append(n)
     _report(case + " golden parity (loss %.7f, ref32 %.7f, ref64 %.7f)" % (float(losses["loss"]), ref_loss32, ref_loss64), rows)
     assert not bad, bad
-    if not big:
-        assert abs(losses["accuracy"] - g.scalar("accuracy")) < 1e-6
+    assert abs(losses["accuracy"] - g.scalar("accuracy")) <= (0.051 if case in BIG_CASES else 1e-6)
     w = g.array("msl")
     for i in range(len(w)):
         assert abs(float(losses["loss_importance_vector_%d" % i]) - w[i]) < 1e-7
@@ -258,8 +261,8 @@ def _gpu_decisions(m, g, batch, epoch):
     return dec
 
 
-@pytest.mark.parametrize("case", ["tiny_pp", "omniglot_mamlpp_5w1s", "omniglot_mamlpp_20w5s", "mini_imagenet_mamlpp_5w1s"])
-def test_decision_forced_parity_full_size(case, cuda_device):
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_decision_forced_parity(case, cuda_device):
     """Full-size parity that is immune to tie-breaking chaos.  The network is piecewise smooth: its only
     discontinuities are the leaky-ReLU branch and the pooling arg-max.  We (1) read back the decisions the
     GPU took, (2) check each one is CONSISTENT with exact arithmetic -- it may differ from the fp64 choice
