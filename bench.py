@@ -231,7 +231,7 @@ def main():
     B = int(args.batch_size)
     n_pool = 8
     host_batches = [synthetic_batch(args, iteration=1000 * rank + i) for i in range(n_pool)]
-    dev_batches = [tuple(t.to(dev) for t in hb) for hb in host_batches]
+    dev_batches = [(hb[0].to(dev), hb[1].to(dev), hb[2].long().to(dev), hb[3].long().to(dev)) for hb in host_batches]
     pinned_batches = [tuple(t.pin_memory() for t in hb) for hb in host_batches]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 

@@ -135,7 +135,7 @@ struct HeadArgs {
   const float* Wfc; const float* bfc; long long theta_stride;     // [N][D], [N] (internal order), per task
   const float* uW; const float* ub; long long u_stride;           // tangent direction (HEAD_TANGENT)
   const long long* y; long long y_stride;         // labels [n]
-  const float* scale_ptr;                         // nullable: loss weight (device scalar)
+  float scale;                                    // loss weight folded into dlogits (1 for the support loss)
   float* gW; float* gb; long long g_stride;       // gradient (or H*u) output for the head tensors
   float* df; long long df_stride;                 // [n][D] gradient (or its tangent) w.r.t. features
   float* loss_out; long long loss_stride;         // per-task scalar (HEAD_TARGET_FWD)
@@ -204,7 +204,7 @@ struct ExportArgs {
   long long st_pass_stride, st_layer_stride;         // arena strides (doubles)
   const float* losses;                               // [tasks][MAML_MAX_STEPS] target losses
   const float* correct;                              // [tasks]
-  const float* weights;                              // device [MAML_MAX_STEPS] target weights
+  float weights[MAML_MAX_STEPS];                     // target-pass loss weights
   unsigned target_mask; int num_steps; int training;
   int tasks, task_offset, tasks_global;
   int n_s, n_t;

@@ -83,13 +83,20 @@ struct maml_b200_handle {
   float *sup_partial = nullptr, *tgt_partial = nullptr;
   ChunkPlan plan_sup, plan_tgt;
   double* stats = nullptr; long long stats_task_stride = 0, st_pass_stride = 0, st_layer_stride = 0, stats_count = 0;
-  float *losses = nullptr, *correct = nullptr, *weights_dev = nullptr, *decay_dev = nullptr;
+  float *losses = nullptr, *correct = nullptr, *decay_dev = nullptr;
   double* abar = nullptr;
   float* pinned = nullptr;            // host staging ring for small per-call scalars (16 slots x 32 floats)
   int pin_slot = 0;
   long long last_launches = 0;
   int last_tasks = 0;
   Profiler prof;
+  // side streams / events for fork-join inside one iteration, CUDA-graph cache
+  cudaStream_t s_cap = nullptr, s_tgt = nullptr, s_wg = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_wg = nullptr, ev_pack = nullptr, ev_tgt[MAML_MAX_STEPS] = {};
+  bool use_graphs = true;
+  struct GraphEntry { maml_b200_iter_args it; const void* p[7]; cudaGraphExec_t exec; long long launches; unsigned long long stamp; };
+  std::vector<GraphEntry> graphs;
+  unsigned long long graph_clock = 0;
   // tensor-core path (blocks l >= 1 when F % 32 == 0)
   bool use_tc = false;
   float *pack_theta = nullptr, *pack_u = nullptr;       // [4 planes][steps][T][(L-1)*9*F*F]
@@ -155,9 +162,9 @@ static void plan_chunks(maml_b200_handle* h, int n, ChunkPlan* cp) {
     const long long rows = (long long)n * h->geo[l].G;
     int nch, rpc;
     if (l == 0) {
-      nch = (int)std::min<long long>(256, std::max<long long>(1, (rows + 255) / 256));
+      nch = (int)std::min<long long>(256, std::max<long long>(1, (rows + 63) / 64));
     } else {
-      nch = (int)std::min<long long>(64, std::max<long long>(1, (rows + 511) / 512));
+      nch = (int)std::min<long long>(64, std::max<long long>(1, (rows + 127) / 128));
     }
     rpc = (int)rup((rows + nch - 1) / nch, 16);
     nch = (int)((rows + rpc - 1) / rpc);
@@ -290,7 +297,6 @@ static void carve(maml_b200_handle* h, Bump& b) {
   h->losses = b.f(T * MAML_MAX_STEPS);
   h->correct = b.f(T);
   h->abar = b.d(T * h->pl.nseg_inner * MAML_MAX_STEPS);
-  h->weights_dev = b.f(MAML_MAX_STEPS);
   h->decay_dev = b.f(MAML_MAX_STEPS);
 }
 
@@ -316,7 +322,7 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   build_geometry(h);
   build_layout(h);
   // tensor-core (tcgen05 / TMA, 3xTF32) convolutions for blocks l >= 1; reserved bit 1 forces the fp32 FFMA kernels (tests)
-  h->use_tc = (h->F % 32 == 0) && (h->L > 1) && !(cfg->reserved & 2);
+  h->use_tc = (h->L > 1) && !(cfg->reserved & 2);      // F in {16, 32, 48, 64}: ragged K chunks are zero-filled by TMA
   plan_chunks(h, h->n_s, &h->plan_sup);
   plan_chunks(h, h->n_t, &h->plan_tgt);
   Bump sz{nullptr, 0};
@@ -331,12 +337,29 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   if (make_all_maps(h)) { cudaFree(h->ws); delete h; return 1; }
   e = cudaMallocHost((void**)&h->pinned, 16 * 32 * sizeof(float));
   if (e != cudaSuccess) { cudaFree(h->ws); delete h; return fail(std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
+  h->use_graphs = !(cfg->reserved & 4) && !getenv("MAML_B200_NO_GRAPH");
+  bool ok = cudaStreamCreateWithFlags(&h->s_cap, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&h->s_tgt, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&h->s_wg, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->ev_wg, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming) == cudaSuccess;
+  for (int s = 0; ok && s < MAML_MAX_STEPS; ++s) ok = cudaEventCreateWithFlags(&h->ev_tgt[s], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { maml_b200_destroy(h); return fail("stream / event creation failed"); }
   *out = h;
   return 0;
 }
 
 extern "C" void maml_b200_destroy(maml_b200_handle* h) {
   if (!h) return;
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (h->s_cap) cudaStreamDestroy(h->s_cap);
+  if (h->s_tgt) cudaStreamDestroy(h->s_tgt);
+  if (h->s_wg) cudaStreamDestroy(h->s_wg);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_wg) cudaEventDestroy(h->ev_wg);
+  if (h->ev_pack) cudaEventDestroy(h->ev_pack);
+  for (int s = 0; s < MAML_MAX_STEPS; ++s) if (h->ev_tgt[s]) cudaEventDestroy(h->ev_tgt[s]);
   if (h->ws) cudaFree(h->ws);
   if (h->pinned) cudaFreeHost(h->pinned);
   delete h;
@@ -484,7 +507,11 @@ static void forward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const
 
 // primal backward of one pass (dp[L-1] already written by the head): BN backward, wgrad, dgrad
 static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const float* theta, int th_step, const float* meta,
-                          int bn_step, int kind_fwd, int kind_bwd, float* partial, const ChunkPlan& cp, int T, cudaStream_t st) {
+                          int bn_step, int kind_fwd, int kind_bwd, float* partial, const ChunkPlan& cp, int T, cudaStream_t st,
+                          bool fork_wgrad) {
+  // wgrad of block l only feeds the parameter-space reduction at the end of the pass: it runs on a side stream,
+  // concurrently with dgrad(l) and the BatchNorm backward of block l-1 (joined by the caller's param_reduce).
+  cudaStream_t wst = fork_wgrad ? h->s_wg : st;
   for (int l = h->L - 1; l >= 0; --l) {
     const LayerGeom& g = h->geo[l];
     BnBwdArgs b{};
@@ -498,6 +525,7 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
     b.g = bn_geom(h, l, ps.n); b.tasks = T;
     launch_bnbwd_reduce(b, st);
     launch_bnbwd_apply(b, st);
+    if (fork_wgrad) { cudaEventRecord(h->ev_fork, st); cudaStreamWaitEvent(h->s_wg, h->ev_fork, 0); }
 
     WgradArgs w{};
     w.nsrc = 1;
@@ -509,11 +537,11 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
     if (l == 0) {
       w.A[0] = ps.xg; w.a_stride[0] = ps.xg_stride; w.kc = h->C;
       w.alg_flops = conv_flops(h, 0, ps.n, T, 1);
-      launch_wgrad0(w, st);
+      launch_wgrad0(w, wst);
     } else {
       w.A[0] = AIN(ps, l, slot); w.a_stride[0] = STRIDE(ps, ain, l); w.kc = h->F;
       w.alg_flops = conv_flops(h, l, ps.n, T, 1);
-      launch_wgrad(w, st);
+      launch_wgrad(w, wst);
       if (h->use_tc) {
         TcOp op = tc_op_dz(h, ps, l, slot, h->theta_map, th_step, -1, 0);
         tc_conv(h, l, ps.n, 1, &op, nullptr, 0, DP(ps, l - 1, slot), STRIDE(ps, dp, l - 1), CONV_PLAIN, nullptr, 0, nullptr, T, st);
@@ -529,6 +557,7 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
       }
     }
   }
+  if (fork_wgrad) { cudaEventRecord(h->ev_wg, h->s_wg); cudaStreamWaitEvent(st, h->ev_wg, 0); }
 }
 
 // forward-mode tangent of (support forward + support backward) at step s in direction u  =>  H u into `partial`
@@ -583,7 +612,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
   const ChunkPlan& cp = h->plan_sup;
   {
     HeadArgs a{};
-    a.mode = HEAD_TANGENT; a.n = h->n_s; a.N = h->N; a.D = h->D;
+    a.mode = HEAD_TANGENT; a.n = h->n_s; a.N = h->N; a.D = h->D; a.scale = 1.f;
     a.f = AIN(sp, h->L, s); a.f_stride = STRIDE(sp, ain, h->L);
     a.fdot = AIN(tn, h->L, 0); a.fdot_stride = STRIDE(tn, ain, h->L);
     a.Wfc = theta + h->pl.fcw_off; a.bfc = theta + h->pl.fcb_off; a.theta_stride = h->Ppad;
@@ -612,6 +641,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
     b.g = bn_geom(h, l, sp.n); b.tasks = T;
     launch_bnbwd_tan_reduce(b, st);
     launch_bnbwd_tan_apply(b, st);
+    cudaEventRecord(h->ev_fork, st); cudaStreamWaitEvent(h->s_wg, h->ev_fork, 0);
 
     WgradArgs w{};
     w.D[0] = DZ(tn, l, 0); w.d_stride[0] = STRIDE(tn, dz, l);
@@ -623,14 +653,14 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
       w.nsrc = 1;
       w.A[0] = sp.xg; w.a_stride[0] = sp.xg_stride; w.kc = h->C;
       w.alg_flops = conv_flops(h, 0, sp.n, T, 1);
-      launch_wgrad0(w, st);
+      launch_wgrad0(w, h->s_wg);
     } else {
       w.nsrc = 2;
       w.A[0] = AIN(sp, l, s); w.a_stride[0] = STRIDE(sp, ain, l); w.kc = h->F;
       w.A[1] = AIN(tn, l, 0); w.a_stride[1] = STRIDE(tn, ain, l);
       w.D[1] = DZ(sp, l, s); w.d_stride[1] = STRIDE(sp, dz, l);
       w.alg_flops = conv_flops(h, l, sp.n, T, 2);
-      launch_wgrad(w, st);
+      launch_wgrad(w, h->s_wg);
       if (h->use_tc) {
         TcOp ops[2];
         ops[0] = tc_op_dz(h, tn, l, 0, h->theta_map, s, -1, 0);     // dgrad(W, dz_dot)
@@ -652,6 +682,11 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
   }
 }
 
+static void join_wgrad(maml_b200_handle* h, cudaStream_t st) {
+  cudaEventRecord(h->ev_wg, h->s_wg);
+  cudaStreamWaitEvent(st, h->ev_wg, 0);
+}
+
 static void pack_theta_step(maml_b200_handle* h, int step, int T, cudaStream_t st) {
   if (!h->use_tc) return;
   const long long TP = (long long)h->maxT * h->Ppad;
@@ -663,27 +698,16 @@ static void pack_u(maml_b200_handle* h, int T, cudaStream_t st) {
   launch_pack_weights(h->pl, h->u, h->Ppad, h->pack_u, h->pack_task, h->pack_u_plane, T, st);
 }
 
-extern "C" int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200_iter_args* it, const float* meta,
-                                            const float* x_support, const int64_t* y_support, const float* x_target,
-                                            const int64_t* y_target, float* result, float* last_logits, void* stream) {
-  if (!h || !it || !meta || !x_support || !y_support || !x_target || !y_target || !result) return fail("null argument");
+// enqueue one whole iteration; `st` is either the caller's stream (eager / profiling) or the capture stream
+static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it, const float* meta, const float* x_support,
+                             const long long* ys, const float* x_target, const long long* yt, float* result, float* last_logits,
+                             cudaStream_t st) {
   const int T = it->n_tasks;
-  if (T < 1 || T > h->maxT) return fail("n_tasks out of range");
-  if (it->num_steps < 1 || it->num_steps > h->S) return fail("num_steps out of range (must be <= inner_steps)");
-  if (it->tasks_global < T) return fail("tasks_global < n_tasks");
   const unsigned mask = it->target_mask & ((1u << it->num_steps) - 1u);
-  if (mask == 0) return fail("target_mask selects no target pass");
-  cudaStream_t st = (cudaStream_t)stream;
-  const long long launches0 = g_launch_counter;
   const long long TP = (long long)h->maxT * h->Ppad;
-  const long long* ys = (const long long*)y_support;
-  const long long* yt = (const long long*)y_target;
   int last_t = 0;
   for (int s = 0; s < it->num_steps; ++s) if (mask & (1u << s)) last_t = s;
 
-  float* pin = h->pinned + 32 * (h->pin_slot++ & 15);
-  for (int s = 0; s < MAML_MAX_STEPS; ++s) pin[s] = it->target_weight[s];
-  CK(cudaMemcpyAsync(h->weights_dev, pin, MAML_MAX_STEPS * sizeof(float), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(h->stats, 0, (size_t)h->stats_count * sizeof(double), st));
   CK(cudaMemsetAsync(h->abar, 0, (size_t)h->maxT * h->pl.nseg_inner * MAML_MAX_STEPS * sizeof(double), st));
   CK(cudaMemsetAsync(h->losses, 0, (size_t)h->maxT * MAML_MAX_STEPS * sizeof(float), st));
@@ -694,14 +718,15 @@ extern "C" int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200
   launch_import_theta(h->pl, meta, h->theta, h->Ppad, T, st);
   pack_theta_step(h, 0, T, st);
 
-  // ---------------- phase A: unroll the inner loop
+  // ---------------- phase A: unroll the inner loop.  Support chain on `st`; the target pass of step s (forward at
+  // theta^{s+1}, and its backward) only feeds phase B, so it runs on a side stream concurrently with step s+1.
   for (int s = 0; s < it->num_steps; ++s) {
     const float* th = h->theta + (long long)s * TP;
     float* th_next = h->theta + (long long)(s + 1) * TP;
     forward_pass(h, h->sup, s, th, s, meta, s, PASS_SUP_FWD, T, st);
     {
       HeadArgs a{};
-      a.mode = HEAD_SUPPORT; a.n = h->n_s; a.N = h->N; a.D = h->D;
+      a.mode = HEAD_SUPPORT; a.n = h->n_s; a.N = h->N; a.D = h->D; a.scale = 1.f;
       a.f = AIN(h->sup, h->L, s); a.f_stride = STRIDE(h->sup, ain, h->L);
       a.Wfc = th + h->pl.fcw_off; a.bfc = th + h->pl.fcb_off; a.theta_stride = h->Ppad;
       a.y = ys; a.y_stride = h->n_s;
@@ -711,15 +736,18 @@ extern "C" int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200
       a.tasks = T;
       launch_head(a, st);
     }
-    backward_pass(h, h->sup, s, th, s, meta, s, PASS_SUP_FWD, PASS_SUP_BWD, h->sup_partial, h->plan_sup, T, st);
+    backward_pass(h, h->sup, s, th, s, meta, s, PASS_SUP_FWD, PASS_SUP_BWD, h->sup_partial, h->plan_sup, T, st, true);
     launch_param_reduce(h->pl, h->plan_sup.pd, h->sup_partial, PR_UPDATE, th, th_next, h->g + (long long)s * TP, nullptr, meta, s,
                         h->Ppad, T, st);
     pack_theta_step(h, s + 1, T, st);
     if (mask & (1u << s)) {
+      cudaStream_t ts_ = h->s_tgt;
+      CK(cudaEventRecord(h->ev_pack, st));
+      CK(cudaStreamWaitEvent(ts_, h->ev_pack, 0));
       const int ts = (h->cfg.reserved & 1) ? s : 0;
-      forward_pass(h, h->tgt, ts, th_next, s + 1, meta, s, PASS_TGT_FWD, T, st);
+      forward_pass(h, h->tgt, ts, th_next, s + 1, meta, s, PASS_TGT_FWD, T, ts_);
       HeadArgs a{};
-      a.mode = HEAD_TARGET_FWD; a.n = h->n_t; a.N = h->N; a.D = h->D;
+      a.mode = HEAD_TARGET_FWD; a.n = h->n_t; a.N = h->N; a.D = h->D; a.scale = 1.f;
       a.f = AIN(h->tgt, h->L, ts); a.f_stride = STRIDE(h->tgt, ain, h->L);
       a.Wfc = th_next + h->pl.fcw_off; a.bfc = th_next + h->pl.fcb_off; a.theta_stride = h->Ppad;
       a.y = yt; a.y_stride = h->n_t;
@@ -729,35 +757,40 @@ extern "C" int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200
         a.correct_out = h->correct; a.correct_stride = 1;
       }
       a.tasks = T;
-      launch_head(a, st);
+      launch_head(a, ts_);
       if (it->training) {
         HeadArgs bqa = a;
-        bqa.mode = HEAD_TARGET_BWD; bqa.scale_ptr = h->weights_dev + s;
+        bqa.mode = HEAD_TARGET_BWD; bqa.scale = it->target_weight[s];
         bqa.logits_out = nullptr; bqa.correct_out = nullptr; bqa.loss_out = nullptr;
         bqa.gW = h->tgt_partial + h->plan_tgt.pd.off[2 * h->L]; bqa.gb = h->tgt_partial + h->plan_tgt.pd.off[2 * h->L + 1];
         bqa.g_stride = h->plan_tgt.pd.task_stride;
         bqa.df = DP(h->tgt, h->L - 1, ts); bqa.df_stride = STRIDE(h->tgt, dp, h->L - 1);
-        launch_head(bqa, st);
-        backward_pass(h, h->tgt, ts, th_next, s + 1, meta, s, PASS_TGT_FWD, PASS_TGT_BWD, h->tgt_partial, h->plan_tgt, T, st);
+        launch_head(bqa, ts_);
+        backward_pass(h, h->tgt, ts, th_next, s + 1, meta, s, PASS_TGT_FWD, PASS_TGT_BWD, h->tgt_partial, h->plan_tgt, T, ts_, false);
         launch_param_reduce(h->pl, h->plan_tgt.pd, h->tgt_partial, PR_STORE, nullptr, nullptr, h->tgrad + (long long)s * TP, nullptr,
-                            meta, s, h->Ppad, T, st);
+                            meta, s, h->Ppad, T, ts_);
       }
+      CK(cudaEventRecord(h->ev_tgt[s], ts_));
     }
   }
 
-  // ---------------- phase B: reverse sweep
+  // ---------------- phase B: reverse sweep (joins the target chain step by step)
   if (it->training) {
     CK(cudaMemsetAsync(h->tbar, 0, (size_t)TP * sizeof(float), st));
     for (int s = it->num_steps - 1; s >= 0; --s) {
       const float* th = h->theta + (long long)s * TP;
-      const float* tg = (mask & (1u << s)) ? h->tgrad + (long long)s * TP : nullptr;
+      const float* tg = nullptr;
+      if (mask & (1u << s)) { tg = h->tgrad + (long long)s * TP; CK(cudaStreamWaitEvent(st, h->ev_tgt[s], 0)); }
       launch_dots_u(h->pl, h->tbar, tg, h->g + (long long)s * TP, h->u, h->abar, meta, s, h->Ppad, T, st);
       if (it->second_order) {
         pack_u(h, T, st);
         tangent_pass(h, s, th, h->u, meta, ys, T, st);
+        join_wgrad(h, st);
         launch_param_reduce(h->pl, h->plan_sup.pd, h->sup_partial, PR_SUB, nullptr, nullptr, nullptr, h->tbar, meta, s, h->Ppad, T, st);
       }
     }
+  } else {
+    for (int s = 0; s < it->num_steps; ++s) if (mask & (1u << s)) CK(cudaStreamWaitEvent(st, h->ev_tgt[s], 0));
   }
 
   ExportArgs e{};
@@ -765,17 +798,70 @@ extern "C" int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200
   e.tbar = h->tbar; e.task_stride = h->Ppad;
   e.abar = h->abar;
   e.stats = h->stats; e.stats_task_stride = h->stats_task_stride; e.st_pass_stride = h->st_pass_stride; e.st_layer_stride = h->st_layer_stride;
-  e.losses = h->losses; e.correct = h->correct; e.weights = h->weights_dev;
+  e.losses = h->losses; e.correct = h->correct;
+  for (int s = 0; s < MAML_MAX_STEPS; ++s) e.weights[s] = it->target_weight[s];
   e.target_mask = mask; e.num_steps = it->num_steps; e.training = it->training;
   e.tasks = T; e.task_offset = it->task_offset; e.tasks_global = it->tasks_global;
   e.n_s = h->n_s; e.n_t = h->n_t;
   for (int l = 0; l < h->L; ++l) e.hw[l] = h->geo[l].h * h->geo[l].w;
   e.result = result;
   launch_export(e, st);
+  return 0;
+}
 
-  h->last_launches = g_launch_counter - launches0;
+extern "C" int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200_iter_args* it, const float* meta,
+                                            const float* x_support, const int64_t* y_support, const float* x_target,
+                                            const int64_t* y_target, float* result, float* last_logits, void* stream) {
+  if (!h || !it || !meta || !x_support || !y_support || !x_target || !y_target || !result) return fail("null argument");
+  const int T = it->n_tasks;
+  if (T < 1 || T > h->maxT) return fail("n_tasks out of range");
+  if (it->num_steps < 1 || it->num_steps > h->S) return fail("num_steps out of range (must be <= inner_steps)");
+  if (it->tasks_global < T) return fail("tasks_global < n_tasks");
+  if ((it->target_mask & ((1u << it->num_steps) - 1u)) == 0) return fail("target_mask selects no target pass");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long* ys = (const long long*)y_support;
+  const long long* yt = (const long long*)y_target;
   h->last_tasks = T;
-  CK(cudaGetLastError());
+
+  if (!h->use_graphs || g_prof) {
+    // eager: launches go straight to the caller's stream (side streams fork / join through events)
+    const long long launches0 = g_launch_counter;
+    if (enqueue_iteration(h, it, meta, x_support, ys, x_target, yt, result, last_logits, st)) return 1;
+    h->last_launches = g_launch_counter - launches0;
+    CK(cudaGetLastError());
+    return 0;
+  }
+
+  // CUDA graph: the launch sequence depends only on the schedule and the buffer addresses -> capture once, replay.
+  const void* ptrs[7] = {meta, x_support, y_support, x_target, y_target, result, last_logits};
+  maml_b200_handle::GraphEntry* hit = nullptr;
+  for (auto& g : h->graphs)
+    if (memcmp(&g.it, it, sizeof(*it)) == 0 && memcmp(g.p, ptrs, sizeof(ptrs)) == 0) { hit = &g; break; }
+  if (!hit) {
+    if (h->graphs.size() >= 32) {           // evict the least recently used entry
+      size_t victim = 0;
+      for (size_t i = 1; i < h->graphs.size(); ++i) if (h->graphs[i].stamp < h->graphs[victim].stamp) victim = i;
+      cudaGraphExecDestroy(h->graphs[victim].exec);
+      h->graphs.erase(h->graphs.begin() + victim);
+    }
+    const long long launches0 = g_launch_counter;
+    CK(cudaStreamBeginCapture(h->s_cap, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue_iteration(h, it, meta, x_support, ys, x_target, yt, result, last_logits, h->s_cap);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->s_cap, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
+    if (e != cudaSuccess) return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    maml_b200_handle::GraphEntry ge;
+    ge.it = *it; memcpy(ge.p, ptrs, sizeof(ptrs)); ge.exec = nullptr; ge.launches = g_launch_counter - launches0; ge.stamp = 0;
+    e = cudaGraphInstantiate(&ge.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    h->graphs.push_back(ge);
+    hit = &h->graphs.back();
+  }
+  hit->stamp = ++h->graph_clock;
+  h->last_launches = hit->launches;
+  CK(cudaGraphLaunch(hit->exec, st));
   return 0;
 }
 

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
   }
   __syncthreads();
 
-  const float wscale = (a.scale_ptr ? *a.scale_ptr : 1.f);
+  const float wscale = a.scale;
   const float inv_n = 1.f / (float)n;
   for (int i = tid; i < n; i += 256) {
     float mx = logits[i * N];

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   constexpr int B_BYTES = NCOLS * 128;
   constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
   constexpr int NACC = 5;                       // 4 x hi*hi (round-robin over k-steps) + 1 x (lo*hi + hi*lo)
-  constexpr int TMEM_COLS = NCOLS <= 32 ? 256 : 512;   // power of two >= NACC * NCOLS
+  constexpr int TMEM_COLS = NCOLS <= 16 ? 128 : (NCOLS <= 48 ? 256 : 512);   // power of two >= NACC * NCOLS
   constexpr int PITCH = NCOLS + 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int task = blockIdx.y;
   const int j0 = blockIdx.x * 128;
-  const int kchunks = a.kc >> 5;
+  const int kchunks = (a.kc + 31) >> 5;        // a ragged last chunk (kc = 16 or 48) is zero-filled by TMA
   const int it0 = 9 * kchunks;
   const int nit = a.nsrc * it0;
 
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     asm volatile("bar.sync 1, 128;" ::: "memory");
     float* out = a.out + (long long)task * a.out_stride;
     const float* zh = a.zh ? a.zh + (long long)task * a.zh_stride : nullptr;
-    constexpr int PARTS = 128 / NCOLS;           // 2 for 64, 4 for 32
+    constexpr int PARTS = 128 / NCOLS;           // 2 for 64 and 48, 4 for 32, 8 for 16
     const int col = et % NCOLS, part = et / NCOLS;
     double s1 = 0.0, s2 = 0.0;
     for (int idx = et; idx < 128 * NCOLS; idx += 128) {
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     if (a.mode != CONV_PLAIN) {
       if (PARTS > 2) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (part >= 2 && part < PARTS) { atomicAdd(&sred[part - 2][col][0], s1); atomicAdd(&sred[part - 2][col][1], s2); }
+        if (part >= 2 && part < PARTS) { atomicAdd(&sred[part & 1][col][0], s1); atomicAdd(&sred[part & 1][col][1], s2); }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (et < NCOLS * 2) {
@@ -255,14 +255,18 @@ size_t tc_conv_smem_bytes(int ncols) { return (size_t)TC_STAGES * (2 * TC_A_BYTE
 int tc_conv_prepare() {
   cudaError_t e1 = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_conv_smem_bytes(64));
   cudaError_t e2 = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_conv_smem_bytes(32));
-  return (e1 == cudaSuccess && e2 == cudaSuccess) ? 0 : 1;
+  cudaError_t e3 = cudaFuncSetAttribute(conv_tc_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_conv_smem_bytes(48));
+  cudaError_t e4 = cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_conv_smem_bytes(16));
+  return (e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess && e4 == cudaSuccess) ? 0 : 1;
 }
 
 void launch_conv_tc(const TcMaps& maps, const TcConvArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_CONV, a.alg_flops, st);
   dim3 grid((a.rows + 127) / 128, a.tasks);
   if (a.ncols == 64) conv_tc_kernel<64><<<grid, 192, tc_conv_smem_bytes(64), st>>>(maps, a);
-  else conv_tc_kernel<32><<<grid, 192, tc_conv_smem_bytes(32), st>>>(maps, a);
+  else if (a.ncols == 48) conv_tc_kernel<48><<<grid, 192, tc_conv_smem_bytes(48), st>>>(maps, a);
+  else if (a.ncols == 32) conv_tc_kernel<32><<<grid, 192, tc_conv_smem_bytes(32), st>>>(maps, a);
+  else conv_tc_kernel<16><<<grid, 192, tc_conv_smem_bytes(16), st>>>(maps, a);
   CUDA_CHECK_LAUNCH();
 }
 

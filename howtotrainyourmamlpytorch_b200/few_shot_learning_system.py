@@ -285,12 +285,20 @@ class MAMLFewShotClassifier(nn.Module):
         return self._engine
 
     def _stage(self, key, tensor, dtype):
-        """Pinned host staging + async H2D copy (replaces the reference's unpinned synchronous
-        ``torch.Tensor(x).float().to(device)``, :355-358)."""
-        t = torch.as_tensor(np.asarray(tensor) if not torch.is_tensor(tensor) else tensor)
+        """Pinned host staging + async H2D copy into a PERSISTENT device buffer (replaces the reference's unpinned
+        synchronous ``torch.Tensor(x).float().to(device)``, :355-358).  Persistent addresses keep the engine's
+        CUDA-graph cache hot.  Labels follow the reference's float -> long conversion (:357-358)."""
+        t = tensor if torch.is_tensor(tensor) else torch.as_tensor(np.asarray(tensor))
         if t.device.type == "cuda":
+            if t.dtype == dtype and t.is_contiguous() and t.device == self.device:
+                return t
+            if dtype == torch.int64 and t.is_floating_point():
+                return t.to(self.device).long().contiguous()
             return t.to(self.device, dtype).contiguous()
-        t = t.to(dtype)
+        if dtype == torch.int64:
+            t = t.to(torch.float32).long() if t.is_floating_point() else t.long()
+        else:
+            t = t.to(dtype)
         buf = self._staging.get(key)
         if buf is None or buf[0].shape != t.shape:
             buf = (torch.empty(t.shape, dtype=dtype).pin_memory(), torch.empty(t.shape, dtype=dtype, device=self.device))
@@ -306,15 +314,18 @@ class MAMLFewShotClassifier(nn.Module):
                 "MAMLFewShotClassifier needs a CUDA (sm_100a) device: the hot path has no CPU fallback")
         xs = self._stage("xs", x_support, torch.float32)
         xt = self._stage("xt", x_target, torch.float32)
-        ys = self._stage("ys", y_support, torch.float32).long()      # float -> long like the reference
-        yt = self._stage("yt", y_target, torch.float32).long()
+        ys = self._stage("ys", y_support, torch.int64)
+        yt = self._stage("yt", y_target, torch.int64)
         B = xs.shape[0]
         n_t = xt.shape[1] * xt.shape[2]
         N = int(self.args.num_classes_per_set)
         eng = self._ensure_engine(B)
         num_steps, second, mask, weights, w_msl = self._schedule(epoch, training_phase)
         task_offset, B_global = sharding.shard_of(self.rank, self.world_size, B)
-        logits = torch.empty(B, n_t, N, dtype=torch.float32, device=self.device)
+        logits = self._staging.get(("logits", B))
+        if logits is None:
+            logits = torch.empty(B, n_t, N, dtype=torch.float32, device=self.device)
+            self._staging[("logits", B)] = logits
         with torch.cuda.device(self.device):
             eng.fwd_bwd(n_tasks=B, task_offset=task_offset, tasks_global=B_global, num_steps=num_steps,
                         second_order=second, training=training_phase, target_mask=mask, target_weight=weights,
