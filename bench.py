@@ -199,6 +199,8 @@ def main():
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch-size", type=int, default=None, help="tasks per GPU (default: the config's batch_size)")
+    ap.add_argument("--no-flush", action="store_true", help="diagnostic: do not flush L2 between timed steps")
+    ap.add_argument("--sync-each-step", action="store_true", help="diagnostic: synchronize after every timed step")
     cli = ap.parse_args()
 
     import torch
@@ -246,7 +248,9 @@ def main():
         return model._run(dev_batches[i % n_pool], 0, training_phase=True, apply_update=True)
 
     # ---------------- device-resident throughput (value)
-    for i in range(W):
+    # warm-up: at least W steps and at least one pass over every distinct episode batch (the engine captures one
+    # CUDA graph per distinct set of buffer addresses; captures belong to warm-up, not to the timed region)
+    for i in range(max(W, n_pool)):
         device_step(i)
     barrier()
     sampler = ClockSampler(local_rank)
@@ -255,10 +259,13 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     wall0 = time.perf_counter()
     for i in range(K):
-        flush.zero_()
+        if not cli.no_flush:
+            flush.zero_()
         ev[i][0].record()
         device_step(W + i)
         ev[i][1].record()
+        if cli.sync_each_step:
+            torch.cuda.synchronize()
     barrier()
     wall_dev = time.perf_counter() - wall0
     step_ms = [a.elapsed_time(b) for a, b in ev]
@@ -266,7 +273,7 @@ def main():
     launches_per_step = model._engine.last_launch_count() + 1 + (1 if args.per_step_bn_statistics else 0)
 
     # ---------------- end to end through the public API with host buffers (e2e)
-    for i in range(3):
+    for i in range(max(3, W)):
         model.run_train_iter(pinned_batches[i % n_pool], 0)
     barrier()
     t0 = time.perf_counter()
@@ -329,6 +336,8 @@ def main():
             "roofline": roofline,
             "gflop_per_task": fpt / 1e9,
             "wall_s_device_loop": wall_dev,
+            "step_ms": {"min": min(step_ms), "median": sorted(step_ms)[len(step_ms) // 2], "max": max(step_ms)},
+            "workspace_mib": eng.workspace_bytes / 2 ** 20,
             "last_loss": float(losses["loss"]),
         }
         if not cli.no_cpu_baseline and world == 1:

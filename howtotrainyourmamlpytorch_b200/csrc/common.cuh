@@ -136,7 +136,9 @@ struct HeadArgs {
   const float* uW; const float* ub; long long u_stride;           // tangent direction (HEAD_TANGENT)
   const long long* y; long long y_stride;         // labels [n]
   float scale;                                    // loss weight folded into dlogits (1 for the support loss)
-  float* gW; float* gb; long long g_stride;       // gradient (or H*u) output for the head tensors
+  float* gW; float* gb; long long g_stride;       // gradient (or H*u) output for the head tensors (chunk 0)
+  long long g_chunk_stride;                       // stride between the row-group chunks of gW / gb
+  int rows_per_cta;                               // rows of the batch handled by one CTA (grid.x = row groups)
   float* df; long long df_stride;                 // [n][D] gradient (or its tangent) w.r.t. features
   float* loss_out; long long loss_stride;         // per-task scalar (HEAD_TARGET_FWD)
   float* logits_out; long long logits_stride;     // nullable [n][N]

@@ -66,7 +66,8 @@ struct PassSet {            // activation buffers of one kind of pass (support: 
   CUtensorMap dz_map[MAML_MAX_LAYERS][2];
 };
 
-struct ChunkPlan { int rows_per_chunk[MAML_MAX_LAYERS]; int nchunks[MAML_MAX_LAYERS]; PartialDesc pd; long long size; };
+struct ChunkPlan { int rows_per_chunk[MAML_MAX_LAYERS]; int nchunks[MAML_MAX_LAYERS]; PartialDesc pd; long long size; int head_groups; };
+static const int HEAD_ROWS_PER_CTA = 16;
 
 struct maml_b200_handle {
   maml_b200_config cfg;
@@ -99,6 +100,7 @@ struct maml_b200_handle {
   unsigned long long graph_clock = 0;
   // tensor-core path (blocks l >= 1 when F % 32 == 0)
   bool use_tc = false;
+  int tc_bo_mode = 0;      // 0: row-shifted UMMA descriptors keep base_offset = 0 (correct on B200); 1: experiment (env MAML_B200_TC_BO)
   float *pack_theta = nullptr, *pack_u = nullptr;       // [4 planes][steps][T][(L-1)*9*F*F]
   long long pack_theta_plane = 0, pack_u_plane = 0, pack_task = 0;
   CUtensorMap theta_map[4], u_map[4];                   // planes: W hi, W lo, WT hi, WT lo
@@ -162,7 +164,7 @@ static void plan_chunks(maml_b200_handle* h, int n, ChunkPlan* cp) {
     const long long rows = (long long)n * h->geo[l].G;
     int nch, rpc;
     if (l == 0) {
-      nch = (int)std::min<long long>(256, std::max<long long>(1, (rows + 63) / 64));
+      nch = (int)std::min<long long>(512, std::max<long long>(1, (rows + 63) / 64));
     } else {
       nch = (int)std::min<long long>(64, std::max<long long>(1, (rows + 127) / 128));
     }
@@ -174,8 +176,13 @@ static void plan_chunks(maml_b200_handle* h, int n, ChunkPlan* cp) {
     cp->pd.off[2 * l + 1] = off + 9LL * h->geo[l].cin * h->F; cp->pd.cstride[2 * l + 1] = cs; cp->pd.nchunks[2 * l + 1] = nch;
     off += cs * nch;
   }
-  cp->pd.off[2 * h->L] = off; cp->pd.cstride[2 * h->L] = 0; cp->pd.nchunks[2 * h->L] = 1; off += (long long)h->N * h->D;
-  cp->pd.off[2 * h->L + 1] = off; cp->pd.cstride[2 * h->L + 1] = 0; cp->pd.nchunks[2 * h->L + 1] = 1; off += h->N;
+  // head: one gradient chunk per row group of the batch (gW [N][D] followed by gb [N] inside each chunk)
+  const int hg = (n + HEAD_ROWS_PER_CTA - 1) / HEAD_ROWS_PER_CTA;
+  const long long hcs = (long long)h->N * h->D + h->N;
+  cp->head_groups = hg;
+  cp->pd.off[2 * h->L] = off; cp->pd.cstride[2 * h->L] = hcs; cp->pd.nchunks[2 * h->L] = hg;
+  cp->pd.off[2 * h->L + 1] = off + (long long)h->N * h->D; cp->pd.cstride[2 * h->L + 1] = hcs; cp->pd.nchunks[2 * h->L + 1] = hg;
+  off += hcs * hg;
   cp->size = rup(off, 64);
   cp->pd.task_stride = cp->size;
 }
@@ -216,8 +223,9 @@ static int make_map(CUtensorMap* m, const float* base, long long rows, int cols,
 static int make_pass_maps(maml_b200_handle* h, PassSet& ps, bool has_dz) {
   for (int l = 1; l < h->L; ++l) {
     for (int pl = 0; pl < 2; ++pl) {
-      if (make_map(&ps.ain_map[l][pl], ps.ain_base[l] + (pl + 1) * ps.ain_plane[l], ps.ain_plane[l] / h->F, h->F, 128)) return 1;
-      if (has_dz && make_map(&ps.dz_map[l][pl], ps.dz_base[l] + (pl + 1) * ps.dz_plane[l], ps.dz_plane[l] / h->F, h->F, 128)) return 1;
+      const int rp = tc_conv_rpad(h->geo[l].gw);       // one TMA box = the 128-row tile plus its halo
+      if (make_map(&ps.ain_map[l][pl], ps.ain_base[l] + (pl + 1) * ps.ain_plane[l], ps.ain_plane[l] / h->F, h->F, rp)) return 1;
+      if (has_dz && make_map(&ps.dz_map[l][pl], ps.dz_base[l] + (pl + 1) * ps.dz_plane[l], ps.dz_plane[l] / h->F, h->F, rp)) return 1;
     }
   }
   return 0;
@@ -310,7 +318,6 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   if (cfg->n_way < 2 || cfg->n_way > 32) return fail("n_way must be in [2, 32]");
   const int n_s = cfg->n_way * cfg->k_shot, n_t = cfg->n_way * cfg->t_target;
   if (n_s < 1 || n_t < 1 || n_s > 128 || n_t > 128) return fail("N*K and N*T must be in [1, 128]");
-  if ((long long)5 * std::max(n_s, n_t) * cfg->n_way * 4 > 48 * 1024) return fail("head tile does not fit shared memory");
   {
     int hh = cfg->height, ww = cfg->width;
     for (int l = 0; l < cfg->num_stages; ++l) { if (hh < 2 || ww < 2) return fail("image too small for num_stages"); hh /= 2; ww /= 2; }
@@ -322,7 +329,10 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   build_geometry(h);
   build_layout(h);
   // tensor-core (tcgen05 / TMA, 3xTF32) convolutions for blocks l >= 1; reserved bit 1 forces the fp32 FFMA kernels (tests)
-  h->use_tc = (h->L > 1) && !(cfg->reserved & 2);      // F in {16, 32, 48, 64}: ragged K chunks are zero-filled by TMA
+  h->use_tc = (h->L > 1) && !(cfg->reserved & 2);
+  if (const char* bo = getenv("MAML_B200_TC_BO")) h->tc_bo_mode = atoi(bo);
+  for (int l = 1; l < h->L && h->use_tc; ++l)
+    if (tc_conv_rpad(h->geo[l].gw) > 256 || tc_conv_ring(h->F, h->geo[l].gw) < 2) h->use_tc = false;   // image too wide for one halo box      // F in {16, 32, 48, 64}: ragged K chunks are zero-filled by TMA
   plan_chunks(h, h->n_s, &h->plan_sup);
   plan_chunks(h, h->n_t, &h->plan_tgt);
   Bump sz{nullptr, 0};
@@ -450,6 +460,7 @@ static void tc_conv(maml_b200_handle* h, int l, int n, int nsrc, const TcOp* ops
   TcMaps maps;
   TcConvArgs a{};
   a.nsrc = nsrc; a.kc = h->F; a.rows = n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.ncols = h->F; a.mode = mode; a.tasks = T;
+  a.halo = g.gw + 1; a.rpad = tc_conv_rpad(g.gw); a.nb = tc_conv_ring(h->F, g.gw); a.bo_mode = h->tc_bo_mode; a.timeline = getenv("MAML_B200_TC_TIMELINE") ? 1 : 0;
   for (int s = 0; s < nsrc; ++s) {
     maps.m[s * 4 + 0] = ops[s].a_maps[0]; maps.m[s * 4 + 1] = ops[s].a_maps[1];
     maps.m[s * 4 + 2] = ops[s].b_maps[ops[s].b_pair]; maps.m[s * 4 + 3] = ops[s].b_maps[ops[s].b_pair + 1];
@@ -619,6 +630,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
     a.uW = u + h->pl.fcw_off; a.ub = u + h->pl.fcb_off; a.u_stride = h->Ppad;
     a.y = y_support; a.y_stride = h->n_s;
     a.gW = h->sup_partial + cp.pd.off[2 * h->L]; a.gb = h->sup_partial + cp.pd.off[2 * h->L + 1]; a.g_stride = cp.pd.task_stride;
+    a.g_chunk_stride = cp.pd.cstride[2 * h->L]; a.rows_per_cta = HEAD_ROWS_PER_CTA;
     a.df = DP(tn, h->L - 1, 0); a.df_stride = STRIDE(tn, dp, h->L - 1);
     a.tasks = T;
     launch_head(a, st);
@@ -732,6 +744,7 @@ static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it,
       a.y = ys; a.y_stride = h->n_s;
       a.gW = h->sup_partial + h->plan_sup.pd.off[2 * h->L]; a.gb = h->sup_partial + h->plan_sup.pd.off[2 * h->L + 1];
       a.g_stride = h->plan_sup.pd.task_stride;
+      a.g_chunk_stride = h->plan_sup.pd.cstride[2 * h->L]; a.rows_per_cta = HEAD_ROWS_PER_CTA;
       a.df = DP(h->sup, h->L - 1, s); a.df_stride = STRIDE(h->sup, dp, h->L - 1);
       a.tasks = T;
       launch_head(a, st);
@@ -751,7 +764,7 @@ static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it,
       a.f = AIN(h->tgt, h->L, ts); a.f_stride = STRIDE(h->tgt, ain, h->L);
       a.Wfc = th_next + h->pl.fcw_off; a.bfc = th_next + h->pl.fcb_off; a.theta_stride = h->Ppad;
       a.y = yt; a.y_stride = h->n_t;
-      a.loss_out = h->losses + s; a.loss_stride = MAML_MAX_STEPS;
+      a.loss_out = h->losses + s; a.loss_stride = MAML_MAX_STEPS; a.rows_per_cta = HEAD_ROWS_PER_CTA;
       if (s == last_t) {
         a.logits_out = last_logits; a.logits_stride = (long long)h->n_t * h->N;
         a.correct_out = h->correct; a.correct_stride = 1;
@@ -764,6 +777,7 @@ static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it,
         bqa.logits_out = nullptr; bqa.correct_out = nullptr; bqa.loss_out = nullptr;
         bqa.gW = h->tgt_partial + h->plan_tgt.pd.off[2 * h->L]; bqa.gb = h->tgt_partial + h->plan_tgt.pd.off[2 * h->L + 1];
         bqa.g_stride = h->plan_tgt.pd.task_stride;
+        bqa.g_chunk_stride = h->plan_tgt.pd.cstride[2 * h->L];
         bqa.df = DP(h->tgt, h->L - 1, ts); bqa.df_stride = STRIDE(h->tgt, dp, h->L - 1);
         launch_head(bqa, ts_);
         backward_pass(h, h->tgt, ts, th_next, s + 1, meta, s, PASS_TGT_FWD, PASS_TGT_BWD, h->tgt_partial, h->plan_tgt, T, ts_, false);
@@ -956,6 +970,15 @@ extern "C" int64_t maml_b200_debug_read(maml_b200_handle* h, const char* name, i
   else if (nm == "tgrad") { if (step >= 0 && step < h->S) { src = h->tgrad + (long long)step * TP + (long long)task * h->Ppad; count = h->pl.P; ok = true; } }
   else if (nm == "tbar") { src = h->tbar + (long long)task * h->Ppad; count = h->pl.P; ok = true; }
   else if (nm == "u") { src = h->u + (long long)task * h->Ppad; count = h->pl.P; ok = true; }
+  else if (nm == "tc_timeline") {
+    static long long tl[16]; static float tf[16];
+    cudaDeviceSynchronize();
+    if (tc_read_timeline(tl)) { fail("timeline read failed"); return -1; }
+    for (int i = 0; i < 16; ++i) tf[i] = (float)(tl[i] - tl[0]);
+    const long long ncopy = std::min<long long>(16, capacity);
+    if (host_out && ncopy > 0) memcpy(host_out, tf, ncopy * sizeof(float));
+    return 16;
+  }
   else if (nm == "losses") { src = h->losses + (long long)task * MAML_MAX_STEPS; count = MAML_MAX_STEPS; ok = true; }
   if (!ok) { fail("unknown debug tap / bad index: " + nm); return -1; }
   const long long ncopy = std::min<long long>(count, capacity);

@@ -15,28 +15,33 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
+  // grid (row groups, tasks): everything except the weight gradient is row-local, so each CTA owns `rows_per_cta`
+  // rows of the batch and writes its own chunk of (gW, gb); the parameter-space kernel sums the chunks in order.
   extern __shared__ float smh[];
-  __shared__ float s_rowloss[128];
-  __shared__ float s_rowcorrect[128];
-  const int task = blockIdx.x;
+  __shared__ float s_rowloss[64];
+  __shared__ float s_rowcorrect[64];
+  const int task = blockIdx.y;
   const int n = a.n, N = a.N, D = a.D;
+  const int row0 = blockIdx.x * a.rows_per_cta;
+  const int nl = min(a.rows_per_cta, n - row0);          // local rows
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int R = a.rows_per_cta;
   float* logits = smh;
-  float* prob = smh + n * N;
-  float* dl = smh + 2 * n * N;
-  float* ldot = smh + 3 * n * N;
-  float* dldot = smh + 4 * n * N;
+  float* prob = smh + R * N;
+  float* dl = smh + 2 * R * N;
+  float* ldot = smh + 3 * R * N;
+  float* dldot = smh + 4 * R * N;
   const bool tan = (a.mode == HEAD_TANGENT);
 
-  const float* f = a.f + (long long)task * a.f_stride;
+  const float* f = a.f + (long long)task * a.f_stride + (long long)row0 * D;
   const float* W = a.Wfc + (long long)task * a.theta_stride;
   const float* b = a.bfc + (long long)task * a.theta_stride;
-  const float* fd = tan ? a.fdot + (long long)task * a.fdot_stride : nullptr;
+  const float* fd = tan ? a.fdot + (long long)task * a.fdot_stride + (long long)row0 * D : nullptr;
   const float* uW = tan ? a.uW + (long long)task * a.u_stride : nullptr;
   const float* ub = tan ? a.ub + (long long)task * a.u_stride : nullptr;
-  const long long* y = a.y + (long long)task * a.y_stride;
+  const long long* y = a.y + (long long)task * a.y_stride + row0;
 
-  for (int o = warp; o < n * N; o += 8) {
+  for (int o = warp; o < nl * N; o += 8) {
     const int i = o / N, k = o - i * N;
     float s = 0.f, sd = 0.f;
     for (int d = lane; d < D; d += 32) {
@@ -55,7 +60,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
 
   const float wscale = a.scale;
   const float inv_n = 1.f / (float)n;
-  for (int i = tid; i < n; i += 256) {
+  for (int i = tid; i < nl; i += 256) {
     float mx = logits[i * N];
     int am = 0;
     for (int k = 1; k < N; ++k) {
@@ -78,33 +83,34 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
         const float p = prob[i * N + k];
         dldot[i * N + k] = (p * ldot[i * N + k] - p * pd) * inv_n;
       }
-    if (i < 128) { s_rowloss[i] = lse - logits[i * N + yi]; s_rowcorrect[i] = (am == yi) ? 1.f : 0.f; }
+    s_rowloss[i] = lse - logits[i * N + yi];
+    s_rowcorrect[i] = (am == yi) ? 1.f : 0.f;
   }
   __syncthreads();
 
   if (a.mode == HEAD_TARGET_FWD) {
     if (tid == 0) {
       float ls = 0.f, cs = 0.f;
-      for (int i = 0; i < n; ++i) { ls += s_rowloss[i]; cs += s_rowcorrect[i]; }
-      a.loss_out[(long long)task * a.loss_stride] = ls * inv_n;
-      if (a.correct_out) a.correct_out[(long long)task * a.correct_stride] = cs;
+      for (int i = 0; i < nl; ++i) { ls += s_rowloss[i]; cs += s_rowcorrect[i]; }
+      atomicAdd(&a.loss_out[(long long)task * a.loss_stride], ls * inv_n);       // zeroed at iteration start
+      if (a.correct_out) atomicAdd(&a.correct_out[(long long)task * a.correct_stride], cs);
     }
     if (a.logits_out) {
-      float* lo = a.logits_out + (long long)task * a.logits_stride;
-      for (int o = tid; o < n * N; o += 256) lo[o] = logits[o];
+      float* lo = a.logits_out + (long long)task * a.logits_stride + (long long)row0 * N;
+      for (int o = tid; o < nl * N; o += 256) lo[o] = logits[o];
     }
     return;
   }
 
-  float* gW = a.gW + (long long)task * a.g_stride;
-  float* gb = a.gb + (long long)task * a.g_stride;
+  float* gW = a.gW + (long long)task * a.g_stride + (long long)blockIdx.x * a.g_chunk_stride;
+  float* gb = a.gb + (long long)task * a.g_stride + (long long)blockIdx.x * a.g_chunk_stride;
   for (int o = tid; o < N * D; o += 256) {
     const int k = o / D, d = o - k * D;
     float s = 0.f;
     if (!tan) {
-      for (int i = 0; i < n; ++i) s = fmaf(dl[i * N + k], f[(long long)i * D + d], s);
+      for (int i = 0; i < nl; ++i) s = fmaf(dl[i * N + k], f[(long long)i * D + d], s);
     } else {
-      for (int i = 0; i < n; ++i)
+      for (int i = 0; i < nl; ++i)
         s += dldot[i * N + k] * f[(long long)i * D + d] + dl[i * N + k] * fd[(long long)i * D + d];
     }
     gW[o] = s;
@@ -112,11 +118,11 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
   if (tid < N) {
     float s = 0.f;
     const float* src = tan ? dldot : dl;
-    for (int i = 0; i < n; ++i) s += src[i * N + tid];
+    for (int i = 0; i < nl; ++i) s += src[i * N + tid];
     gb[tid] = s;
   }
-  float* df = a.df + (long long)task * a.df_stride;
-  for (int o = tid; o < n * D; o += 256) {
+  float* df = a.df + (long long)task * a.df_stride + (long long)row0 * D;
+  for (int o = tid; o < nl * D; o += 256) {
     const int i = o / D, d = o - i * D;
     float s = 0.f;
     if (!tan) {
@@ -131,7 +137,8 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
 
 void launch_head(const HeadArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_HEAD, 0.0, st);
-  const size_t smem = (size_t)5 * a.n * a.N * sizeof(float);
-  head_kernel<<<a.tasks, 256, smem, st>>>(a);
+  const size_t smem = (size_t)5 * a.rows_per_cta * a.N * sizeof(float);
+  dim3 grid((a.n + a.rows_per_cta - 1) / a.rows_per_cta, a.tasks);
+  head_kernel<<<grid, 256, smem, st>>>(a);
   CUDA_CHECK_LAUNCH();
 }

@@ -18,7 +18,7 @@
 // (18 accumulations each instead of 216), the small terms get a fifth, and the epilogue adds the five with
 // IEEE fp32 adds.
 //
-// CTA = one 128-row M tile x all N (<= 64) columns.  Warp roles: warp 0 = TMA producer (one thread),
+// CTA = one 128-row M tile x all N (<= 64) columns.  Warp roles: warp 0 / warp 6 = TMA producers for B / A (one thread each),
 // warp 1 = TMEM allocator + MMA issuer (one thread), warps 2..5 = epilogue (TMEM -> registers -> shared ->
 // coalesced global store, + bias, + fp64 BatchNorm statistics).  4-stage smem ring, mbarrier full/empty,
 // tcgen05.commit frees stages and publishes the accumulator.
@@ -28,7 +28,6 @@
 
 namespace {
 
-constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = 128 * 128;          // 128 rows x 32 fp32 (one 128B swizzle span per row)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -64,6 +63,10 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tc_mma_tf32_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
 //   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused: one swizzle atom along K) | [32,46) SBO >> 4 = 1024 B
 //   (8 rows x 128 B) | [46,48) version = 1 | [61,64) layout type = 2 (SWIZZLE_128B)
@@ -85,16 +88,32 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 
 __device__ __forceinline__ int tap_shift_tc(int tap, int gw) { return (tap / 3 - 1) * gw + (tap % 3 - 1); }
 
+// K-major SWIZZLE_128B descriptor whose start is `row_off` rows into a 1024B-aligned tile.  Measured on B200: the
+// 128B swizzle XOR is a function of the ABSOLUTE shared-memory address bits [7,10) (as for TMA writes), so a start
+// address moved by row_off * 128 B addresses rows row_off .. row_off+127 of the tile correctly with the
+// matrix-base-offset field left at 0; setting base_offset = row_off mod 8 (bo_mode = 1) gives wrong results.
+// This is what lets ONE halo tile serve all nine filter taps.
+__device__ __forceinline__ uint64_t make_desc_sw128_rows(uint32_t tile_base, int row_off, int kbyte, int bo_mode) {
+  uint64_t d = make_desc_sw128(tile_base + (uint32_t)row_off * 128u + (uint32_t)kbyte);
+  if (bo_mode) d |= (uint64_t)(row_off & 7) << 49;
+  return d;
+}
+
+// debug timeline (clock64 at pipeline milestones of CTA (0,0)); written only when TcConvArgs::timeline != 0
+__device__ long long g_tc_timeline[16];
+#define TC_MARK(i) do { if (a.timeline && blockIdx.x == 0 && blockIdx.y == 0) g_tc_timeline[i] = clock64(); } while (0)
+
 template <int NCOLS>
-__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvArgs a) {
+__global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvArgs a) {
   constexpr int B_BYTES = NCOLS * 128;
-  constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
-  constexpr int NACC = 5;                       // 4 x hi*hi (round-robin over k-steps) + 1 x (lo*hi + hi*lo)
+  constexpr int BSTAGE = 2 * B_BYTES;            // B_hi + B_lo of one (tap, k-chunk)
+  constexpr int NACC = 5;                        // 4 x hi*hi (round-robin over k-steps) + 1 x (lo*hi + hi*lo)
   constexpr int TMEM_COLS = NCOLS <= 16 ? 128 : (NCOLS <= 48 ? 256 : 512);   // power of two >= NACC * NCOLS
   constexpr int PITCH = NCOLS + 1;
+  constexpr int MAXB = 8;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], accum_bar;
+  __shared__ uint64_t a_full[2], a_empty[2], b_full[MAXB], b_empty[MAXB], accum_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ int row_ok[128];
   __shared__ double sred[2][NCOLS][2];
@@ -102,12 +121,16 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int task = blockIdx.y;
   const int j0 = blockIdx.x * 128;
-  const int kchunks = (a.kc + 31) >> 5;        // a ragged last chunk (kc = 16 or 48) is zero-filled by TMA
-  const int it0 = 9 * kchunks;
-  const int nit = a.nsrc * it0;
+  if (threadIdx.x == 0) TC_MARK(0);
+  const int kchunks = (a.kc + 31) >> 5;          // a ragged last chunk (kc = 16 or 48) is zero-filled by TMA
+  const int nph = a.nsrc * kchunks;              // A phases: (source, k-chunk); 9 taps each
+  const int nb = a.nb;                           // B ring depth
+  const int abuf = a.rpad * 128;                 // bytes of one A halo buffer (hi or lo)
+  uint8_t* bring = smem + 4 * (size_t)abuf;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < nb; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     mbar_init(&accum_bar, 1);
     fence_barrier_init();
   }
@@ -119,26 +142,40 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  if (threadIdx.x == 0) TC_MARK(1);
 
-  if (warp == 0) {
+  if (warp == 6) {
     if (lane == 0) {
-      // ===== TMA producer =====
-      for (int it = 0; it < nit; ++it) {
-        const int stage = it % TC_STAGES;
-        const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        const int s = it / it0;
-        const int local = it - s * it0;
-        const int tap = local / kchunks;
-        const int kc0 = (local - tap * kchunks) << 5;
-        const int arow = a.a_row_base[s] + task * a.a_task_rows[s] + j0 + a.sign[s] * tap_shift_tc(tap, a.gw);
-        const int brow = a.b_row_base[s] + task * a.b_task_rows[s] + tap * NCOLS;
-        const uint32_t st = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-        tma_load_2d(st, &maps.m[s * 4 + 0], &full_bar[stage], kc0, arow);
-        tma_load_2d(st + TC_A_BYTES, &maps.m[s * 4 + 1], &full_bar[stage], kc0, arow);
-        tma_load_2d(st + 2 * TC_A_BYTES, &maps.m[s * 4 + 2], &full_bar[stage], kc0, brow);
-        tma_load_2d(st + 2 * TC_A_BYTES + B_BYTES, &maps.m[s * 4 + 3], &full_bar[stage], kc0, brow);
+      // ===== TMA producer A: per phase (source, k-chunk) ONE halo tile of A (hi, lo); all 9 taps read it at row
+      // offsets.  Double-buffered, so phase ph+1 streams in while the MMAs of phase ph run.
+      for (int ph = 0; ph < nph; ++ph) {
+        const int s = ph / kchunks;
+        const int kc0 = (ph - s * kchunks) << 5;
+        const int ab = ph & 1;
+        mbar_wait(&a_empty[ab], (((uint32_t)ph >> 1) & 1u) ^ 1u);
+        const int arow = a.a_row_base[s] + task * a.a_task_rows[s] + j0 - a.halo;
+        const uint32_t ad = smem_u32(smem + (size_t)ab * 2 * abuf);
+        mbar_arrive_expect_tx(&a_full[ab], 2u * (uint32_t)abuf);
+        tma_load_2d(ad, &maps.m[s * 4 + 0], &a_full[ab], kc0, arow);
+        tma_load_2d(ad + abuf, &maps.m[s * 4 + 1], &a_full[ab], kc0, arow);
+      }
+    }
+  } else if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer B: one (B_hi, B_lo) stage per (phase, tap) through the ring
+      int stage = 0; uint32_t bphase = 0;
+      for (int ph = 0; ph < nph; ++ph) {
+        const int s = ph / kchunks;
+        const int kc0 = (ph - s * kchunks) << 5;
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&b_empty[stage], bphase ^ 1u);
+          const int brow = a.b_row_base[s] + task * a.b_task_rows[s] + tap * NCOLS;
+          const uint32_t bd = smem_u32(bring + (size_t)stage * BSTAGE);
+          mbar_arrive_expect_tx(&b_full[stage], BSTAGE);
+          tma_load_2d(bd, &maps.m[s * 4 + 2], &b_full[stage], kc0, brow);
+          tma_load_2d(bd + B_BYTES, &maps.m[s * 4 + 3], &b_full[stage], kc0, brow);
+          if (++stage == nb) { stage = 0; bphase ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -147,32 +184,63 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), both K-major,
       // N>>3 at bit 17, M>>4 at bit 24
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOLS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      for (int it = 0; it < nit; ++it) {
-        const int stage = it % TC_STAGES;
-        const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t st = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+      // The issuing thread is the serial resource of this kernel: descriptors are built once per phase / stage and
+      // advanced with 64-bit adds on the 16-byte-unit address field (K step: +32 B = +2; tap: row_off * 128 B).
+      const uint64_t desc_base = make_desc_sw128(0);
+      int stage = 0; uint32_t bphase = 0; int kstep = 0;
+      for (int ph = 0; ph < nph; ++ph) {
+        const int s = ph / kchunks;
+        const int ab = ph & 1;
+        mbar_wait(&a_full[ab], ((uint32_t)ph >> 1) & 1u);
+        if (ph == 0) TC_MARK(2);
+        const uint32_t a_hi = smem_u32(smem + (size_t)ab * 2 * abuf);
+        const uint64_t ahd = desc_base + (uint64_t)(a_hi >> 4);
+        const uint64_t ald = ahd + (uint64_t)(abuf >> 4);
+        const int sgn = a.sign[s];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {          // 4 x UMMA_K(8 tf32 = 32 B) per 128 B swizzle span
-          const uint64_t ah = make_desc_sw128(st + k * 32);
-          const uint64_t al = make_desc_sw128(st + TC_A_BYTES + k * 32);
-          const uint64_t bh = make_desc_sw128(st + 2 * TC_A_BYTES + k * 32);
-          const uint64_t bl = make_desc_sw128(st + 2 * TC_A_BYTES + B_BYTES + k * 32);
-          const int kstep = it * 4 + k;
-          tc_mma_tf32(tmem_base + 4 * NCOLS, al, bh, idesc, kstep > 0 ? 1u : 0u);
-          tc_mma_tf32(tmem_base + 4 * NCOLS, ah, bl, idesc, 1u);
-          tc_mma_tf32(tmem_base + (uint32_t)(kstep & 3) * NCOLS, ah, bh, idesc, kstep >= 4 ? 1u : 0u);
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&b_full[stage], bphase);
+          if (ph == 0 && tap == 0) TC_MARK(3);
+          if (ph == 1 && tap == 0) TC_MARK(4);
+          tc_fence_after();
+          const int row_off = a.halo + sgn * ((tap / 3 - 1) * a.gw + (tap % 3 - 1));    // in [0, 2 * halo]
+          const uint64_t ah0 = ahd + (uint64_t)(row_off * 8);
+          const uint64_t al0 = ald + (uint64_t)(row_off * 8);
+          const uint64_t bh0 = desc_base + (uint64_t)(smem_u32(bring + (size_t)stage * BSTAGE) >> 4);
+          const uint64_t bl0 = bh0 + (uint64_t)(B_BYTES >> 4);
+          if (kstep == 0) {
+            // first four k-steps initialise the five accumulators
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              tc_mma_tf32(tmem_base + 4 * NCOLS, al0 + 2 * k, bh0 + 2 * k, idesc, k > 0 ? 1u : 0u);
+              tc_mma_tf32_acc(tmem_base + 4 * NCOLS, ah0 + 2 * k, bl0 + 2 * k, idesc);
+              tc_mma_tf32(tmem_base + (uint32_t)k * NCOLS, ah0 + 2 * k, bh0 + 2 * k, idesc, 0u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              tc_mma_tf32_acc(tmem_base + 4 * NCOLS, al0 + 2 * k, bh0 + 2 * k, idesc);
+              tc_mma_tf32_acc(tmem_base + 4 * NCOLS, ah0 + 2 * k, bl0 + 2 * k, idesc);
+              tc_mma_tf32_acc(tmem_base + (uint32_t)k * NCOLS, ah0 + 2 * k, bh0 + 2 * k, idesc);
+            }
+          }
+          kstep += 4;
+          tc_commit(&b_empty[stage]);            // frees this B stage once the MMAs above have read it
+          if (++stage == nb) { stage = 0; bphase ^= 1u; }
         }
-        tc_commit(&empty_bar[stage]);            // frees this smem stage once the MMAs above have read it
+        tc_commit(&a_empty[ab]);                 // A halo buffer pair reusable after this phase's MMAs
       }
-      tc_commit(&accum_bar);                     // accumulator complete
+      TC_MARK(5);
+      tc_commit(&accum_bar);                     // accumulators complete
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4.  Thread (q, lane) owns tile row r = 32 q + lane:
+    // it sums the five accumulators, adds the bias and stores its 4*NCOLS contiguous bytes straight to global;
+    // a shared-memory copy of the tile is kept only when BatchNorm statistics are wanted (column sums).
     const int et = threadIdx.x - 64;             // 0..127
     const int q = warp & 3;
-    const int r = q * 32 + lane;                 // tile row owned by this thread in TMEM
+    const int r = q * 32 + lane;
+    __shared__ float s_bias[NCOLS];
     {
       const int row = j0 + et;
       int ok = 0;
@@ -182,11 +250,16 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
         ok = (yy >= 1 && yy <= a.h && xx >= 1 && xx <= a.w) ? 1 : 0;
       }
       row_ok[et] = ok;
+      if (et < NCOLS) s_bias[et] = a.bias ? a.bias[(long long)task * a.bias_stride + et] : 0.f;
     }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     mbar_wait(&accum_bar, 0);
+    if (et == 0) TC_MARK(6);
     tc_fence_after();
-    float* tile = reinterpret_cast<float*>(smem);  // all MMAs have completed: the stage ring is free
-    const float* bias = a.bias ? a.bias + (long long)task * a.bias_stride : nullptr;
+    float* tile = reinterpret_cast<float*>(smem);  // all MMAs have completed: operand buffers are free
+    const bool want_stats = (a.mode != CONV_PLAIN);
+    const int grow = j0 + r;
+    float* orow = a.out + (long long)task * a.out_stride + (long long)grow * NCOLS;
 #pragma unroll
     for (int c0 = 0; c0 < NCOLS; c0 += 16) {
       uint32_t v0[16], v1[16], v2[16], v3[16], v4[16];
@@ -197,37 +270,41 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
       tc_ld16(ta + 3 * NCOLS, v3);
       tc_ld16(ta + 4 * NCOLS, v4);
       tc_wait_ld();
+      float o[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float big = (__uint_as_float(v0[i]) + __uint_as_float(v1[i])) + (__uint_as_float(v2[i]) + __uint_as_float(v3[i]));
-        tile[r * PITCH + c0 + i] = (big + __uint_as_float(v4[i])) + (bias ? bias[c0 + i] : 0.f);
+        o[i] = (big + __uint_as_float(v4[i])) + s_bias[c0 + i];
+      }
+      if (grow < a.rows) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(orow + c0 + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+      }
+      if (want_stats) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) tile[r * PITCH + c0 + i] = o[i];
       }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    float* out = a.out + (long long)task * a.out_stride;
-    const float* zh = a.zh ? a.zh + (long long)task * a.zh_stride : nullptr;
-    constexpr int PARTS = 128 / NCOLS;           // 2 for 64 and 48, 4 for 32, 8 for 16
-    const int col = et % NCOLS, part = et / NCOLS;
-    double s1 = 0.0, s2 = 0.0;
-    for (int idx = et; idx < 128 * NCOLS; idx += 128) {
-      const int rr = idx / NCOLS, cc = idx - rr * NCOLS;
-      const int row = j0 + rr;
-      if (row < a.rows) out[(long long)row * NCOLS + cc] = tile[rr * PITCH + cc];
-    }
-    if (a.mode != CONV_PLAIN && part < PARTS) {
-      for (int rr = part; rr < 128; rr += PARTS) {
-        if (row_ok[rr]) {
-          const float v = tile[rr * PITCH + col];
-          if (a.mode == CONV_FWD_STATS) { s1 += (double)v; s2 += (double)v * (double)v; }
-          else {
-            const float zv = zh[(long long)(j0 + rr) * NCOLS + col];
-            s1 += (double)v; s2 += (double)zv * (double)v;
+    if (et == 0) TC_MARK(7);
+    if (want_stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const float* zh = a.zh ? a.zh + (long long)task * a.zh_stride : nullptr;
+      constexpr int PARTS = 128 / NCOLS;           // 2 for 64 and 48, 4 for 32, 8 for 16
+      const int col = et % NCOLS, part = et / NCOLS;
+      double s1 = 0.0, s2 = 0.0;
+      if (part < PARTS) {
+        for (int rr = part; rr < 128; rr += PARTS) {
+          if (row_ok[rr]) {
+            const float v = tile[rr * PITCH + col];
+            if (a.mode == CONV_FWD_STATS) { s1 += (double)v; s2 += (double)v * (double)v; }
+            else {
+              const float zv = zh[(long long)(j0 + rr) * NCOLS + col];
+              s1 += (double)v; s2 += (double)zv * (double)v;
+            }
           }
         }
+        if (part < 2) { sred[part][col][0] = s1; sred[part][col][1] = s2; }
       }
-      if (part < 2) { sred[part][col][0] = s1; sred[part][col][1] = s2; }
-    }
-    if (a.mode != CONV_PLAIN) {
       if (PARTS > 2) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (part >= 2 && part < PARTS) { atomicAdd(&sred[part & 1][col][0], s1); atomicAdd(&sred[part & 1][col][1], s2); }
@@ -241,8 +318,10 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
     }
   }
 
+  if (threadIdx.x == 64) TC_MARK(8);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TC_MARK(9);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
   }
@@ -250,23 +329,37 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const __grid_constant__
 
 }  // namespace
 
-size_t tc_conv_smem_bytes(int ncols) { return (size_t)TC_STAGES * (2 * TC_A_BYTES + 2 * ncols * 128) + 1024; }
+int tc_read_timeline(long long* out16) { return cudaMemcpyFromSymbol(out16, g_tc_timeline, 16 * sizeof(long long)) == cudaSuccess ? 0 : 1; }
+
+// halo tile rows (multiple of 8) for a grid of pitch gw, and the deepest B ring that fits next to 4 halo buffers
+int tc_conv_rpad(int gw) { return ((128 + 2 * (gw + 1)) + 7) / 8 * 8; }
+int tc_conv_ring(int ncols, int gw) {
+  const long long avail = 227LL * 1024 - 4096 /* static smem */ - 1024 /* alignment */ - 4LL * tc_conv_rpad(gw) * 128;
+  long long nb = avail / (2LL * ncols * 128);
+  if (nb > 8) nb = 8;
+  return (int)nb;
+}
+size_t tc_conv_smem_bytes(int ncols, int gw) {
+  return (size_t)4 * tc_conv_rpad(gw) * 128 + (size_t)tc_conv_ring(ncols, gw) * 2 * ncols * 128 + 1024;
+}
 
 int tc_conv_prepare() {
-  cudaError_t e1 = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_conv_smem_bytes(64));
-  cudaError_t e2 = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_conv_smem_bytes(32));
-  cudaError_t e3 = cudaFuncSetAttribute(conv_tc_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_conv_smem_bytes(48));
-  cudaError_t e4 = cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_conv_smem_bytes(16));
+  const int maxs = 227 * 1024 - 4096;    // static shared memory (barriers, row flags, fp64 partials) takes the rest
+  cudaError_t e1 = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
+  cudaError_t e2 = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
+  cudaError_t e3 = cudaFuncSetAttribute(conv_tc_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
+  cudaError_t e4 = cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
   return (e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess && e4 == cudaSuccess) ? 0 : 1;
 }
 
 void launch_conv_tc(const TcMaps& maps, const TcConvArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_CONV, a.alg_flops, st);
   dim3 grid((a.rows + 127) / 128, a.tasks);
-  if (a.ncols == 64) conv_tc_kernel<64><<<grid, 192, tc_conv_smem_bytes(64), st>>>(maps, a);
-  else if (a.ncols == 48) conv_tc_kernel<48><<<grid, 192, tc_conv_smem_bytes(48), st>>>(maps, a);
-  else if (a.ncols == 32) conv_tc_kernel<32><<<grid, 192, tc_conv_smem_bytes(32), st>>>(maps, a);
-  else conv_tc_kernel<16><<<grid, 192, tc_conv_smem_bytes(16), st>>>(maps, a);
+  const size_t smem = tc_conv_smem_bytes(a.ncols, a.gw);
+  if (a.ncols == 64) conv_tc_kernel<64><<<grid, 224, smem, st>>>(maps, a);
+  else if (a.ncols == 48) conv_tc_kernel<48><<<grid, 224, smem, st>>>(maps, a);
+  else if (a.ncols == 32) conv_tc_kernel<32><<<grid, 224, smem, st>>>(maps, a);
+  else conv_tc_kernel<16><<<grid, 224, smem, st>>>(maps, a);
   CUDA_CHECK_LAUNCH();
 }
 

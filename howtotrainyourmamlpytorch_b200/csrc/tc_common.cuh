@@ -7,6 +7,7 @@ struct alignas(64) TcMaps { CUtensorMap m[8]; };   // per source: A_hi, A_lo, B_
 
 struct TcConvArgs {
   int nsrc, kc, rows, gw, G, h, w, ncols, mode, tasks;
+  int halo, rpad, nb, bo_mode, timeline;   // halo = gw + 1 rows; rpad = halo-tile rows (multiple of 8); nb = B ring depth
   int a_row_base[2];     // row (in the A tensor map) of grid row 0 of task 0 for this pass slot (includes the guard)
   int a_task_rows[2];    // rows per task in the A tensor map
   int sign[2];           // +1 conv, -1 dgrad
@@ -19,8 +20,11 @@ struct TcConvArgs {
   double alg_flops;
 };
 
-size_t tc_conv_smem_bytes(int ncols);
+int tc_conv_rpad(int gw);
+int tc_conv_ring(int ncols, int gw);
+size_t tc_conv_smem_bytes(int ncols, int gw);
 int tc_conv_prepare();
+int tc_read_timeline(long long* out16);
 void launch_conv_tc(const TcMaps& maps, const TcConvArgs& a, cudaStream_t st);
 void launch_pack_weights(const ParamLayout& pl, const float* theta, long long theta_task_stride, float* pack,
                          long long pack_task_stride, long long plane_stride, int tasks, cudaStream_t st);
