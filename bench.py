@@ -315,10 +315,16 @@ def main():
         tf32_peak = peaks["bf16_tflops"] / 2.0            # dense TF32 = half of dense bf16 (measured burst)
         peak_3x = tf32_peak / 3.0                         # fp32-faithful 3xTF32 operand split
         achieved = dom_fl / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r1.json")))["dominant_kernel_traffic_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {
-            "bound": "tensor", "kernel": "3x3 implicit-GEMM conv (conv_rows_kernel + wgrad_kernel)",
+            "bound": "tensor", "kernel": "3x3 implicit-GEMM conv: conv_tc_kernel (tcgen05, 3xTF32) + wgrad_kernel (FFMA)",
             "achieved": achieved, "peak": peak_3x, "unit": "TFLOP/s", "frac": achieved / peak_3x,
-            "traffic": None,
+            "traffic": traffic,
+            "traffic_note": "dram__bytes_read+write of one conv_tc_kernel launch (ncu --set full, cold cache; profiles/ncu_summary_r1.json)",
             "peak_source": peak_src + ": bf16_tflops %.1f / 2 (tf32) / 3 (3xTF32 split)" % peaks["bf16_tflops"],
             "launches_profiled": int(dom_n), "mean_launch_us": 1e3 * dom_ms / max(dom_n, 1),
             "share_of_step": dom_ms / tot_prof_ms if tot_prof_ms > 0 else None,

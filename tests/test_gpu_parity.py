@@ -325,3 +325,32 @@ def test_decision_forced_parity(case, cuda_device):
     assert not bad, bad
     got_logits = torch.from_numpy(np.stack(preds)).double()
     assert float((got_logits - ref["logits"]).abs().max()) <= 1e-4 * float(ref["logits"].abs().max())
+
+
+@pytest.mark.parametrize("case", ["tiny_pp", "tiny_odd", "tiny_maml"])
+def test_tensor_core_convs_match_fp32_ffma_convs(case, cuda_device):
+    """Kernel-level A/B: the tcgen05 3xTF32 implicit-GEMM convolutions against their exact-fp32 FFMA twins
+    (`reserved` bit 1) on the same inputs -- every intermediate of the first support forward / backward must
+    agree to 2e-5 (no chaos: a single pass has no inner-loop amplification)."""
+    from howtotrainyourmamlpytorch_b200 import MAMLFewShotClassifier
+    g = load_golden(case)
+    a = g.args
+    outs = []
+    for force in (False, True):
+        m = MAMLFewShotClassifier(im_shape=(2, a.image_channels, a.image_height, a.image_width), device=cuda_device, args=a)
+        m._debug_force_fp32_convs = force
+        m.load_state_dict(g.state())
+        m.meta_gradient(g.batch(0), g.iters[0][0])
+        eng = m._engine
+        L = int(a.num_stages)
+        taps = {}
+        for l in range(L):
+            taps["zh%d" % l] = eng.debug_read("sup_zh", 0, 0, l)
+            taps["dz%d" % l] = eng.debug_read("sup_dz", 0, 0, l)
+            if l < L - 1:
+                taps["dp%d" % l] = eng.debug_read("sup_dp", 0, 0, l)
+        taps["g0"] = eng.debug_read("g", 0, 0, 0)
+        outs.append(taps)
+    for k in outs[0]:
+        x, y = torch.from_numpy(outs[0][k]), torch.from_numpy(outs[1][k])
+        assert rel_err(x, y) <= 2e-5, (k, rel_err(x, y))
