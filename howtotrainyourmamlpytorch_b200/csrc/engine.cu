@@ -348,6 +348,7 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   e = cudaMallocHost((void**)&h->pinned, 16 * 32 * sizeof(float));
   if (e != cudaSuccess) { cudaFree(h->ws); delete h; return fail(std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
   h->use_graphs = !(cfg->reserved & 4) && !getenv("MAML_B200_NO_GRAPH");
+  g_use_pdl = getenv("MAML_B200_PDL") ? 1 : 0;   // measured: no gain inside the captured graph (4.16 vs 4.02 ms), so off by default
   bool ok = cudaStreamCreateWithFlags(&h->s_cap, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&h->s_tgt, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&h->s_wg, cudaStreamNonBlocking) == cudaSuccess &&

@@ -60,6 +60,7 @@ struct WinIter {
 
 // ------------------------------------------------------------------------------- forward
 __global__ void __launch_bounds__(256) bnact_kernel(BnActArgs a) {
+  pdl_prologue();
   __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64];
   const BnGeom g = a.g;
   const int task = blockIdx.y;
@@ -117,7 +118,7 @@ static inline dim3 bn_grid(const BnGeom& g, int tasks, int* block) {
 void launch_bnact(const BnActArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
-  bnact_kernel<<<grid, block, 0, st>>>(a);
+  launch_pdl(bnact_kernel, dim3(grid), dim3(block), (size_t)(0), st, a);
   CUDA_CHECK_LAUNCH();
 }
 
@@ -173,6 +174,7 @@ __device__ __forceinline__ void block_reduce_stats(double (&s1)[4], double (&s2)
 
 // ------------------------------------------------------------------------------- backward: reduce
 __global__ void __launch_bounds__(256) bnbwd_reduce_kernel(BnBwdArgs a) {
+  pdl_prologue();
   __shared__ float s_g[64], s_b[64];
   const BnGeom g = a.g;
   const int task = blockIdx.y;
@@ -206,13 +208,14 @@ void launch_bnbwd_reduce(const BnBwdArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
   if (grid.x > 148) grid.x = 148;
-  bnbwd_reduce_kernel<<<grid, block, 0, st>>>(a);
+  launch_pdl(bnbwd_reduce_kernel, dim3(grid), dim3(block), (size_t)(0), st, a);
   CUDA_CHECK_LAUNCH();
 }
 
 // ------------------------------------------------------------------------------- backward: apply
 // dz = r * gamma * (dy - S1/m - zh * S2/m)   at every valid position (dy != 0 only at the arg-max)
 __global__ void __launch_bounds__(256) bnbwd_apply_kernel(BnBwdArgs a) {
+  pdl_prologue();
   __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_c1[64], s_c2[64];
   const BnGeom g = a.g;
   const int task = blockIdx.y;
@@ -272,13 +275,14 @@ __global__ void __launch_bounds__(256) bnbwd_apply_kernel(BnBwdArgs a) {
 void launch_bnbwd_apply(const BnBwdArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
-  bnbwd_apply_kernel<<<grid, block, 0, st>>>(a);
+  launch_pdl(bnbwd_apply_kernel, dim3(grid), dim3(block), (size_t)(0), st, a);
   CUDA_CHECK_LAUNCH();
 }
 
 // ------------------------------------------------------------------------------- tangent forward
 // zhdot = r * (zdot - mean(zdot) - zh * mean(zh * zdot));  pdot = slope * gamma * zhdot at the arg-max
 __global__ void __launch_bounds__(256) bnact_tan_kernel(BnActTanArgs a) {
+  pdl_prologue();
   __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_md[64], s_q[64];
   const BnGeom g = a.g;
   const int task = blockIdx.y;
@@ -337,13 +341,14 @@ __global__ void __launch_bounds__(256) bnact_tan_kernel(BnActTanArgs a) {
 void launch_bnact_tan(const BnActTanArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
-  bnact_tan_kernel<<<grid, block, 0, st>>>(a);
+  launch_pdl(bnact_tan_kernel, dim3(grid), dim3(block), (size_t)(0), st, a);
   CUDA_CHECK_LAUNCH();
 }
 
 // ------------------------------------------------------------------------------- tangent backward: reduce
 // T1 = sum dydot,  T2 = sum (dydot * zh + dy * zhdot)   (both only at the arg-max position)
 __global__ void __launch_bounds__(256) bnbwd_tan_reduce_kernel(BnBwdTanArgs a) {
+  pdl_prologue();
   __shared__ float s_g[64], s_b[64];
   const BnGeom g = a.g;
   const int task = blockIdx.y;
@@ -387,13 +392,14 @@ void launch_bnbwd_tan_reduce(const BnBwdTanArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
   if (grid.x > 148) grid.x = 148;
-  bnbwd_tan_reduce_kernel<<<grid, block, 0, st>>>(a);
+  launch_pdl(bnbwd_tan_reduce_kernel, dim3(grid), dim3(block), (size_t)(0), st, a);
   CUDA_CHECK_LAUNCH();
 }
 
 // ------------------------------------------------------------------------------- tangent backward: apply
 // dzdot = -r*q*dz + r*gamma*(dydot - T1/m - zhdot*S2/m - zh*T2/m)
 __global__ void __launch_bounds__(256) bnbwd_tan_apply_kernel(BnBwdTanArgs a) {
+  pdl_prologue();
   __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_q[64], s_c2[64], s_t1[64], s_t2[64];
   const BnGeom g = a.g;
   const int task = blockIdx.y;
@@ -453,6 +459,6 @@ __global__ void __launch_bounds__(256) bnbwd_tan_apply_kernel(BnBwdTanArgs a) {
 void launch_bnbwd_tan_apply(const BnBwdTanArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
-  bnbwd_tan_apply_kernel<<<grid, block, 0, st>>>(a);
+  launch_pdl(bnbwd_tan_apply_kernel, dim3(grid), dim3(block), (size_t)(0), st, a);
   CUDA_CHECK_LAUNCH();
 }

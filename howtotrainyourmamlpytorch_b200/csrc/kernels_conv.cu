@@ -9,6 +9,7 @@
 #include "common.cuh"
 
 long long g_launch_counter = 0;
+int g_use_pdl = 0;
 
 __device__ __forceinline__ int tap_shift(int tap, int gw) { return (tap / 3 - 1) * gw + (tap % 3 - 1); }
 
@@ -92,6 +93,7 @@ __device__ __forceinline__ void conv_epilogue(float (&acc)[4][FN], int j0, int r
 // ---------------------------------------------------------------------------------------------
 template <int FN>
 __global__ void __launch_bounds__(256) conv_rows_kernel(ConvArgs a) {
+  pdl_prologue();
   constexpr int NC = 16 * FN;
   __shared__ __align__(16) float As[16][68];
   __shared__ __align__(16) float Ws[16][NC];
@@ -187,10 +189,10 @@ void launch_conv_rows(const ConvArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_CONV, a.alg_flops, st);
   dim3 grid((a.rows + 63) / 64, a.tasks);
   switch (a.ncols / 16) {
-    case 1: conv_rows_kernel<1><<<grid, 256, 0, st>>>(a); break;
-    case 2: conv_rows_kernel<2><<<grid, 256, 0, st>>>(a); break;
-    case 3: conv_rows_kernel<3><<<grid, 256, 0, st>>>(a); break;
-    default: conv_rows_kernel<4><<<grid, 256, 0, st>>>(a); break;
+    case 1: launch_pdl(conv_rows_kernel<1>, dim3(grid), dim3(256), (size_t)(0), st, a); break;
+    case 2: launch_pdl(conv_rows_kernel<2>, dim3(grid), dim3(256), (size_t)(0), st, a); break;
+    case 3: launch_pdl(conv_rows_kernel<3>, dim3(grid), dim3(256), (size_t)(0), st, a); break;
+    default: launch_pdl(conv_rows_kernel<4>, dim3(grid), dim3(256), (size_t)(0), st, a); break;
   }
   CUDA_CHECK_LAUNCH();
 }
@@ -200,6 +202,7 @@ void launch_conv_rows(const ConvArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 template <int FN>
 __global__ void __launch_bounds__(256) conv0_kernel(Conv0Args a) {
+  pdl_prologue();
   constexpr int NC = 16 * FN;
   extern __shared__ float sm0[];
   __shared__ double sred[8 * NC * 2];
@@ -255,10 +258,10 @@ void launch_conv0(const Conv0Args& a, cudaStream_t st) {
   dim3 grid((a.rows + 63) / 64, a.tasks);
   const size_t smem = (size_t)(9 * a.c0 * a.ncols + (64 + 2 * (a.gw + 1)) * a.c0) * sizeof(float);
   switch (a.ncols / 16) {
-    case 1: conv0_kernel<1><<<grid, 256, smem, st>>>(a); break;
-    case 2: conv0_kernel<2><<<grid, 256, smem, st>>>(a); break;
-    case 3: conv0_kernel<3><<<grid, 256, smem, st>>>(a); break;
-    default: conv0_kernel<4><<<grid, 256, smem, st>>>(a); break;
+    case 1: launch_pdl(conv0_kernel<1>, dim3(grid), dim3(256), (size_t)(smem), st, a); break;
+    case 2: launch_pdl(conv0_kernel<2>, dim3(grid), dim3(256), (size_t)(smem), st, a); break;
+    case 3: launch_pdl(conv0_kernel<3>, dim3(grid), dim3(256), (size_t)(smem), st, a); break;
+    default: launch_pdl(conv0_kernel<4>, dim3(grid), dim3(256), (size_t)(smem), st, a); break;
   }
   CUDA_CHECK_LAUNCH();
 }
@@ -271,6 +274,7 @@ void launch_conv0(const Conv0Args& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 template <int CN, int FN>
 __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
+  pdl_prologue();
   constexpr int KC = 16 * CN, NC = 16 * FN;
   __shared__ __align__(16) float As[16][KC];
   __shared__ __align__(16) float Ds[16][NC];
@@ -357,7 +361,7 @@ void launch_wgrad(const WgradArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_WGRAD, a.alg_flops, st);
   dim3 grid(a.nchunks * 9, a.tasks);
   const int cn = a.kc / 16, fn = a.ncols / 16;
-#define WG_CASE(C, F_) if (cn == C && fn == F_) { wgrad_kernel<C, F_><<<grid, 256, 0, st>>>(a); CUDA_CHECK_LAUNCH(); return; }
+#define WG_CASE(C, F_) if (cn == C && fn == F_) { launch_pdl(wgrad_kernel<C, F_>, dim3(grid), dim3(256), (size_t)(0), st, a); CUDA_CHECK_LAUNCH(); return; }
   WG_CASE(1, 1) WG_CASE(2, 2) WG_CASE(3, 3) WG_CASE(4, 4)
 #undef WG_CASE
 }
@@ -366,6 +370,7 @@ void launch_wgrad(const WgradArgs& a, cudaStream_t st) {
 // Per 64-row sub-tile the dz rows and the image window (rows +/- halo) are staged in shared memory; thread
 // (grp, f) accumulates the (tap, c) combinations q = grp, grp + NG, ... for output channel f.
 __global__ void __launch_bounds__(256) wgrad0_kernel(WgradArgs a) {
+  pdl_prologue();
   extern __shared__ float smw[];
   const int task = blockIdx.y, chunk = blockIdx.x;
   const int tid = threadIdx.x;
@@ -437,7 +442,7 @@ void launch_wgrad0(const WgradArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_WGRAD0, a.alg_flops, st);
   dim3 grid(a.nchunks, a.tasks);
   const size_t smem = (size_t)(64 * a.ncols + (64 + 2 * (a.gw + 1)) * a.kc) * sizeof(float);
-  wgrad0_kernel<<<grid, 256, smem, st>>>(a);
+  launch_pdl(wgrad0_kernel, dim3(grid), dim3(256), (size_t)(smem), st, a);
   CUDA_CHECK_LAUNCH();
 }
 
@@ -446,6 +451,7 @@ void launch_wgrad0(const WgradArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 __global__ void prep_x_kernel(const float* __restrict__ x, float* __restrict__ xg, long long xg_task_stride, int n,
                               int C, int H, int W) {
+  pdl_prologue();
   const int task = blockIdx.y;
   const long long total = (long long)n * H * W;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -464,6 +470,6 @@ void launch_prep_x(const float* x, float* xg, long long xg_task_stride, int task
   ProfScope prof_scope__(PROF_PARAM, 0.0, st);
   const long long total = (long long)n * H * W;
   dim3 grid((unsigned)((total + 255) / 256), tasks);
-  prep_x_kernel<<<grid, 256, 0, st>>>(x, xg, xg_task_stride, n, C, H, W);
+  launch_pdl(prep_x_kernel, dim3(grid), dim3(256), (size_t)(0), st, x, xg, xg_task_stride, n, C, H, W);
   CUDA_CHECK_LAUNCH();
 }

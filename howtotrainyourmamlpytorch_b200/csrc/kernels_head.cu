@@ -15,6 +15,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
+  pdl_prologue();
   // grid (row groups, tasks): everything except the weight gradient is row-local, so each CTA owns `rows_per_cta`
   // rows of the batch and writes its own chunk of (gW, gb); the parameter-space kernel sums the chunks in order.
   extern __shared__ float smh[];
@@ -139,6 +140,6 @@ void launch_head(const HeadArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_HEAD, 0.0, st);
   const size_t smem = (size_t)5 * a.rows_per_cta * a.N * sizeof(float);
   dim3 grid((a.n + a.rows_per_cta - 1) / a.rows_per_cta, a.tasks);
-  head_kernel<<<grid, 256, smem, st>>>(a);
+  launch_pdl(head_kernel, dim3(grid), dim3(256), (size_t)(smem), st, a);
   CUDA_CHECK_LAUNCH();
 }

@@ -105,6 +105,7 @@ __device__ long long g_tc_timeline[16];
 
 template <int NCOLS>
 __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvArgs a) {
+  pdl_trigger();
   constexpr int B_BYTES = NCOLS * 128;
   constexpr int BSTAGE = 2 * B_BYTES;            // B_hi + B_lo of one (tap, k-chunk)
   constexpr int NACC = 5;                        // 4 x hi*hi (round-robin over k-steps) + 1 x (lo*hi + hi*lo)
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();          // set-up above overlapped the previous kernel's tail; its results are needed from here on
   if (threadIdx.x == 0) TC_MARK(1);
 
   if (warp == 6) {
@@ -356,10 +358,10 @@ void launch_conv_tc(const TcMaps& maps, const TcConvArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_CONV, a.alg_flops, st);
   dim3 grid((a.rows + 127) / 128, a.tasks);
   const size_t smem = tc_conv_smem_bytes(a.ncols, a.gw);
-  if (a.ncols == 64) conv_tc_kernel<64><<<grid, 224, smem, st>>>(maps, a);
-  else if (a.ncols == 48) conv_tc_kernel<48><<<grid, 224, smem, st>>>(maps, a);
-  else if (a.ncols == 32) conv_tc_kernel<32><<<grid, 224, smem, st>>>(maps, a);
-  else conv_tc_kernel<16><<<grid, 224, smem, st>>>(maps, a);
+  if (a.ncols == 64) launch_pdl(conv_tc_kernel<64>, dim3(grid), dim3(224), (size_t)(smem), st, maps, a);
+  else if (a.ncols == 48) launch_pdl(conv_tc_kernel<48>, dim3(grid), dim3(224), (size_t)(smem), st, maps, a);
+  else if (a.ncols == 32) launch_pdl(conv_tc_kernel<32>, dim3(grid), dim3(224), (size_t)(smem), st, maps, a);
+  else launch_pdl(conv_tc_kernel<16>, dim3(grid), dim3(224), (size_t)(smem), st, maps, a);
   CUDA_CHECK_LAUNCH();
 }
 
@@ -376,6 +378,7 @@ __device__ __forceinline__ float tf32_rna(float x) {
 
 __global__ void pack_weights_kernel(ParamLayout pl, const float* __restrict__ theta, long long theta_task_stride,
                                     float* __restrict__ pack, long long pack_task_stride, long long plane_stride) {
+  pdl_prologue();
   const int task = blockIdx.y;
   const long long per_layer = 9LL * pl.F * pl.F;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -401,6 +404,6 @@ void launch_pack_weights(const ParamLayout& pl, const float* theta, long long th
   const long long n = 9LL * pl.F * pl.F * (pl.L - 1);
   if (n <= 0) return;
   dim3 grid((unsigned)((n + 255) / 256), tasks);
-  pack_weights_kernel<<<grid, 256, 0, st>>>(pl, theta, theta_task_stride, pack, pack_task_stride, plane_stride);
+  launch_pdl(pack_weights_kernel, dim3(grid), dim3(256), (size_t)(0), st, pl, theta, theta_task_stride, pack, pack_task_stride, plane_stride);
   CUDA_CHECK_LAUNCH();
 }
