@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "maml_b200_workspace_bytes", "maml_b200_num_segments", "maml_b200_segment", "maml_b200_meta_size",
     "maml_b200_result_size", "maml_b200_meta_batch_fwd_bwd", "maml_b200_adam_step",
     "maml_b200_running_stats_update", "maml_b200_debug_read", "maml_b200_last_launch_count",
-    "maml_b200_profile", "maml_b200_profile_read",
+    "maml_b200_profile", "maml_b200_profile_read", "maml_b200_net_forward",
 ]
 PROF_CATS = ["conv_igemm", "conv_first_block", "wgrad", "wgrad_first_block", "bn_act_pool", "head", "param"]
 
@@ -72,6 +72,8 @@ def load_library():
     lib.maml_b200_result_size.restype = i64
     lib.maml_b200_meta_batch_fwd_bwd.argtypes = [vp, ctypes.POINTER(IterArgs), vp, vp, vp, vp, vp, vp, vp, vp]
     lib.maml_b200_meta_batch_fwd_bwd.restype = ctypes.c_int
+    lib.maml_b200_net_forward.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    lib.maml_b200_net_forward.restype = ctypes.c_int
     lib.maml_b200_adam_step.argtypes = [vp, vp, vp, vp, vp, f32, i32, u32, u32, vp]
     lib.maml_b200_adam_step.restype = ctypes.c_int
     lib.maml_b200_running_stats_update.argtypes = [vp, vp, vp, vp, ctypes.POINTER(f32), vp]
@@ -147,6 +149,11 @@ class Engine(object):
             self.h, ctypes.byref(it), meta.data_ptr(), xs.data_ptr(), ys.data_ptr(), xt.data_ptr(), yt.data_ptr(),
             result.data_ptr(), last_logits.data_ptr() if last_logits is not None else None, self._stream())
         _check(self.lib, rc, "maml_b200_meta_batch_fwd_bwd")
+
+    def net_forward(self, n_tasks, num_step, meta_like, x, logits):
+        rc = self.lib.maml_b200_net_forward(self.h, int(n_tasks), int(num_step), meta_like.data_ptr(), x.data_ptr(),
+                                            logits.data_ptr(), self._stream())
+        _check(self.lib, rc, "maml_b200_net_forward")
 
     def adam_step(self, meta, grad, exp_avg, exp_avg_sq, lr, step, trainable_mask, clamp_mask):
         rc = self.lib.maml_b200_adam_step(self.h, meta.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(),

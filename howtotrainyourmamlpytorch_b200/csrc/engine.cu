@@ -86,6 +86,7 @@ struct maml_b200_handle {
   double* stats = nullptr; long long stats_task_stride = 0, st_pass_stride = 0, st_layer_stride = 0, stats_count = 0;
   float *losses = nullptr, *correct = nullptr, *decay_dev = nullptr;
   double* abar = nullptr;
+  long long* zero_labels = nullptr;   // [max(n_s, n_t)] zeros (label-free forward)
   float* pinned = nullptr;            // host staging ring for small per-call scalars (16 slots x 32 floats)
   int pin_slot = 0;
   long long last_launches = 0;
@@ -306,6 +307,7 @@ static void carve(maml_b200_handle* h, Bump& b) {
   h->correct = b.f(T);
   h->abar = b.d(T * h->pl.nseg_inner * MAML_MAX_STEPS);
   h->decay_dev = b.f(MAML_MAX_STEPS);
+  h->zero_labels = (long long*)b.d(std::max(h->n_s, h->n_t));
 }
 
 extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** out) {
@@ -877,6 +879,37 @@ extern "C" int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200
   hit->stamp = ++h->graph_clock;
   h->last_launches = hit->launches;
   CK(cudaGraphLaunch(hit->exec, st));
+  return 0;
+}
+
+// Stand-alone functional forward (level B1 of the boundary): logits of `n_tasks` independent batches of N*T images
+// under externally supplied weights.  `meta_like` has the layout of the meta vector (conv / linear entries = the
+// weights to use, BatchNorm entries = gamma / beta; LSLR entries ignored).  BatchNorm uses batch statistics and the
+// gamma / beta of `num_step`, exactly like reference VGGReLUNormNetwork.forward (training flag is ignored there too).
+extern "C" int maml_b200_net_forward(maml_b200_handle* h, int32_t n_tasks, int32_t num_step, const float* meta_like,
+                                    const float* x, float* logits, void* stream) {
+  if (!h || !meta_like || !x || !logits) return fail("null argument");
+  if (n_tasks < 1 || n_tasks > h->maxT) return fail("n_tasks out of range");
+  if (num_step < 0 || num_step >= h->S) return fail("num_step out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int T = n_tasks;
+  CK(cudaMemsetAsync(h->stats, 0, (size_t)h->stats_count * sizeof(double), st));
+  CK(cudaMemsetAsync(h->losses, 0, (size_t)h->maxT * MAML_MAX_STEPS * sizeof(float), st));
+  CK(cudaMemsetAsync(h->correct, 0, (size_t)h->maxT * sizeof(float), st));
+  launch_prep_x(x, h->tgt.xg, h->tgt.xg_stride, T, h->n_t, h->C, h->H, h->W, st);
+  launch_import_theta(h->pl, meta_like, h->theta, h->Ppad, T, st);
+  pack_theta_step(h, 0, T, st);
+  forward_pass(h, h->tgt, 0, h->theta, 0, meta_like, num_step, PASS_TGT_FWD, T, st);
+  HeadArgs a{};
+  a.mode = HEAD_TARGET_FWD; a.n = h->n_t; a.N = h->N; a.D = h->D; a.scale = 1.f;
+  a.f = AIN(h->tgt, h->L, 0); a.f_stride = STRIDE(h->tgt, ain, h->L);
+  a.Wfc = h->theta + h->pl.fcw_off; a.bfc = h->theta + h->pl.fcb_off; a.theta_stride = h->Ppad;
+  a.y = h->zero_labels; a.y_stride = 0;
+  a.loss_out = h->losses; a.loss_stride = MAML_MAX_STEPS; a.rows_per_cta = HEAD_ROWS_PER_CTA;
+  a.logits_out = logits; a.logits_stride = (long long)h->n_t * h->N;
+  a.tasks = T;
+  launch_head(a, st);
+  CK(cudaGetLastError());
   return 0;
 }
 

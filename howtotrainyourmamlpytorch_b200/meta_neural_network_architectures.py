@@ -103,11 +103,57 @@ class VGGReLUNormNetwork(nn.Module):
         self.layer_dict["linear"] = MetaLinearLayer(input_shape=(shape[0], feat), num_filters=self.num_output_classes,
                                                     use_bias=True)
 
+    def _segment_tensors(self, params):
+        """Tensors in the engine's meta-vector order (conv.weight, conv.bias, norm.bias, norm.weight per block; linear)."""
+        own = dict(self.named_parameters())
+        fast = {}
+        if params is not None:
+            for k, v in params.items():
+                k = k.replace("module.", "")
+                fast[k] = v[0] if v.dim() == own[k].dim() + 1 else v   # strip the reference's replica dim
+        out = []
+        for i in range(self.num_stages):
+            p = "layer_dict.conv%d." % i
+            for n in (p + "conv.weight", p + "conv.bias", p + "norm_layer.bias", p + "norm_layer.weight"):
+                out.append(fast.get(n, own[n]))
+        for n in ("layer_dict.linear.weights", "layer_dict.linear.bias"):
+            out.append(fast.get(n, own[n]))
+        return out
+
     def forward(self, x, num_step, params=None, training=False, backup_running_statistics=False):
-        raise NotImplementedError(
-            "VGGReLUNormNetwork is a parameter container here: the conv/BN/leaky-ReLU/maxpool/linear arithmetic "
-            "of this network runs inside the CUDA engine, driven by MAMLFewShotClassifier.run_train_iter / "
-            "run_validation_iter (see INTEGRATION.md)")
+        """Logits of a batch under externally supplied ("fast") weights -- reference
+        ``VGGReLUNormNetwork.forward`` (:620-660): ``params`` maps ``layer_dict.conv{i}.conv.{weight,bias}`` /
+        ``layer_dict.linear.{weights,bias}`` to tensors carrying a leading replica dim (as the reference passes them)
+        or not; missing entries fall back to the module's own parameters.  BatchNorm always uses batch statistics
+        (the reference hard-codes ``training=True``, :246-247) with the gamma / beta of ``num_step``.
+        Runs on the CUDA engine (C ABI ``maml_b200_net_forward``); the running-statistics EMA side effect of the
+        reference is not applied by this stand-alone operator (they are write-only bookkeeping there).
+        The batch size must be a multiple of the number of classes (episode shaped)."""
+        from . import _native
+        if x.device.type != "cuda":
+            raise _native.NativeLibraryError("VGGReLUNormNetwork.forward needs a CUDA (sm_100a) device: no CPU fallback")
+        n = int(x.shape[0])
+        N = self.num_output_classes
+        if n % N != 0:
+            raise ValueError("batch size %d is not a multiple of num_output_classes %d" % (n, N))
+        key = (n, x.device.index)
+        cache = self.__dict__.setdefault("_engines", {})
+        if key not in cache:
+            a = self.args
+            with torch.cuda.device(x.device):
+                eng = _native.Engine(n_way=N, k_shot=1, t_target=n // N, channels=int(x.shape[1]), height=int(x.shape[2]),
+                                     width=int(x.shape[3]), filters=self.cnn_filters, num_stages=self.num_stages,
+                                     inner_steps=int(a.number_of_training_steps_per_iter),
+                                     per_step_bn=bool(a.per_step_bn_statistics), max_tasks=1)
+            cache[key] = (eng, torch.zeros(eng.meta_size, dtype=torch.float32, device=x.device),
+                          torch.empty(1, n, N, dtype=torch.float32, device=x.device))
+        eng, meta_like, logits = cache[key]
+        tensors = self._segment_tensors(params)
+        for (off, size), t in zip(eng.segments, tensors):
+            meta_like[off:off + size].copy_(t.detach().reshape(-1).to(torch.float32))
+        with torch.cuda.device(x.device):
+            eng.net_forward(1, int(num_step), meta_like, x.detach().to(torch.float32).contiguous(), logits)
+        return logits[0].clone()
 
     def zero_grad(self, params=None):
         if params is None:

@@ -105,6 +105,13 @@ int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200_iter_args*
                                  const float* x_target, const int64_t* y_target,
                                  float* result, float* last_logits, void* stream);
 
+/* Stand-alone functional forward: replaces reference VGGReLUNormNetwork.forward(x, num_step, params)
+ * (meta_neural_network_architectures.py:620-660) for batches of N*T images: conv / BatchNorm(batch statistics, gamma and
+ * beta of `num_step`) / leaky-ReLU / maxpool x stages, flatten, linear.  `meta_like`: same layout as the meta vector,
+ * conv / linear entries = the (fast) weights to use.  x [n_tasks, N*T, C, H, W]; logits [n_tasks, N*T, N] (out). */
+int maml_b200_net_forward(maml_b200_handle* h, int32_t n_tasks, int32_t num_step, const float* meta_like,
+                          const float* x, float* logits, void* stream);
+
 /* Outer step on the flat vectors: optional clamp to [-10,10] (reference :332-335), Adam
  * (betas 0.9/0.999, eps 1e-8, no weight decay; reference :69,:336).  `grad` is the first
  * meta_size floats of (the all-reduced) result.  Bit i of trainable_mask / clamp_mask refers to

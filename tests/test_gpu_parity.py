@@ -354,3 +354,28 @@ def test_tensor_core_convs_match_fp32_ffma_convs(case, cuda_device):
     for k in outs[0]:
         x, y = torch.from_numpy(outs[0][k]), torch.from_numpy(outs[1][k])
         assert rel_err(x, y) <= 2e-5, (k, rel_err(x, y))
+
+
+@pytest.mark.parametrize("case", ["tiny_pp", "tiny_maml", "omniglot_mamlpp_5w1s"])
+def test_functional_network_operator(case, cuda_device):
+    """Level B1: VGGReLUNormNetwork.forward(x, num_step, params) as a stand-alone operator vs the oracle's
+    functional forward (F.conv2d / F.batch_norm / F.leaky_relu / F.max_pool2d / F.linear), with external fast weights
+    carrying the reference's leading replica dim, and with params=None."""
+    g = load_golden(case)
+    a = g.args
+    m = _model(g, cuda_device)
+    xs, xt, ys, yt = g.batch(0)
+    x = xt[0].reshape(-1, *xt.shape[-3:])
+    state = g.state()
+    inner = O.inner_param_names(a)
+    gen = torch.Generator().manual_seed(5)
+    fast_cpu = {n: state[n] + 0.05 * torch.randn(state[n].shape, generator=gen) for n in inner}
+    for step in (0, int(a.number_of_training_steps_per_iter) - 1):
+        ref = O._net_forward(x, fast_cpu, state, a, step)
+        params = {n[len("classifier."):]: v.to(cuda_device).unsqueeze(0) for n, v in fast_cpu.items()}
+        got = m.classifier.forward(x.to(cuda_device), num_step=step, params=params, training=True)
+        assert got.shape == ref.shape
+        assert float((got.cpu() - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) + 1e-6, (case, step)
+    ref0 = O._net_forward(x, {n: state[n] for n in inner}, state, a, 0)
+    got0 = m.classifier.forward(x.to(cuda_device), num_step=0)
+    assert float((got0.cpu() - ref0).abs().max()) <= 2e-5 * float(ref0.abs().max()) + 1e-6

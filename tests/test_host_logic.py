@@ -68,8 +68,8 @@ def test_no_cpu_fallback():
     m = _model(g)
     with pytest.raises(_native.NativeLibraryError):
         m.run_train_iter(g.batch(0), 0)
-    with pytest.raises(NotImplementedError):
-        m.classifier.forward(torch.zeros(1, 3, 20, 20), num_step=0)
+    with pytest.raises(_native.NativeLibraryError):
+        m.classifier.forward(torch.zeros(3, 3, 20, 20), num_step=0)
 
 
 def test_lslr_update_rule_is_the_reference_formula():
