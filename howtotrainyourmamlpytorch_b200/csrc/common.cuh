@@ -194,7 +194,8 @@ void launch_import_theta(const ParamLayout& pl, const float* meta, float* theta0
                          int tasks, cudaStream_t st);
 void launch_param_reduce(const ParamLayout& pl, const PartialDesc& pd, const float* partial, int mode,
                          const float* theta_in, float* theta_out, float* g_out, float* tbar,
-                         const float* meta, int step, long long task_stride, int tasks, cudaStream_t st);
+                         const float* meta, int step, long long task_stride, int tasks, cudaStream_t st,
+                         int seg_lo = 0, int seg_hi = -1);
 void launch_dots_u(const ParamLayout& pl, float* tbar, const float* tgrad, const float* g, float* u, double* abar,
                    const float* meta, int step, long long task_stride, int tasks, cudaStream_t st);
 

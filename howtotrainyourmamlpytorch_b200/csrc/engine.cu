@@ -96,6 +96,9 @@ struct maml_b200_handle {
   cudaStream_t s_cap = nullptr, s_tgt = nullptr, s_wg = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_wg = nullptr, ev_pack = nullptr, ev_tgt[MAML_MAX_STEPS] = {};
   bool use_graphs = true;
+  // results produced on s_wg (upper-block parameter reduction, weight packs) that the main chain has not joined yet:
+  // consumed right before the first kernel that reads them (block 1's convolution / the head)
+  bool wg_pending = false;
   struct GraphEntry { maml_b200_iter_args it; const void* p[7]; cudaGraphExec_t exec; long long launches; unsigned long long stamp; };
   std::vector<GraphEntry> graphs;
   unsigned long long graph_clock = 0;
@@ -333,6 +336,7 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   // tensor-core (tcgen05 / TMA, 3xTF32) convolutions for blocks l >= 1; reserved bit 1 forces the fp32 FFMA kernels (tests)
   h->use_tc = (h->L > 1) && !(cfg->reserved & 2);
   if (const char* bo = getenv("MAML_B200_TC_BO")) h->tc_bo_mode = atoi(bo);
+  if (const char* sp = getenv("MAML_B200_TC_SPLIT")) tc_conv_set_split(atoi(sp));
   for (int l = 1; l < h->L && h->use_tc; ++l)
     if (tc_conv_rpad(h->geo[l].gw) > 256 || tc_conv_ring(h->F, h->geo[l].gw) < 2) h->use_tc = false;   // image too wide for one halo box      // F in {16, 32, 48, 64}: ragged K chunks are zero-filled by TMA
   plan_chunks(h, h->n_s, &h->plan_sup);
@@ -456,13 +460,46 @@ static TcOp tc_op_dz(const maml_b200_handle* h, const PassSet& ps, int l, int sl
   return o;
 }
 
+// what a backward pass does with its gradient chunks once they are complete
+struct ReduceSpec {
+  int mode;                       // PR_UPDATE / PR_SUB
+  const float* theta_in; float* theta_out; float* g_out; float* tbar;
+  int step;
+  int pack_step;                  // >= 0: re-pack theta[pack_step] for the tensor-core convs afterwards
+};
+
+static void pack_theta_step(maml_b200_handle* h, int step, int T, cudaStream_t st);
+
+// The first block's weight gradient is the LAST product of a backward pass, every other tensor's chunks are complete
+// much earlier.  So the reduction (+ LSLR update + tensor-core weight packing) of blocks >= 1 and the linear layer runs
+// on the wgrad side stream while the main chain finishes block 0; only the 9*C*F + F first-block values are reduced on
+// the critical path.  The main chain joins the side stream lazily (join_pending) before block 1 needs those weights.
+static void reduce_upper_on_side(maml_b200_handle* h, const ReduceSpec& rs, const PartialDesc& pd, const float* partial,
+                                 const float* meta, int T) {
+  launch_param_reduce(h->pl, pd, partial, rs.mode, rs.theta_in, rs.theta_out, rs.g_out, rs.tbar, meta, rs.step, h->Ppad, T,
+                      h->s_wg, 2, -1);
+  if (rs.pack_step >= 0) pack_theta_step(h, rs.pack_step, T, h->s_wg);
+  cudaEventRecord(h->ev_wg, h->s_wg);
+  h->wg_pending = true;
+}
+static void reduce_lower(maml_b200_handle* h, const ReduceSpec& rs, const PartialDesc& pd, const float* partial,
+                         const float* meta, int T, cudaStream_t st) {
+  launch_param_reduce(h->pl, pd, partial, rs.mode, rs.theta_in, rs.theta_out, rs.g_out, rs.tbar, meta, rs.step, h->Ppad, T,
+                      st, 0, 2);
+}
+static void join_pending(maml_b200_handle* h, cudaStream_t st) {
+  if (!h->wg_pending) return;
+  cudaStreamWaitEvent(st, h->ev_wg, 0);
+  h->wg_pending = false;
+}
+
 static void tc_conv(maml_b200_handle* h, int l, int n, int nsrc, const TcOp* ops, const float* bias, long long bias_stride,
                     float* out, long long out_stride, int mode, const float* zh, long long zh_stride, double* stats, int T,
                     cudaStream_t st) {
   const LayerGeom& g = h->geo[l];
   TcMaps maps;
   TcConvArgs a{};
-  a.nsrc = nsrc; a.kc = h->F; a.rows = n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.ncols = h->F; a.mode = mode; a.tasks = T;
+  a.nsrc = nsrc; a.kc = h->F; a.rows = n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.ncols = h->F; a.mode = mode; a.tasks = T; a.plan_tasks = h->maxT;
   a.halo = g.gw + 1; a.rpad = tc_conv_rpad(g.gw); a.nb = tc_conv_ring(h->F, g.gw); a.bo_mode = h->tc_bo_mode; a.timeline = getenv("MAML_B200_TC_TIMELINE") ? 1 : 0;
   for (int s = 0; s < nsrc; ++s) {
     maps.m[s * 4 + 0] = ops[s].a_maps[0]; maps.m[s * 4 + 1] = ops[s].a_maps[1];
@@ -482,6 +519,7 @@ static void forward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const
                          int bn_step, int stat_kind, int T, cudaStream_t st) {
   for (int l = 0; l < h->L; ++l) {
     const LayerGeom& g = h->geo[l];
+    if (l == 1 && st != h->s_tgt) join_pending(h, st);
     if (l == 0) {
       Conv0Args a{};
       a.X = ps.xg; a.x_stride = ps.xg_stride;
@@ -522,10 +560,12 @@ static void forward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const
 // primal backward of one pass (dp[L-1] already written by the head): BN backward, wgrad, dgrad
 static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const float* theta, int th_step, const float* meta,
                           int bn_step, int kind_fwd, int kind_bwd, float* partial, const ChunkPlan& cp, int T, cudaStream_t st,
-                          bool fork_wgrad) {
-  // wgrad of block l only feeds the parameter-space reduction at the end of the pass: it runs on a side stream,
-  // concurrently with dgrad(l) and the BatchNorm backward of block l-1 (joined by the caller's param_reduce).
+                          bool fork_wgrad, const ReduceSpec* rs = nullptr) {
+  // wgrad of block l >= 1 only feeds the parameter-space reduction: it runs on a side stream, concurrently with
+  // dgrad(l) and the BatchNorm backward of block l-1.  With a ReduceSpec the reduction itself is split (see
+  // reduce_upper_on_side); without one the caller reduces after this function returns.
   cudaStream_t wst = fork_wgrad ? h->s_wg : st;
+  const bool split = fork_wgrad && rs != nullptr;
   for (int l = h->L - 1; l >= 0; --l) {
     const LayerGeom& g = h->geo[l];
     BnBwdArgs b{};
@@ -551,11 +591,13 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
     if (l == 0) {
       w.A[0] = ps.xg; w.a_stride[0] = ps.xg_stride; w.kc = h->C;
       w.alg_flops = conv_flops(h, 0, ps.n, T, 1);
-      launch_wgrad0(w, wst);
+      if (split && h->L == 1) reduce_upper_on_side(h, *rs, cp.pd, partial, meta, T);
+      launch_wgrad0(w, split ? st : wst);
     } else {
       w.A[0] = AIN(ps, l, slot); w.a_stride[0] = STRIDE(ps, ain, l); w.kc = h->F;
       w.alg_flops = conv_flops(h, l, ps.n, T, 1);
       launch_wgrad(w, wst);
+      if (split && l == 1) reduce_upper_on_side(h, *rs, cp.pd, partial, meta, T);
       if (h->use_tc) {
         TcOp op = tc_op_dz(h, ps, l, slot, h->theta_map, th_step, -1, 0);
         tc_conv(h, l, ps.n, 1, &op, nullptr, 0, DP(ps, l - 1, slot), STRIDE(ps, dp, l - 1), CONV_PLAIN, nullptr, 0, nullptr, T, st);
@@ -571,15 +613,17 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
       }
     }
   }
-  if (fork_wgrad) { cudaEventRecord(h->ev_wg, h->s_wg); cudaStreamWaitEvent(st, h->ev_wg, 0); }
+  if (split) reduce_lower(h, *rs, cp.pd, partial, meta, T, st);
+  else if (fork_wgrad) { cudaEventRecord(h->ev_wg, h->s_wg); cudaStreamWaitEvent(st, h->ev_wg, 0); }
 }
 
 // forward-mode tangent of (support forward + support backward) at step s in direction u  =>  H u into `partial`
 static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const float* u, const float* meta,
-                         const long long* y_support, int T, cudaStream_t st) {
+                         const long long* y_support, int T, cudaStream_t st, const ReduceSpec& rs) {
   const PassSet& sp = h->sup; const PassSet& tn = h->tan;
   for (int l = 0; l < h->L; ++l) {
     const LayerGeom& g = h->geo[l];
+    if (l == 1) join_pending(h, st);
     if (l == 0) {
       Conv0Args a{};
       a.X = sp.xg; a.x_stride = sp.xg_stride;
@@ -624,6 +668,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
     launch_bnact_tan(b, st);
   }
   const ChunkPlan& cp = h->plan_sup;
+  join_pending(h, st);
   {
     HeadArgs a{};
     a.mode = HEAD_TANGENT; a.n = h->n_s; a.N = h->N; a.D = h->D; a.scale = 1.f;
@@ -668,7 +713,8 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
       w.nsrc = 1;
       w.A[0] = sp.xg; w.a_stride[0] = sp.xg_stride; w.kc = h->C;
       w.alg_flops = conv_flops(h, 0, sp.n, T, 1);
-      launch_wgrad0(w, h->s_wg);
+      if (h->L == 1) reduce_upper_on_side(h, rs, cp.pd, h->sup_partial, meta, T);
+      launch_wgrad0(w, st);
     } else {
       w.nsrc = 2;
       w.A[0] = AIN(sp, l, s); w.a_stride[0] = STRIDE(sp, ain, l); w.kc = h->F;
@@ -676,6 +722,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
       w.D[1] = DZ(sp, l, s); w.d_stride[1] = STRIDE(sp, dz, l);
       w.alg_flops = conv_flops(h, l, sp.n, T, 2);
       launch_wgrad(w, h->s_wg);
+      if (l == 1) reduce_upper_on_side(h, rs, cp.pd, h->sup_partial, meta, T);
       if (h->use_tc) {
         TcOp ops[2];
         ops[0] = tc_op_dz(h, tn, l, 0, h->theta_map, s, -1, 0);     // dgrad(W, dz_dot)
@@ -695,11 +742,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
       }
     }
   }
-}
-
-static void join_wgrad(maml_b200_handle* h, cudaStream_t st) {
-  cudaEventRecord(h->ev_wg, h->s_wg);
-  cudaStreamWaitEvent(st, h->ev_wg, 0);
+  reduce_lower(h, rs, cp.pd, h->sup_partial, meta, T, st);
 }
 
 static void pack_theta_step(maml_b200_handle* h, int step, int T, cudaStream_t st) {
@@ -732,6 +775,7 @@ static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it,
   launch_prep_x(x_target, h->tgt.xg, h->tgt.xg_stride, T, h->n_t, h->C, h->H, h->W, st);
   launch_import_theta(h->pl, meta, h->theta, h->Ppad, T, st);
   pack_theta_step(h, 0, T, st);
+  h->wg_pending = false;
 
   // ---------------- phase A: unroll the inner loop.  Support chain on `st`; the target pass of step s (forward at
   // theta^{s+1}, and its backward) only feeds phase B, so it runs on a side stream concurrently with step s+1.
@@ -739,6 +783,7 @@ static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it,
     const float* th = h->theta + (long long)s * TP;
     float* th_next = h->theta + (long long)(s + 1) * TP;
     forward_pass(h, h->sup, s, th, s, meta, s, PASS_SUP_FWD, T, st);
+    join_pending(h, st);
     {
       HeadArgs a{};
       a.mode = HEAD_SUPPORT; a.n = h->n_s; a.N = h->N; a.D = h->D; a.scale = 1.f;
@@ -752,14 +797,15 @@ static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it,
       a.tasks = T;
       launch_head(a, st);
     }
-    backward_pass(h, h->sup, s, th, s, meta, s, PASS_SUP_FWD, PASS_SUP_BWD, h->sup_partial, h->plan_sup, T, st, true);
-    launch_param_reduce(h->pl, h->plan_sup.pd, h->sup_partial, PR_UPDATE, th, th_next, h->g + (long long)s * TP, nullptr, meta, s,
-                        h->Ppad, T, st);
-    pack_theta_step(h, s + 1, T, st);
+    // LSLR update theta^{s+1} = theta^s - alpha[.][s] * g and the tensor-core packs of theta^{s+1}: blocks >= 1 and the
+    // linear layer on the side stream, block 0 at the end of the main chain
+    ReduceSpec rs{PR_UPDATE, th, th_next, h->g + (long long)s * TP, nullptr, s, s + 1};
+    backward_pass(h, h->sup, s, th, s, meta, s, PASS_SUP_FWD, PASS_SUP_BWD, h->sup_partial, h->plan_sup, T, st, true, &rs);
     if (mask & (1u << s)) {
       cudaStream_t ts_ = h->s_tgt;
       CK(cudaEventRecord(h->ev_pack, st));
-      CK(cudaStreamWaitEvent(ts_, h->ev_pack, 0));
+      CK(cudaStreamWaitEvent(ts_, h->ev_pack, 0));       // block-0 weights of theta^{s+1}
+      CK(cudaStreamWaitEvent(ts_, h->ev_wg, 0));         // everything else + packs (side stream)
       const int ts = (h->cfg.reserved & 1) ? s : 0;
       forward_pass(h, h->tgt, ts, th_next, s + 1, meta, s, PASS_TGT_FWD, T, ts_);
       HeadArgs a{};
@@ -798,15 +844,23 @@ static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it,
       const float* th = h->theta + (long long)s * TP;
       const float* tg = nullptr;
       if (mask & (1u << s)) { tg = h->tgrad + (long long)s * TP; CK(cudaStreamWaitEvent(st, h->ev_tgt[s], 0)); }
+      join_pending(h, st);                               // g^s / tbar parts reduced on the side stream
       launch_dots_u(h->pl, h->tbar, tg, h->g + (long long)s * TP, h->u, h->abar, meta, s, h->Ppad, T, st);
       if (it->second_order) {
-        pack_u(h, T, st);
-        tangent_pass(h, s, th, h->u, meta, ys, T, st);
-        join_wgrad(h, st);
-        launch_param_reduce(h->pl, h->plan_sup.pd, h->sup_partial, PR_SUB, nullptr, nullptr, nullptr, h->tbar, meta, s, h->Ppad, T, st);
+        // the tensor-core packs of u are first needed by block 1 of the tangent forward: pack on the side stream
+        // while the main chain runs block 0
+        CK(cudaEventRecord(h->ev_fork, st));
+        CK(cudaStreamWaitEvent(h->s_wg, h->ev_fork, 0));
+        pack_u(h, T, h->s_wg);
+        CK(cudaEventRecord(h->ev_wg, h->s_wg));
+        h->wg_pending = true;
+        ReduceSpec rs{PR_SUB, nullptr, nullptr, nullptr, h->tbar, s, -1};
+        tangent_pass(h, s, th, h->u, meta, ys, T, st, rs);
       }
     }
+    join_pending(h, st);
   } else {
+    join_pending(h, st);
     for (int s = 0; s < it->num_steps; ++s) if (mask & (1u << s)) CK(cudaStreamWaitEvent(st, h->ev_tgt[s], 0));
   }
 

@@ -369,6 +369,7 @@ void launch_wgrad(const WgradArgs& a, cudaStream_t st) {
 // first block wgrad: A = image matrix [rows][c0] (c0 <= 4), D = dz [rows][F].
 // Per 64-row sub-tile the dz rows and the image window (rows +/- halo) are staged in shared memory; thread
 // (grp, f) accumulates the (tap, c) combinations q = grp, grp + NG, ... for output channel f.
+template <int MAXQ>
 __global__ void __launch_bounds__(256) wgrad0_kernel(WgradArgs a) {
   pdl_prologue();
   extern __shared__ float smw[];
@@ -378,8 +379,7 @@ __global__ void __launch_bounds__(256) wgrad0_kernel(WgradArgs a) {
   const int NG = 256 / Fc;
   const int grp = tid / Fc, f = tid - grp * Fc;
   const bool active = grp < NG;
-  const int ncombo = 9 * c0;
-  constexpr int MAXQ = 9;
+  const int ncombo = 9 * c0;            // host guarantees MAXQ * NG >= ncombo
   constexpr int RT = 64;
   const int halo = a.gw + 1;
   float* Ds = smw;                       // [RT][Fc]
@@ -442,7 +442,11 @@ void launch_wgrad0(const WgradArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_WGRAD0, a.alg_flops, st);
   dim3 grid(a.nchunks, a.tasks);
   const size_t smem = (size_t)(64 * a.ncols + (64 + 2 * (a.gw + 1)) * a.kc) * sizeof(float);
-  launch_pdl(wgrad0_kernel, dim3(grid), dim3(256), (size_t)(smem), st, a);
+  const int need = (9 * a.kc + (256 / a.ncols) - 1) / (256 / a.ncols);      // (tap, c) combinations per thread
+  if (need <= 3) launch_pdl(wgrad0_kernel<3>, dim3(grid), dim3(256), (size_t)(smem), st, a);
+  else if (need <= 6) launch_pdl(wgrad0_kernel<6>, dim3(grid), dim3(256), (size_t)(smem), st, a);
+  else if (need <= 9) launch_pdl(wgrad0_kernel<9>, dim3(grid), dim3(256), (size_t)(smem), st, a);
+  else launch_pdl(wgrad0_kernel<36>, dim3(grid), dim3(256), (size_t)(smem), st, a);
   CUDA_CHECK_LAUNCH();
 }
 

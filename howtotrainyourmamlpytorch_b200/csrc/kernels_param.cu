@@ -69,10 +69,11 @@ __device__ __forceinline__ int seg_of(const ParamLayout& pl, long long i) {
 __global__ void param_reduce_kernel(ParamLayout pl, PartialDesc pd, const float* __restrict__ partial, int mode,
                                     const float* __restrict__ theta_in, float* __restrict__ theta_out,
                                     float* __restrict__ g_out, float* __restrict__ tbar,
-                                    const float* __restrict__ meta, int step, long long task_stride) {
+                                    const float* __restrict__ meta, int step, long long task_stride, long long i_lo,
+                                    long long i_hi) {
   pdl_prologue();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= pl.P) return;
+  const long long i = i_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= i_hi) return;
   const int task = blockIdx.y;
   const int seg = seg_of(pl, i);
   const float* p = partial + (long long)task * pd.task_stride + pd.off[seg] + (i - pl.seg_off[seg]);
@@ -92,10 +93,16 @@ __global__ void param_reduce_kernel(ParamLayout pl, PartialDesc pd, const float*
 
 void launch_param_reduce(const ParamLayout& pl, const PartialDesc& pd, const float* partial, int mode,
                          const float* theta_in, float* theta_out, float* g_out, float* tbar, const float* meta, int step,
-                         long long task_stride, int tasks, cudaStream_t st) {
+                         long long task_stride, int tasks, cudaStream_t st, int seg_lo, int seg_hi) {
+  // inner tensors [seg_lo, seg_hi) only (default: all) -- the engine reduces the first block's tensors separately
+  // because their gradient chunks are the last thing a backward pass produces
+  if (seg_hi < 0 || seg_hi > pl.nseg_inner) seg_hi = pl.nseg_inner;
+  if (seg_lo >= seg_hi) return;
+  const long long i_lo = pl.seg_off[seg_lo];
+  const long long i_hi = seg_hi == pl.nseg_inner ? pl.P : pl.seg_off[seg_hi];
   ProfScope prof_scope__(PROF_PARAM, 0.0, st);
-  dim3 grid((unsigned)((pl.P + 255) / 256), tasks);
-  launch_pdl(param_reduce_kernel, dim3(grid), dim3(256), (size_t)(0), st, pl, pd, partial, mode, theta_in, theta_out, g_out, tbar, meta, step, task_stride);
+  dim3 grid((unsigned)((i_hi - i_lo + 255) / 256), tasks);
+  launch_pdl(param_reduce_kernel, dim3(grid), dim3(256), (size_t)(0), st, pl, pd, partial, mode, theta_in, theta_out, g_out, tbar, meta, step, task_stride, i_lo, i_hi);
   CUDA_CHECK_LAUNCH();
 }
 

@@ -23,6 +23,8 @@
 // coalesced global store, + bias, + fp64 BatchNorm statistics).  4-stage smem ring, mbarrier full/empty,
 // tcgen05.commit frees stages and publishes the accumulator.
 #include <cuda.h>
+#include <map>
+#include <utility>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -86,6 +88,21 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// thread-block-cluster helpers (split-K over the CTAs of one cluster, reduction through distributed shared memory)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float dsmem_ld(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ int tap_shift_tc(int tap, int gw) { return (tap / 3 - 1) * gw + (tap % 3 - 1); }
 
 // K-major SWIZZLE_128B descriptor whose start is `row_off` rows into a 1024B-aligned tile.  Measured on B200: the
@@ -126,6 +143,11 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
   const int kchunks = (a.kc + 31) >> 5;          // a ragged last chunk (kc = 16 or 48) is zero-filled by TMA
   const int nph = a.nsrc * kchunks;              // A phases: (source, k-chunk); 9 taps each
   const int nb = a.nb;                           // B ring depth
+  // split-K: the gridDim.z CTAs of a cluster share one output tile; CTA z accumulates stages [st_lo, st_hi) of the
+  // nph * 9 (phase, tap) stages and the partial tiles are summed through distributed shared memory in the epilogue
+  const int nsplit = (int)gridDim.z, zrank = (int)blockIdx.z;
+  const int st_lo = zrank * (nph * 9) / nsplit, st_hi = (zrank + 1) * (nph * 9) / nsplit;
+  const int ph_lo = st_lo / 9, ph_hi = (st_hi - 1) / 9;
   const int abuf = a.rpad * 128;                 // bytes of one A halo buffer (hi or lo)
   uint8_t* bring = smem + 4 * (size_t)abuf;
 
@@ -150,11 +172,12 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
     if (lane == 0) {
       // ===== TMA producer A: per phase (source, k-chunk) ONE halo tile of A (hi, lo); all 9 taps read it at row
       // offsets.  Double-buffered, so phase ph+1 streams in while the MMAs of phase ph run.
-      for (int ph = 0; ph < nph; ++ph) {
+      for (int ph = ph_lo; ph <= ph_hi; ++ph) {
         const int s = ph / kchunks;
         const int kc0 = (ph - s * kchunks) << 5;
-        const int ab = ph & 1;
-        mbar_wait(&a_empty[ab], (((uint32_t)ph >> 1) & 1u) ^ 1u);
+        const int lp = ph - ph_lo;
+        const int ab = lp & 1;
+        mbar_wait(&a_empty[ab], (((uint32_t)lp >> 1) & 1u) ^ 1u);
         const int arow = a.a_row_base[s] + task * a.a_task_rows[s] + j0 - a.halo;
         const uint32_t ad = smem_u32(smem + (size_t)ab * 2 * abuf);
         mbar_arrive_expect_tx(&a_full[ab], 2u * (uint32_t)abuf);
@@ -166,18 +189,17 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
     if (lane == 0) {
       // ===== TMA producer B: one (B_hi, B_lo) stage per (phase, tap) through the ring
       int stage = 0; uint32_t bphase = 0;
-      for (int ph = 0; ph < nph; ++ph) {
+      for (int st = st_lo; st < st_hi; ++st) {
+        const int ph = st / 9, tap = st - ph * 9;
         const int s = ph / kchunks;
         const int kc0 = (ph - s * kchunks) << 5;
-        for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait(&b_empty[stage], bphase ^ 1u);
-          const int brow = a.b_row_base[s] + task * a.b_task_rows[s] + tap * NCOLS;
-          const uint32_t bd = smem_u32(bring + (size_t)stage * BSTAGE);
-          mbar_arrive_expect_tx(&b_full[stage], BSTAGE);
-          tma_load_2d(bd, &maps.m[s * 4 + 2], &b_full[stage], kc0, brow);
-          tma_load_2d(bd + B_BYTES, &maps.m[s * 4 + 3], &b_full[stage], kc0, brow);
-          if (++stage == nb) { stage = 0; bphase ^= 1u; }
-        }
+        mbar_wait(&b_empty[stage], bphase ^ 1u);
+        const int brow = a.b_row_base[s] + task * a.b_task_rows[s] + tap * NCOLS;
+        const uint32_t bd = smem_u32(bring + (size_t)stage * BSTAGE);
+        mbar_arrive_expect_tx(&b_full[stage], BSTAGE);
+        tma_load_2d(bd, &maps.m[s * 4 + 2], &b_full[stage], kc0, brow);
+        tma_load_2d(bd + B_BYTES, &maps.m[s * 4 + 3], &b_full[stage], kc0, brow);
+        if (++stage == nb) { stage = 0; bphase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -190,47 +212,50 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
       // advanced with 64-bit adds on the 16-byte-unit address field (K step: +32 B = +2; tap: row_off * 128 B).
       const uint64_t desc_base = make_desc_sw128(0);
       int stage = 0; uint32_t bphase = 0; int kstep = 0;
-      for (int ph = 0; ph < nph; ++ph) {
-        const int s = ph / kchunks;
-        const int ab = ph & 1;
-        mbar_wait(&a_full[ab], ((uint32_t)ph >> 1) & 1u);
-        if (ph == 0) TC_MARK(2);
-        const uint32_t a_hi = smem_u32(smem + (size_t)ab * 2 * abuf);
-        const uint64_t ahd = desc_base + (uint64_t)(a_hi >> 4);
-        const uint64_t ald = ahd + (uint64_t)(abuf >> 4);
-        const int sgn = a.sign[s];
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait(&b_full[stage], bphase);
-          if (ph == 0 && tap == 0) TC_MARK(3);
-          if (ph == 1 && tap == 0) TC_MARK(4);
-          tc_fence_after();
-          const int row_off = a.halo + sgn * ((tap / 3 - 1) * a.gw + (tap % 3 - 1));    // in [0, 2 * halo]
-          const uint64_t ah0 = ahd + (uint64_t)(row_off * 8);
-          const uint64_t al0 = ald + (uint64_t)(row_off * 8);
-          const uint64_t bh0 = desc_base + (uint64_t)(smem_u32(bring + (size_t)stage * BSTAGE) >> 4);
-          const uint64_t bl0 = bh0 + (uint64_t)(B_BYTES >> 4);
-          if (kstep == 0) {
-            // first four k-steps initialise the five accumulators
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              tc_mma_tf32(tmem_base + 4 * NCOLS, al0 + 2 * k, bh0 + 2 * k, idesc, k > 0 ? 1u : 0u);
-              tc_mma_tf32_acc(tmem_base + 4 * NCOLS, ah0 + 2 * k, bl0 + 2 * k, idesc);
-              tc_mma_tf32(tmem_base + (uint32_t)k * NCOLS, ah0 + 2 * k, bh0 + 2 * k, idesc, 0u);
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              tc_mma_tf32_acc(tmem_base + 4 * NCOLS, al0 + 2 * k, bh0 + 2 * k, idesc);
-              tc_mma_tf32_acc(tmem_base + 4 * NCOLS, ah0 + 2 * k, bl0 + 2 * k, idesc);
-              tc_mma_tf32_acc(tmem_base + (uint32_t)k * NCOLS, ah0 + 2 * k, bh0 + 2 * k, idesc);
-            }
-          }
-          kstep += 4;
-          tc_commit(&b_empty[stage]);            // frees this B stage once the MMAs above have read it
-          if (++stage == nb) { stage = 0; bphase ^= 1u; }
+      uint64_t ahd = 0, ald = 0;
+      int sgn = 1, ab = 0;
+      for (int st = st_lo; st < st_hi; ++st) {
+        const int ph = st / 9, tap = st - ph * 9;
+        if (tap == 0 || st == st_lo) {
+          const int lp = ph - ph_lo;
+          ab = lp & 1;
+          mbar_wait(&a_full[ab], ((uint32_t)lp >> 1) & 1u);
+          if (st == st_lo) TC_MARK(2);
+          const uint32_t a_hi = smem_u32(smem + (size_t)ab * 2 * abuf);
+          ahd = desc_base + (uint64_t)(a_hi >> 4);
+          ald = ahd + (uint64_t)(abuf >> 4);
+          sgn = a.sign[ph / kchunks];
         }
-        tc_commit(&a_empty[ab]);                 // A halo buffer pair reusable after this phase's MMAs
+        mbar_wait(&b_full[stage], bphase);
+        if (st == st_lo) TC_MARK(3);
+        if (st == st_lo + 9) TC_MARK(4);
+        tc_fence_after();
+        const int ty = tap / 3;
+        const int row_off = a.halo + sgn * ((ty - 1) * a.gw + (tap - 3 * ty - 1));    // in [0, 2 * halo]
+        const uint64_t ah0 = ahd + (uint64_t)(row_off * 8);
+        const uint64_t al0 = ald + (uint64_t)(row_off * 8);
+        const uint64_t bh0 = desc_base + (uint64_t)(smem_u32(bring + (size_t)stage * BSTAGE) >> 4);
+        const uint64_t bl0 = bh0 + (uint64_t)(B_BYTES >> 4);
+        if (kstep == 0) {
+          // first four k-steps initialise the five accumulators
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            tc_mma_tf32(tmem_base + 4 * NCOLS, al0 + 2 * k, bh0 + 2 * k, idesc, k > 0 ? 1u : 0u);
+            tc_mma_tf32_acc(tmem_base + 4 * NCOLS, ah0 + 2 * k, bl0 + 2 * k, idesc);
+            tc_mma_tf32(tmem_base + (uint32_t)k * NCOLS, ah0 + 2 * k, bh0 + 2 * k, idesc, 0u);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            tc_mma_tf32_acc(tmem_base + 4 * NCOLS, al0 + 2 * k, bh0 + 2 * k, idesc);
+            tc_mma_tf32_acc(tmem_base + 4 * NCOLS, ah0 + 2 * k, bl0 + 2 * k, idesc);
+            tc_mma_tf32_acc(tmem_base + (uint32_t)k * NCOLS, ah0 + 2 * k, bh0 + 2 * k, idesc);
+          }
+        }
+        kstep += 4;
+        tc_commit(&b_empty[stage]);              // frees this B stage once the MMAs above have read it
+        if (++stage == nb) { stage = 0; bphase ^= 1u; }
+        if (tap == 8 || st == st_hi - 1) tc_commit(&a_empty[ab]);   // A halo buffer pair reusable after this phase's MMAs
       }
       TC_MARK(5);
       tc_commit(&accum_bar);                     // accumulators complete
@@ -273,21 +298,60 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
       tc_ld16(ta + 4 * NCOLS, v4);
       tc_wait_ld();
       float o[16];
+      if (nsplit == 1) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float big = (__uint_as_float(v0[i]) + __uint_as_float(v1[i])) + (__uint_as_float(v2[i]) + __uint_as_float(v3[i]));
-        o[i] = (big + __uint_as_float(v4[i])) + s_bias[c0 + i];
-      }
-      if (grow < a.rows) {
+        for (int i = 0; i < 16; ++i) {
+          const float big = (__uint_as_float(v0[i]) + __uint_as_float(v1[i])) + (__uint_as_float(v2[i]) + __uint_as_float(v3[i]));
+          o[i] = (big + __uint_as_float(v4[i])) + s_bias[c0 + i];
+        }
+        if (grow < a.rows) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(orow + c0 + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
-      }
-      if (want_stats) {
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(orow + c0 + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+        }
+        if (want_stats) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) tile[r * PITCH + c0 + i] = o[i];
+          for (int i = 0; i < 16; ++i) tile[r * PITCH + c0 + i] = o[i];
+        }
+      } else {
+        // split-K partial (no bias): parked in shared memory for the cluster reduction below
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float big = (__uint_as_float(v0[i]) + __uint_as_float(v1[i])) + (__uint_as_float(v2[i]) + __uint_as_float(v3[i]));
+          tile[r * PITCH + c0 + i] = big + __uint_as_float(v4[i]);
+        }
       }
     }
     if (et == 0) TC_MARK(7);
+  }
+
+  // rows [row_lo, row_lo + row_n) of the tile are finished by this CTA (all 128 without split-K)
+  int row_lo = 0, row_n = 128;
+  const float* sbuf = reinterpret_cast<const float*>(smem);   // where those rows live (row index relative to row_lo)
+  if (nsplit > 1) {
+    __syncwarp();
+    cluster_sync_all();                            // every CTA's partial tile is in its shared memory
+    row_n = 128 / nsplit; row_lo = zrank * row_n;
+    float* tile2 = reinterpret_cast<float*>(smem + 36 * 1024);
+    sbuf = tile2;
+    if (warp >= 2 && warp < 6) {
+      const int et = threadIdx.x - 64;
+      const uint32_t tile_local = smem_u32(smem);
+      for (int idx = et; idx < row_n * NCOLS; idx += 128) {
+        const int rr = idx / NCOLS, col = idx - rr * NCOLS;
+        const uint32_t off = (uint32_t)(((row_lo + rr) * PITCH + col) * 4);
+        float acc = 0.f;
+        for (int z = 0; z < nsplit; ++z) acc += dsmem_ld(dsmem_addr(tile_local + off, (uint32_t)z));   // fixed order: deterministic
+        acc += a.bias ? a.bias[(long long)task * a.bias_stride + col] : 0.f;
+        tile2[rr * PITCH + col] = acc;
+        const int g = j0 + row_lo + rr;
+        if (g < a.rows) a.out[(long long)task * a.out_stride + (long long)g * NCOLS + col] = acc;
+      }
+    }
+  }
+
+  if (warp >= 2 && warp < 6) {
+    const int et = threadIdx.x - 64;
+    const bool want_stats = (a.mode != CONV_PLAIN);
     if (want_stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const float* zh = a.zh ? a.zh + (long long)task * a.zh_stride : nullptr;
@@ -295,12 +359,12 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
       const int col = et % NCOLS, part = et / NCOLS;
       double s1 = 0.0, s2 = 0.0;
       if (part < PARTS) {
-        for (int rr = part; rr < 128; rr += PARTS) {
-          if (row_ok[rr]) {
-            const float v = tile[rr * PITCH + col];
+        for (int rr = part; rr < row_n; rr += PARTS) {
+          if (row_ok[row_lo + rr]) {
+            const float v = sbuf[rr * PITCH + col];
             if (a.mode == CONV_FWD_STATS) { s1 += (double)v; s2 += (double)v * (double)v; }
             else {
-              const float zv = zh[(long long)(j0 + rr) * NCOLS + col];
+              const float zv = zh[(long long)(j0 + row_lo + rr) * NCOLS + col];
               s1 += (double)v; s2 += (double)zv * (double)v;
             }
           }
@@ -318,6 +382,10 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
         atomicAdd(&stats[c * 2 + which], sred[0][c][which] + sred[1][c][which]);
       }
     }
+  }
+  if (nsplit > 1) {
+    __syncwarp();
+    cluster_sync_all();                            // nobody leaves while a peer still reads its partial tile
   }
 
   if (threadIdx.x == 64) TC_MARK(8);
@@ -354,14 +422,60 @@ int tc_conv_prepare() {
   return (e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess && e4 == cudaSuccess) ? 0 : 1;
 }
 
+// Split-K factor: small layers have fewer tiles than SMs (Omniglot block 3: 8 tiles, block 2: 32), and one tile's
+// serial pipeline (~18 stages x ~1000 cycles) is then the whole kernel.  Spreading the (phase, tap) stages of a tile
+// over a cluster of S CTAs shortens that to 18 / S stages + one distributed-shared-memory reduction.  S is the largest
+// of {8, 4, 2} whose clusters are all co-resident (asked from the occupancy calculator once per shape).
+static int g_tc_split_max = 8;       // env MAML_B200_TC_SPLIT (1 disables split-K)
+template <int NCOLS>
+static int max_clusters(size_t smem, int S) {
+  static std::map<std::pair<size_t, int>, int> cache;
+  auto it = cache.find({smem, S});
+  if (it != cache.end()) return it->second;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(1, 1, S); cfg.blockDim = dim3(224); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = S;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<NCOLS>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  cache[{smem, S}] = n;
+  return n;
+}
+
+template <int NCOLS>
+static void launch_conv_tc_n(const TcMaps& maps, const TcConvArgs& a, size_t smem, cudaStream_t st) {
+  const int tiles = ((a.rows + 127) / 128) * (a.plan_tasks > a.tasks ? a.plan_tasks : a.tasks);
+  const int stages = a.nsrc * ((a.kc + 31) / 32) * 9;
+  int S = 1;
+  for (int cand = g_tc_split_max; cand >= 2; cand >>= 1) {
+    if (cand > 8 || stages < 2 * cand) continue;
+    if (tiles <= max_clusters<NCOLS>(smem, cand)) { S = cand; break; }
+  }
+  dim3 grid((a.rows + 127) / 128, a.tasks, S);
+  if (S == 1) {
+    launch_pdl(conv_tc_kernel<NCOLS>, grid, dim3(224), smem, st, maps, a);
+    return;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = dim3(224); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = S;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, conv_tc_kernel<NCOLS>, maps, a);
+}
+
+void tc_conv_set_split(int max_split) { g_tc_split_max = max_split < 1 ? 1 : (max_split > 8 ? 8 : max_split); }
+
 void launch_conv_tc(const TcMaps& maps, const TcConvArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_CONV, a.alg_flops, st);
-  dim3 grid((a.rows + 127) / 128, a.tasks);
   const size_t smem = tc_conv_smem_bytes(a.ncols, a.gw);
-  if (a.ncols == 64) launch_pdl(conv_tc_kernel<64>, dim3(grid), dim3(224), (size_t)(smem), st, maps, a);
-  else if (a.ncols == 48) launch_pdl(conv_tc_kernel<48>, dim3(grid), dim3(224), (size_t)(smem), st, maps, a);
-  else if (a.ncols == 32) launch_pdl(conv_tc_kernel<32>, dim3(grid), dim3(224), (size_t)(smem), st, maps, a);
-  else launch_pdl(conv_tc_kernel<16>, dim3(grid), dim3(224), (size_t)(smem), st, maps, a);
+  if (a.ncols == 64) launch_conv_tc_n<64>(maps, a, smem, st);
+  else if (a.ncols == 48) launch_conv_tc_n<48>(maps, a, smem, st);
+  else if (a.ncols == 32) launch_conv_tc_n<32>(maps, a, smem, st);
+  else launch_conv_tc_n<16>(maps, a, smem, st);
   CUDA_CHECK_LAUNCH();
 }
 

@@ -7,6 +7,8 @@ struct alignas(64) TcMaps { CUtensorMap m[8]; };   // per source: A_hi, A_lo, B_
 
 struct TcConvArgs {
   int nsrc, kc, rows, gw, G, h, w, ncols, mode, tasks;
+  int plan_tasks;        // split-K is planned for this many tasks (the handle's max_tasks) so that a task's arithmetic
+                         // does not depend on how many tasks share the call
   int halo, rpad, nb, bo_mode, timeline;   // halo = gw + 1 rows; rpad = halo-tile rows (multiple of 8); nb = B ring depth
   int a_row_base[2];     // row (in the A tensor map) of grid row 0 of task 0 for this pass slot (includes the guard)
   int a_task_rows[2];    // rows per task in the A tensor map
@@ -24,6 +26,7 @@ int tc_conv_rpad(int gw);
 int tc_conv_ring(int ncols, int gw);
 size_t tc_conv_smem_bytes(int ncols, int gw);
 int tc_conv_prepare();
+void tc_conv_set_split(int max_split);   // largest split-K cluster size (1 = off)
 int tc_read_timeline(long long* out16);
 void launch_conv_tc(const TcMaps& maps, const TcConvArgs& a, cudaStream_t st);
 void launch_pack_weights(const ParamLayout& pl, const float* theta, long long theta_task_stride, float* pack,

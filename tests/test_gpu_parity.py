@@ -90,6 +90,9 @@ def test_stagewise_against_oracle(case, cuda_device):
         for n, v in inter["sup_g"][s].items():
             if "conv.bias" in n:
                 chk("g[%d] %s" % (s, n[-22:]), gg[n], v, absolute=1e-5)
+            elif "linear.bias" in n:
+                # sum_rows (softmax - onehot): cancels to ~1e-2 of its terms, so fp32 rounding shows up larger
+                chk("g[%d] %s" % (s, n[-22:]), gg[n], v, tol=2e-4)
             else:
                 chk("g[%d] %s" % (s, n[-22:]), gg[n], v, tol=5e-5)
     _report(case + " stagewise", rows)
