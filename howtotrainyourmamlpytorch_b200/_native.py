@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = [
     "maml_b200_result_size", "maml_b200_meta_batch_fwd_bwd", "maml_b200_adam_step",
     "maml_b200_running_stats_update", "maml_b200_debug_read", "maml_b200_last_launch_count",
     "maml_b200_profile", "maml_b200_profile_read", "maml_b200_net_forward",
+    "maml_b200_trace", "maml_b200_trace_read",
 ]
 PROF_CATS = ["conv_igemm", "conv_first_block", "wgrad", "wgrad_first_block", "bn_act_pool", "head", "param"]
 
@@ -82,6 +83,10 @@ def load_library():
     lib.maml_b200_debug_read.restype = i64
     lib.maml_b200_last_launch_count.argtypes = [vp]
     lib.maml_b200_last_launch_count.restype = i64
+    lib.maml_b200_trace.argtypes = [vp, i32]
+    lib.maml_b200_trace.restype = ctypes.c_int
+    lib.maml_b200_trace_read.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), i64]
+    lib.maml_b200_trace_read.restype = i64
     lib.maml_b200_profile.argtypes = [vp, i32]
     lib.maml_b200_profile.restype = ctypes.c_int
     lib.maml_b200_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
@@ -166,6 +171,17 @@ class Engine(object):
         rc = self.lib.maml_b200_running_stats_update(self.h, result.data_ptr(), running_mean.data_ptr(),
                                                      running_var.data_ptr(), arr, self._stream())
         _check(self.lib, rc, "maml_b200_running_stats_update")
+
+    def trace(self, enable):
+        _check(self.lib, self.lib.maml_b200_trace(self.h, int(bool(enable))), "maml_b200_trace")
+
+    def trace_read(self, capacity=4096):
+        """[(t_ns, kernel_id)] of every kernel started since trace(True) / the last read, in start order."""
+        buf = (ctypes.c_uint64 * capacity)()
+        n = self.lib.maml_b200_trace_read(self.h, buf, capacity)
+        if n < 0:
+            raise RuntimeError("maml_b200_trace_read: " + self.lib.maml_b200_last_error().decode())
+        return [(int(buf[i]) >> 8, int(buf[i]) & 0xff) for i in range(n)]
 
     def profile(self, enable):
         _check(self.lib, self.lib.maml_b200_profile(self.h, int(bool(enable))), "maml_b200_profile")

@@ -188,6 +188,9 @@ void launch_bnbwd_reduce(const BnBwdArgs& a, cudaStream_t st);
 void launch_bnbwd_apply(const BnBwdArgs& a, cudaStream_t st);
 void launch_bnbwd_tan_reduce(const BnBwdTanArgs& a, cudaStream_t st);
 void launch_bnbwd_tan_apply(const BnBwdTanArgs& a, cudaStream_t st);
+void launch_bnbwd(const BnBwdArgs& a, cudaStream_t st);          // reduce + apply (one cluster kernel for small blocks)
+void launch_bnbwd_tan(const BnBwdTanArgs& a, cudaStream_t st);
+void bn_set_fuse(int on);
 void launch_head(const HeadArgs& a, cudaStream_t st);
 
 void launch_import_theta(const ParamLayout& pl, const float* meta, float* theta0, long long theta_task_stride,
@@ -234,7 +237,31 @@ enum { PASS_SUP_FWD = 0, PASS_SUP_BWD = 1, PASS_TGT_FWD = 2, PASS_TGT_BWD = 3, P
 // own durations, not the launch gaps, set the critical path -- so the attribute is OFF unless MAML_B200_PDL=1.
 // ---------------------------------------------------------------------------------------------
 extern int g_use_pdl;
-__device__ __forceinline__ void pdl_prologue() {
+extern int g_launch_prio;
+
+// Device-side launch trace (debug; maml_b200_trace): CTA (0,0,0) of every kernel appends (globaltimer ns << 8 | kernel
+// id) to a buffer -> the start-time sequence of one captured iteration, the only timeline available without nsys.
+// One pointer copy per translation unit (no relocatable device code), all set to the same buffer; null = off.
+static __device__ unsigned long long* t_trace_buf = nullptr;
+#define MAML_TRACE_SETTER(fn) void fn(unsigned long long* p) { cudaMemcpyToSymbol(t_trace_buf, &p, sizeof(p)); }
+#define MAML_TRACE_CAP 4094
+__device__ __forceinline__ void trace_mark(int kid) {
+  unsigned long long* t = t_trace_buf;
+  if (t != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    const unsigned long long slot = atomicAdd(t, 1ULL);
+    if (slot < MAML_TRACE_CAP) t[1 + slot] = (now << 8) | (unsigned long long)(kid & 0xff);
+  }
+}
+void trace_set_conv(unsigned long long* p);
+void trace_set_bn(unsigned long long* p);
+void trace_set_head(unsigned long long* p);
+void trace_set_param(unsigned long long* p);
+void trace_set_tc(unsigned long long* p);
+
+__device__ __forceinline__ void pdl_prologue(int kid = 0) {
+  trace_mark(kid);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
@@ -244,10 +271,16 @@ template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  if (g_launch_prio) {          // explicit per-launch priority = the stream's (captured graph nodes keep it)
+    int prio = 0;
+    cudaStreamGetPriority(st, &prio);
+    attr[1].id = cudaLaunchAttributePriority; attr[1].val.priority = prio;
+    cfg.numAttrs = 2;
+  }
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

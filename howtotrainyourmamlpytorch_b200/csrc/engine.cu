@@ -170,7 +170,8 @@ static void plan_chunks(maml_b200_handle* h, int n, ChunkPlan* cp) {
     if (l == 0) {
       nch = (int)std::min<long long>(512, std::max<long long>(1, (rows + 63) / 64));
     } else {
-      nch = (int)std::min<long long>(64, std::max<long long>(1, (rows + 127) / 128));
+      static const int wg_rows = getenv("MAML_B200_WG_ROWS") ? atoi(getenv("MAML_B200_WG_ROWS")) : 128;
+      nch = (int)std::min<long long>(64, std::max<long long>(1, (rows + wg_rows - 1) / wg_rows));
     }
     rpc = (int)rup((rows + nch - 1) / nch, 16);
     nch = (int)((rows + rpc - 1) / rpc);
@@ -337,6 +338,8 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   h->use_tc = (h->L > 1) && !(cfg->reserved & 2);
   if (const char* bo = getenv("MAML_B200_TC_BO")) h->tc_bo_mode = atoi(bo);
   if (const char* sp = getenv("MAML_B200_TC_SPLIT")) tc_conv_set_split(atoi(sp));
+  g_launch_prio = getenv("MAML_B200_LAUNCH_PRIO") ? 1 : 0;
+  if (const char* bf = getenv("MAML_B200_BN_FUSE")) bn_set_fuse(atoi(bf));
   for (int l = 1; l < h->L && h->use_tc; ++l)
     if (tc_conv_rpad(h->geo[l].gw) > 256 || tc_conv_ring(h->F, h->geo[l].gw) < 2) h->use_tc = false;   // image too wide for one halo box      // F in {16, 32, 48, 64}: ragged K chunks are zero-filled by TMA
   plan_chunks(h, h->n_s, &h->plan_sup);
@@ -355,9 +358,16 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   if (e != cudaSuccess) { cudaFree(h->ws); delete h; return fail(std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
   h->use_graphs = !(cfg->reserved & 4) && !getenv("MAML_B200_NO_GRAPH");
   g_use_pdl = getenv("MAML_B200_PDL") ? 1 : 0;   // measured: no gain inside the captured graph (4.16 vs 4.02 ms), so off by default
-  bool ok = cudaStreamCreateWithFlags(&h->s_cap, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&h->s_tgt, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&h->s_wg, cudaStreamNonBlocking) == cudaSuccess &&
+  // Priorities: the support chain (capture stream) is the critical path; the weight-gradient and target streams only
+  // have to finish by the end of a step.  Their many small CTAs would otherwise occupy every SM and keep the
+  // whole-SM tcgen05 conv CTAs of the critical path waiting (measured: ~20 us per step).
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);      // lo = numerically largest = least urgent
+  const bool use_prio = getenv("MAML_B200_NO_PRIO") == nullptr;
+  const int p_main = use_prio ? prio_hi : 0, p_tgt = use_prio ? std::min(prio_lo, prio_hi + 1) : 0, p_wg = use_prio ? prio_lo : 0;
+  bool ok = cudaStreamCreateWithPriority(&h->s_cap, cudaStreamNonBlocking, p_main) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&h->s_tgt, cudaStreamNonBlocking, p_tgt) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&h->s_wg, cudaStreamNonBlocking, p_wg) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->ev_wg, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming) == cudaSuccess;
@@ -500,7 +510,7 @@ static void tc_conv(maml_b200_handle* h, int l, int n, int nsrc, const TcOp* ops
   TcMaps maps;
   TcConvArgs a{};
   a.nsrc = nsrc; a.kc = h->F; a.rows = n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.ncols = h->F; a.mode = mode; a.tasks = T; a.plan_tasks = h->maxT;
-  a.halo = g.gw + 1; a.rpad = tc_conv_rpad(g.gw); a.nb = tc_conv_ring(h->F, g.gw); a.bo_mode = h->tc_bo_mode; a.timeline = getenv("MAML_B200_TC_TIMELINE") ? 1 : 0;
+  a.halo = g.gw + 1; a.rpad = tc_conv_rpad(g.gw); a.nb = tc_conv_ring(h->F, g.gw); a.bo_mode = h->tc_bo_mode; { const char* tl = getenv("MAML_B200_TC_TIMELINE"); a.timeline = (tl && (atoi(tl) <= 0 || atoi(tl) == l)) ? 1 : 0; }
   for (int s = 0; s < nsrc; ++s) {
     maps.m[s * 4 + 0] = ops[s].a_maps[0]; maps.m[s * 4 + 1] = ops[s].a_maps[1];
     maps.m[s * 4 + 2] = ops[s].b_maps[ops[s].b_pair]; maps.m[s * 4 + 3] = ops[s].b_maps[ops[s].b_pair + 1];
@@ -577,8 +587,7 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
     b.dz = DZ(ps, l, slot); b.dz_stride = STRIDE(ps, dz, l);
     if (h->use_tc && l >= 1) { b.dz_hi = DZ_HI(ps, l, slot); b.dz_lo = DZ_LO(ps, l, slot); }
     b.g = bn_geom(h, l, ps.n); b.tasks = T;
-    launch_bnbwd_reduce(b, st);
-    launch_bnbwd_apply(b, st);
+    launch_bnbwd(b, st);
     if (fork_wgrad) { cudaEventRecord(h->ev_fork, st); cudaStreamWaitEvent(h->s_wg, h->ev_fork, 0); }
 
     WgradArgs w{};
@@ -596,8 +605,7 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
     } else {
       w.A[0] = AIN(ps, l, slot); w.a_stride[0] = STRIDE(ps, ain, l); w.kc = h->F;
       w.alg_flops = conv_flops(h, l, ps.n, T, 1);
-      launch_wgrad(w, wst);
-      if (split && l == 1) reduce_upper_on_side(h, *rs, cp.pd, partial, meta, T);
+      // dgrad (critical path) is enqueued before the side-stream wgrad so that its CTAs get SMs first
       if (h->use_tc) {
         TcOp op = tc_op_dz(h, ps, l, slot, h->theta_map, th_step, -1, 0);
         tc_conv(h, l, ps.n, 1, &op, nullptr, 0, DP(ps, l - 1, slot), STRIDE(ps, dp, l - 1), CONV_PLAIN, nullptr, 0, nullptr, T, st);
@@ -611,6 +619,8 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
         a.alg_flops = conv_flops(h, l, ps.n, T, 1);
         launch_conv_rows(a, st);
       }
+      launch_wgrad(w, wst);
+      if (split && l == 1) reduce_upper_on_side(h, *rs, cp.pd, partial, meta, T);
     }
   }
   if (split) reduce_lower(h, *rs, cp.pd, partial, meta, T, st);
@@ -699,8 +709,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
     b.dzdot = DZ(tn, l, 0); b.dzdot_stride = STRIDE(tn, dz, l);
     if (h->use_tc && l >= 1) { b.dzdot_hi = DZ_HI(tn, l, 0); b.dzdot_lo = DZ_LO(tn, l, 0); }
     b.g = bn_geom(h, l, sp.n); b.tasks = T;
-    launch_bnbwd_tan_reduce(b, st);
-    launch_bnbwd_tan_apply(b, st);
+    launch_bnbwd_tan(b, st);
     cudaEventRecord(h->ev_fork, st); cudaStreamWaitEvent(h->s_wg, h->ev_fork, 0);
 
     WgradArgs w{};
@@ -721,8 +730,6 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
       w.A[1] = AIN(tn, l, 0); w.a_stride[1] = STRIDE(tn, ain, l);
       w.D[1] = DZ(sp, l, s); w.d_stride[1] = STRIDE(sp, dz, l);
       w.alg_flops = conv_flops(h, l, sp.n, T, 2);
-      launch_wgrad(w, h->s_wg);
-      if (l == 1) reduce_upper_on_side(h, rs, cp.pd, h->sup_partial, meta, T);
       if (h->use_tc) {
         TcOp ops[2];
         ops[0] = tc_op_dz(h, tn, l, 0, h->theta_map, s, -1, 0);     // dgrad(W, dz_dot)
@@ -740,6 +747,8 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
         a.alg_flops = conv_flops(h, l, sp.n, T, 2);
         launch_conv_rows(a, st);
       }
+      launch_wgrad(w, h->s_wg);
+      if (l == 1) reduce_upper_on_side(h, rs, cp.pd, h->sup_partial, meta, T);
     }
   }
   reduce_lower(h, rs, cp.pd, h->sup_partial, meta, T, st);
@@ -1015,6 +1024,37 @@ extern "C" int maml_b200_profile_read(maml_b200_handle* h, double* ms_by_cat, do
   }
   h->prof.reset();
   return 0;
+}
+
+// device-side launch trace (common.cuh: trace_mark): start timestamps of every kernel of the following calls
+static unsigned long long* g_trace_dev = nullptr;
+static void trace_set_all(unsigned long long* p) {
+  trace_set_conv(p); trace_set_bn(p); trace_set_head(p); trace_set_param(p); trace_set_tc(p);
+}
+extern "C" int maml_b200_trace(maml_b200_handle* h, int32_t enable) {
+  if (!h) return fail("null argument");
+  CK(cudaDeviceSynchronize());
+  if (enable) {
+    if (!g_trace_dev) CK(cudaMalloc(&g_trace_dev, (size_t)(MAML_TRACE_CAP + 2) * sizeof(unsigned long long)));
+    CK(cudaMemset(g_trace_dev, 0, (size_t)(MAML_TRACE_CAP + 2) * sizeof(unsigned long long)));
+    trace_set_all(g_trace_dev);
+  } else {
+    trace_set_all(nullptr);
+  }
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+// out[i] = (globaltimer_ns << 8) | kernel id, in start order; returns the number of entries (<0: error); clears the trace
+extern "C" int64_t maml_b200_trace_read(maml_b200_handle* h, uint64_t* out, int64_t capacity) {
+  if (!h || !out || !g_trace_dev) { fail("trace is not enabled"); return -1; }
+  if (cudaDeviceSynchronize() != cudaSuccess) { fail("device error"); return -1; }
+  unsigned long long n = 0;
+  cudaMemcpy(&n, g_trace_dev, sizeof(n), cudaMemcpyDeviceToHost);
+  if (n > MAML_TRACE_CAP) n = MAML_TRACE_CAP;
+  const long long k = std::min<long long>((long long)n, capacity);
+  cudaMemcpy(out, g_trace_dev + 1, (size_t)k * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemset(g_trace_dev, 0, sizeof(unsigned long long));
+  return (int64_t)k;
 }
 
 // ---------------------------------------------------------------------------------------------

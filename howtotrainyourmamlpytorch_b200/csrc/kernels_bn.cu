@@ -60,7 +60,7 @@ struct WinIter {
 
 // ------------------------------------------------------------------------------- forward
 __global__ void __launch_bounds__(256) bnact_kernel(BnActArgs a) {
-  pdl_prologue();
+  pdl_prologue(6);
   __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64];
   const BnGeom g = a.g;
   const int task = blockIdx.y;
@@ -172,9 +172,75 @@ __device__ __forceinline__ void block_reduce_stats(double (&s1)[4], double (&s2)
   }
 }
 
+// ---- thread-block-cluster helpers for the fused (reduce -> cluster all-reduce -> apply) backward kernels
+__device__ __forceinline__ void bn_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t bn_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t bn_cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ double bn_dsmem_ld_f64(const double* local, uint32_t rank) {
+  const uint32_t la = (uint32_t)__cvta_generic_to_shared(local);
+  uint32_t ra; double v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+  return v;
+}
+// CTA totals of the per-thread partials into shared memory (fixed summation order)
+__device__ __forceinline__ void block_reduce_to_smem(double (&s1)[4], double (&s2)[4], const WinIter& it, double* tot, int F) {
+  __shared__ double red2[256 * 8];
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { red2[tid * 8 + c * 2] = s1[c]; red2[tid * 8 + c * 2 + 1] = s2[c]; }
+  __syncthreads();
+  for (int o = tid; o < F * 2; o += blockDim.x) {
+    const int ch = o >> 1, which = o & 1;
+    const int q = ch >> 2, comp = ch & 3;
+    double t = 0.0;
+    for (int l = 0; l < it.WPB; ++l) t += red2[(l * it.F4 + q) * 8 + comp * 2 + which];
+    tot[o] = t;
+  }
+}
+// sum the CTA totals of all CTAs of the cluster (rank order), publish sums / m in shared memory and (rank 0) the raw
+// sums in the global statistics arena
+__device__ __forceinline__ void cluster_allreduce_stats(const double* tot, int F, double m, float* s_a, float* s_b2, double* gstats) {
+  __syncthreads();
+  bn_cluster_sync();
+  const uint32_t n = bn_cluster_size();
+  const int tid = threadIdx.x;
+  if (tid < F * 2) {
+    double t = 0.0;
+    for (uint32_t z = 0; z < n; ++z) t += bn_dsmem_ld_f64(tot + tid, z);
+    ((tid & 1) ? s_b2 : s_a)[tid >> 1] = (float)(t / m);
+    if (bn_cluster_rank() == 0) gstats[tid] = t;
+  }
+  bn_cluster_sync();
+}
+
 // ------------------------------------------------------------------------------- backward: reduce
+__device__ __forceinline__ void bnbwd_reduce_phase(const BnBwdArgs& a, const BnGeom& g, int task, int cta, int ncta, const WinIter& it,
+                                                   const float* s_g, const float* s_b, double (&s1)[4], double (&s2)[4]) {
+  if (it.lane >= it.WPB) return;
+  const float4 ga = ld4s(s_g, it.q), be = ld4s(s_b, it.q);
+  const float* zhp = a.zh + (long long)task * a.zh_stride;
+  const float* dp = a.dp + (long long)task * a.dp_stride;
+  for (int wi = cta * it.WPB + it.lane; wi < it.NW; wi += ncta * it.WPB) {
+    const int img = wi / (it.hc * it.wc);
+    const int rem = wi - img * it.hc * it.wc;
+    const int wy = rem / it.wc, wx = rem - wy * it.wc;
+    if (wy >= g.ph || wx >= g.pw) continue;
+    float4 zh[4]; long long idx[4]; int4 arg; float4 sl;
+    argmax_window(zhp, g, img, wy, wx, it.q, ga, be, zh, idx, arg, sl);
+    const float4 d = ld4(dp + ((long long)img * g.pG + (wy + g.pb) * g.pgw + (wx + g.pb)) * g.F + it.q * 4);
+    const float dy0 = d.x * sl.x, dy1 = d.y * sl.y, dy2 = d.z * sl.z, dy3 = d.w * sl.w;
+    s1[0] += dy0; s2[0] += (double)dy0 * (double)pick(zh, arg.x, 0);
+    s1[1] += dy1; s2[1] += (double)dy1 * (double)pick(zh, arg.y, 1);
+    s1[2] += dy2; s2[2] += (double)dy2 * (double)pick(zh, arg.z, 2);
+    s1[3] += dy3; s2[3] += (double)dy3 * (double)pick(zh, arg.w, 3);
+  }
+}
+
 __global__ void __launch_bounds__(256) bnbwd_reduce_kernel(BnBwdArgs a) {
-  pdl_prologue();
+  pdl_prologue(7);
   __shared__ float s_g[64], s_b[64];
   const BnGeom g = a.g;
   const int task = blockIdx.y;
@@ -182,25 +248,7 @@ __global__ void __launch_bounds__(256) bnbwd_reduce_kernel(BnBwdArgs a) {
   __syncthreads();
   WinIter it(g);
   double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-  if (it.lane < it.WPB) {
-    const float4 ga = ld4s(s_g, it.q), be = ld4s(s_b, it.q);
-    const float* zhp = a.zh + (long long)task * a.zh_stride;
-    const float* dp = a.dp + (long long)task * a.dp_stride;
-    for (int wi = blockIdx.x * it.WPB + it.lane; wi < it.NW; wi += gridDim.x * it.WPB) {
-      const int img = wi / (it.hc * it.wc);
-      const int rem = wi - img * it.hc * it.wc;
-      const int wy = rem / it.wc, wx = rem - wy * it.wc;
-      if (wy >= g.ph || wx >= g.pw) continue;
-      float4 zh[4]; long long idx[4]; int4 arg; float4 sl;
-      argmax_window(zhp, g, img, wy, wx, it.q, ga, be, zh, idx, arg, sl);
-      const float4 d = ld4(dp + ((long long)img * g.pG + (wy + g.pb) * g.pgw + (wx + g.pb)) * g.F + it.q * 4);
-      const float dy0 = d.x * sl.x, dy1 = d.y * sl.y, dy2 = d.z * sl.z, dy3 = d.w * sl.w;
-      s1[0] += dy0; s2[0] += (double)dy0 * (double)pick(zh, arg.x, 0);
-      s1[1] += dy1; s2[1] += (double)dy1 * (double)pick(zh, arg.y, 1);
-      s1[2] += dy2; s2[2] += (double)dy2 * (double)pick(zh, arg.z, 2);
-      s1[3] += dy3; s2[3] += (double)dy3 * (double)pick(zh, arg.w, 3);
-    }
-  }
+  bnbwd_reduce_phase(a, g, task, blockIdx.x, gridDim.x, it, s_g, s_b, s1, s2);
   block_reduce_stats(s1, s2, it, a.stats_bwd + (long long)task * a.stats_bwd_stride, g.F);
 }
 
@@ -214,27 +262,16 @@ void launch_bnbwd_reduce(const BnBwdArgs& a, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------- backward: apply
 // dz = r * gamma * (dy - S1/m - zh * S2/m)   at every valid position (dy != 0 only at the arg-max)
-__global__ void __launch_bounds__(256) bnbwd_apply_kernel(BnBwdArgs a) {
-  pdl_prologue();
-  __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_c1[64], s_c2[64];
-  const BnGeom g = a.g;
-  const int task = blockIdx.y;
-  const double m = (double)g.n * g.h * g.w;
-  chan_setup(a.stats_fwd + (long long)task * a.stats_fwd_stride, a.gamma, a.beta, m, g.F, s_mu, s_r, s_g, s_b);
-  if (threadIdx.x < g.F) {
-    const double* sb = a.stats_bwd + (long long)task * a.stats_bwd_stride;
-    s_c1[threadIdx.x] = (float)(sb[threadIdx.x * 2] / m);
-    s_c2[threadIdx.x] = (float)(sb[threadIdx.x * 2 + 1] / m);
-  }
-  __syncthreads();
-  WinIter it(g);
+__device__ __forceinline__ void bnbwd_apply_phase(const BnBwdArgs& a, const BnGeom& g, int task, int cta, int ncta, const WinIter& it,
+                                                  const float* s_r, const float* s_g, const float* s_b, const float* s_c1,
+                                                  const float* s_c2) {
   if (it.lane >= it.WPB) return;
   const float4 r = ld4s(s_r, it.q), ga = ld4s(s_g, it.q), be = ld4s(s_b, it.q), c1 = ld4s(s_c1, it.q), c2 = ld4s(s_c2, it.q);
   const float4 rg = make_float4(r.x * ga.x, r.y * ga.y, r.z * ga.z, r.w * ga.w);
   const float* zhp = a.zh + (long long)task * a.zh_stride;
   const float* dp = a.dp + (long long)task * a.dp_stride;
   float* dz = a.dz + (long long)task * a.dz_stride;
-  for (int wi = blockIdx.x * it.WPB + it.lane; wi < it.NW; wi += gridDim.x * it.WPB) {
+  for (int wi = cta * it.WPB + it.lane; wi < it.NW; wi += ncta * it.WPB) {
     const int img = wi / (it.hc * it.wc);
     const int rem = wi - img * it.hc * it.wc;
     const int wy = rem / it.wc, wx = rem - wy * it.wc;
@@ -272,6 +309,74 @@ __global__ void __launch_bounds__(256) bnbwd_apply_kernel(BnBwdArgs a) {
   }
 }
 
+__global__ void __launch_bounds__(256) bnbwd_apply_kernel(BnBwdArgs a) {
+  pdl_prologue(8);
+  __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_c1[64], s_c2[64];
+  const BnGeom g = a.g;
+  const int task = blockIdx.y;
+  const double m = (double)g.n * g.h * g.w;
+  chan_setup(a.stats_fwd + (long long)task * a.stats_fwd_stride, a.gamma, a.beta, m, g.F, s_mu, s_r, s_g, s_b);
+  if (threadIdx.x < g.F) {
+    const double* sb = a.stats_bwd + (long long)task * a.stats_bwd_stride;
+    s_c1[threadIdx.x] = (float)(sb[threadIdx.x * 2] / m);
+    s_c2[threadIdx.x] = (float)(sb[threadIdx.x * 2 + 1] / m);
+  }
+  __syncthreads();
+  WinIter it(g);
+  bnbwd_apply_phase(a, g, task, blockIdx.x, gridDim.x, it, s_r, s_g, s_b, s_c1, s_c2);
+}
+
+// fused: one cluster of CTAs per task does reduce -> all-reduce through distributed shared memory -> apply
+__global__ void __launch_bounds__(256) bnbwd_fused_kernel(BnBwdArgs a) {
+  pdl_prologue(9);
+  __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_c1[64], s_c2[64];
+  __shared__ double tot[128];
+  const BnGeom g = a.g;
+  const int task = blockIdx.y;
+  const double m = (double)g.n * g.h * g.w;
+  chan_setup(a.stats_fwd + (long long)task * a.stats_fwd_stride, a.gamma, a.beta, m, g.F, s_mu, s_r, s_g, s_b);
+  __syncthreads();
+  WinIter it(g);
+  double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  bnbwd_reduce_phase(a, g, task, blockIdx.x, gridDim.x, it, s_g, s_b, s1, s2);
+  block_reduce_to_smem(s1, s2, it, tot, g.F);
+  cluster_allreduce_stats(tot, g.F, m, s_c1, s_c2, a.stats_bwd + (long long)task * a.stats_bwd_stride);
+  bnbwd_apply_phase(a, g, task, blockIdx.x, gridDim.x, it, s_r, s_g, s_b, s_c1, s_c2);
+}
+
+// cluster size for the fused kernels: enough CTAs for <= 4 windows per thread, else 0 (two-kernel path)
+static inline int bn_fused_cluster(const BnGeom& g) {
+  const int F4 = g.F / 4, wpb = 256 / F4;
+  const int NW = g.n * ((g.h + 1) / 2) * ((g.w + 1) / 2);
+  const int need = (NW + wpb - 1) / wpb;
+  if (need > 32) return 0;
+  int cl = 1;
+  while (cl < need && cl < 8) cl <<= 1;
+  return cl;
+}
+template <class A>
+static inline void launch_cluster(void (*kernel)(A), const A& a, int cl, int tasks, int block, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cl, tasks); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, a);
+}
+static int g_bn_fuse = 1;            // env MAML_B200_BN_FUSE=0 -> always the two-kernel path
+void bn_set_fuse(int on) { g_bn_fuse = on; }
+
+// BatchNorm backward of one block (reduce + apply), fused into one cluster kernel when the block is small
+void launch_bnbwd(const BnBwdArgs& a, cudaStream_t st) {
+  const int cl = g_bn_fuse ? bn_fused_cluster(a.g) : 0;
+  if (cl == 0) { launch_bnbwd_reduce(a, st); launch_bnbwd_apply(a, st); return; }
+  ProfScope prof_scope__(PROF_BN, 0.0, st);
+  int block; bn_grid(a.g, a.tasks, &block);
+  launch_cluster(bnbwd_fused_kernel, a, cl, a.tasks, block, st);
+  CUDA_CHECK_LAUNCH();
+}
+
 void launch_bnbwd_apply(const BnBwdArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
@@ -282,7 +387,7 @@ void launch_bnbwd_apply(const BnBwdArgs& a, cudaStream_t st) {
 // ------------------------------------------------------------------------------- tangent forward
 // zhdot = r * (zdot - mean(zdot) - zh * mean(zh * zdot));  pdot = slope * gamma * zhdot at the arg-max
 __global__ void __launch_bounds__(256) bnact_tan_kernel(BnActTanArgs a) {
-  pdl_prologue();
+  pdl_prologue(10);
   __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_md[64], s_q[64];
   const BnGeom g = a.g;
   const int task = blockIdx.y;
@@ -347,8 +452,41 @@ void launch_bnact_tan(const BnActTanArgs& a, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------- tangent backward: reduce
 // T1 = sum dydot,  T2 = sum (dydot * zh + dy * zhdot)   (both only at the arg-max position)
+__device__ __forceinline__ void bnbwd_tan_reduce_phase(const BnBwdTanArgs& a, const BnGeom& g, int task, int cta, int ncta,
+                                                       const WinIter& it, const float* s_g, const float* s_b, double (&s1)[4],
+                                                       double (&s2)[4]) {
+  if (it.lane >= it.WPB) return;
+  const float4 ga = ld4s(s_g, it.q), be = ld4s(s_b, it.q);
+  const float* zhp = a.zh + (long long)task * a.zh_stride;
+  const float* zhd = a.zhdot + (long long)task * a.zhdot_stride;
+  const float* dp = a.dp + (long long)task * a.dp_stride;
+  const float* dpd = a.dpdot + (long long)task * a.dpdot_stride;
+  for (int wi = cta * it.WPB + it.lane; wi < it.NW; wi += ncta * it.WPB) {
+    const int img = wi / (it.hc * it.wc);
+    const int rem = wi - img * it.hc * it.wc;
+    const int wy = rem / it.wc, wx = rem - wy * it.wc;
+    if (wy >= g.ph || wx >= g.pw) continue;
+    float4 zh[4]; long long idx[4]; int4 arg; float4 sl;
+    argmax_window(zhp, g, img, wy, wx, it.q, ga, be, zh, idx, arg, sl);
+    const long long pidx = ((long long)img * g.pG + (wy + g.pb) * g.pgw + (wx + g.pb)) * g.F + it.q * 4;
+    const float4 d = ld4(dp + pidx), dd = ld4(dpd + pidx);
+    const int ar[4] = {arg.x, arg.y, arg.z, arg.w};
+    const float slv[4] = {sl.x, sl.y, sl.z, sl.w};
+    const float dv[4] = {d.x, d.y, d.z, d.w};
+    const float ddv[4] = {dd.x, dd.y, dd.z, dd.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float zhk = pick(zh, ar[c], c);
+      const float zhdk = zhd[idx[ar[c]] + c];
+      const float dy = dv[c] * slv[c], dyd = ddv[c] * slv[c];
+      s1[c] += dyd;
+      s2[c] += (double)dyd * (double)zhk + (double)dy * (double)zhdk;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) bnbwd_tan_reduce_kernel(BnBwdTanArgs a) {
-  pdl_prologue();
+  pdl_prologue(11);
   __shared__ float s_g[64], s_b[64];
   const BnGeom g = a.g;
   const int task = blockIdx.y;
@@ -356,35 +494,7 @@ __global__ void __launch_bounds__(256) bnbwd_tan_reduce_kernel(BnBwdTanArgs a) {
   __syncthreads();
   WinIter it(g);
   double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-  if (it.lane < it.WPB) {
-    const float4 ga = ld4s(s_g, it.q), be = ld4s(s_b, it.q);
-    const float* zhp = a.zh + (long long)task * a.zh_stride;
-    const float* zhd = a.zhdot + (long long)task * a.zhdot_stride;
-    const float* dp = a.dp + (long long)task * a.dp_stride;
-    const float* dpd = a.dpdot + (long long)task * a.dpdot_stride;
-    for (int wi = blockIdx.x * it.WPB + it.lane; wi < it.NW; wi += gridDim.x * it.WPB) {
-      const int img = wi / (it.hc * it.wc);
-      const int rem = wi - img * it.hc * it.wc;
-      const int wy = rem / it.wc, wx = rem - wy * it.wc;
-      if (wy >= g.ph || wx >= g.pw) continue;
-      float4 zh[4]; long long idx[4]; int4 arg; float4 sl;
-      argmax_window(zhp, g, img, wy, wx, it.q, ga, be, zh, idx, arg, sl);
-      const long long pidx = ((long long)img * g.pG + (wy + g.pb) * g.pgw + (wx + g.pb)) * g.F + it.q * 4;
-      const float4 d = ld4(dp + pidx), dd = ld4(dpd + pidx);
-      const int ar[4] = {arg.x, arg.y, arg.z, arg.w};
-      const float slv[4] = {sl.x, sl.y, sl.z, sl.w};
-      const float dv[4] = {d.x, d.y, d.z, d.w};
-      const float ddv[4] = {dd.x, dd.y, dd.z, dd.w};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float zhk = pick(zh, ar[c], c);
-        const float zhdk = zhd[idx[ar[c]] + c];
-        const float dy = dv[c] * slv[c], dyd = ddv[c] * slv[c];
-        s1[c] += dyd;
-        s2[c] += (double)dyd * (double)zhk + (double)dy * (double)zhdk;
-      }
-    }
-  }
+  bnbwd_tan_reduce_phase(a, g, task, blockIdx.x, gridDim.x, it, s_g, s_b, s1, s2);
   block_reduce_stats(s1, s2, it, a.stats_tbwd + (long long)task * a.stats_tbwd_stride, g.F);
 }
 
@@ -398,23 +508,9 @@ void launch_bnbwd_tan_reduce(const BnBwdTanArgs& a, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------- tangent backward: apply
 // dzdot = -r*q*dz + r*gamma*(dydot - T1/m - zhdot*S2/m - zh*T2/m)
-__global__ void __launch_bounds__(256) bnbwd_tan_apply_kernel(BnBwdTanArgs a) {
-  pdl_prologue();
-  __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_q[64], s_c2[64], s_t1[64], s_t2[64];
-  const BnGeom g = a.g;
-  const int task = blockIdx.y;
-  const double m = (double)g.n * g.h * g.w;
-  chan_setup(a.stats_fwd + (long long)task * a.stats_fwd_stride, a.gamma, a.beta, m, g.F, s_mu, s_r, s_g, s_b);
-  if (threadIdx.x < g.F) {
-    const int c = threadIdx.x;
-    s_q[c] = (float)((a.stats_tan + (long long)task * a.stats_tan_stride)[c * 2 + 1] / m);
-    s_c2[c] = (float)((a.stats_bwd + (long long)task * a.stats_bwd_stride)[c * 2 + 1] / m);
-    const double* tb = a.stats_tbwd + (long long)task * a.stats_tbwd_stride;
-    s_t1[c] = (float)(tb[c * 2] / m);
-    s_t2[c] = (float)(tb[c * 2 + 1] / m);
-  }
-  __syncthreads();
-  WinIter it(g);
+__device__ __forceinline__ void bnbwd_tan_apply_phase(const BnBwdTanArgs& a, const BnGeom& g, int task, int cta, int ncta,
+                                                      const WinIter& it, const float* s_r, const float* s_g, const float* s_b,
+                                                      const float* s_q, const float* s_c2, const float* s_t1, const float* s_t2) {
   if (it.lane >= it.WPB) return;
   const float4 r = ld4s(s_r, it.q), ga = ld4s(s_g, it.q), be = ld4s(s_b, it.q);
   const float4 qq = ld4s(s_q, it.q), c2 = ld4s(s_c2, it.q), t1 = ld4s(s_t1, it.q), t2 = ld4s(s_t2, it.q);
@@ -425,7 +521,7 @@ __global__ void __launch_bounds__(256) bnbwd_tan_apply_kernel(BnBwdTanArgs a) {
   const float* dzp = a.dz + (long long)task * a.dz_stride;
   const float* dpd = a.dpdot + (long long)task * a.dpdot_stride;
   float* dzd = a.dzdot + (long long)task * a.dzdot_stride;
-  for (int wi = blockIdx.x * it.WPB + it.lane; wi < it.NW; wi += gridDim.x * it.WPB) {
+  for (int wi = cta * it.WPB + it.lane; wi < it.NW; wi += ncta * it.WPB) {
     const int img = wi / (it.hc * it.wc);
     const int rem = wi - img * it.hc * it.wc;
     const int wy = rem / it.wc, wx = rem - wy * it.wc;
@@ -456,9 +552,65 @@ __global__ void __launch_bounds__(256) bnbwd_tan_apply_kernel(BnBwdTanArgs a) {
   }
 }
 
+__device__ __forceinline__ void bnbwd_tan_setup(const BnBwdTanArgs& a, const BnGeom& g, int task, double m, float* s_mu, float* s_r,
+                                                float* s_g, float* s_b, float* s_q, float* s_c2) {
+  chan_setup(a.stats_fwd + (long long)task * a.stats_fwd_stride, a.gamma, a.beta, m, g.F, s_mu, s_r, s_g, s_b);
+  if (threadIdx.x < g.F) {
+    const int c = threadIdx.x;
+    s_q[c] = (float)((a.stats_tan + (long long)task * a.stats_tan_stride)[c * 2 + 1] / m);
+    s_c2[c] = (float)((a.stats_bwd + (long long)task * a.stats_bwd_stride)[c * 2 + 1] / m);
+  }
+}
+
+__global__ void __launch_bounds__(256) bnbwd_tan_apply_kernel(BnBwdTanArgs a) {
+  pdl_prologue(12);
+  __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_q[64], s_c2[64], s_t1[64], s_t2[64];
+  const BnGeom g = a.g;
+  const int task = blockIdx.y;
+  const double m = (double)g.n * g.h * g.w;
+  bnbwd_tan_setup(a, g, task, m, s_mu, s_r, s_g, s_b, s_q, s_c2);
+  if (threadIdx.x < g.F) {
+    const int c = threadIdx.x;
+    const double* tb = a.stats_tbwd + (long long)task * a.stats_tbwd_stride;
+    s_t1[c] = (float)(tb[c * 2] / m);
+    s_t2[c] = (float)(tb[c * 2 + 1] / m);
+  }
+  __syncthreads();
+  WinIter it(g);
+  bnbwd_tan_apply_phase(a, g, task, blockIdx.x, gridDim.x, it, s_r, s_g, s_b, s_q, s_c2, s_t1, s_t2);
+}
+
+__global__ void __launch_bounds__(256) bnbwd_tan_fused_kernel(BnBwdTanArgs a) {
+  pdl_prologue(13);
+  __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_q[64], s_c2[64], s_t1[64], s_t2[64];
+  __shared__ double tot[128];
+  const BnGeom g = a.g;
+  const int task = blockIdx.y;
+  const double m = (double)g.n * g.h * g.w;
+  bnbwd_tan_setup(a, g, task, m, s_mu, s_r, s_g, s_b, s_q, s_c2);
+  __syncthreads();
+  WinIter it(g);
+  double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  bnbwd_tan_reduce_phase(a, g, task, blockIdx.x, gridDim.x, it, s_g, s_b, s1, s2);
+  block_reduce_to_smem(s1, s2, it, tot, g.F);
+  cluster_allreduce_stats(tot, g.F, m, s_t1, s_t2, a.stats_tbwd + (long long)task * a.stats_tbwd_stride);
+  bnbwd_tan_apply_phase(a, g, task, blockIdx.x, gridDim.x, it, s_r, s_g, s_b, s_q, s_c2, s_t1, s_t2);
+}
+
 void launch_bnbwd_tan_apply(const BnBwdTanArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
   launch_pdl(bnbwd_tan_apply_kernel, dim3(grid), dim3(block), (size_t)(0), st, a);
   CUDA_CHECK_LAUNCH();
 }
+
+void launch_bnbwd_tan(const BnBwdTanArgs& a, cudaStream_t st) {
+  const int cl = g_bn_fuse ? bn_fused_cluster(a.g) : 0;
+  if (cl == 0) { launch_bnbwd_tan_reduce(a, st); launch_bnbwd_tan_apply(a, st); return; }
+  ProfScope prof_scope__(PROF_BN, 0.0, st);
+  int block; bn_grid(a.g, a.tasks, &block);
+  launch_cluster(bnbwd_tan_fused_kernel, a, cl, a.tasks, block, st);
+  CUDA_CHECK_LAUNCH();
+}
+
+MAML_TRACE_SETTER(trace_set_bn)

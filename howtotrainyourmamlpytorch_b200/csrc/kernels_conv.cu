@@ -10,6 +10,7 @@
 
 long long g_launch_counter = 0;
 int g_use_pdl = 0;
+int g_launch_prio = 0;
 
 __device__ __forceinline__ int tap_shift(int tap, int gw) { return (tap / 3 - 1) * gw + (tap % 3 - 1); }
 
@@ -93,7 +94,7 @@ __device__ __forceinline__ void conv_epilogue(float (&acc)[4][FN], int j0, int r
 // ---------------------------------------------------------------------------------------------
 template <int FN>
 __global__ void __launch_bounds__(256) conv_rows_kernel(ConvArgs a) {
-  pdl_prologue();
+  pdl_prologue(1);
   constexpr int NC = 16 * FN;
   __shared__ __align__(16) float As[16][68];
   __shared__ __align__(16) float Ws[16][NC];
@@ -202,7 +203,7 @@ void launch_conv_rows(const ConvArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 template <int FN>
 __global__ void __launch_bounds__(256) conv0_kernel(Conv0Args a) {
-  pdl_prologue();
+  pdl_prologue(2);
   constexpr int NC = 16 * FN;
   extern __shared__ float sm0[];
   __shared__ double sred[8 * NC * 2];
@@ -274,7 +275,7 @@ void launch_conv0(const Conv0Args& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 template <int CN, int FN>
 __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
-  pdl_prologue();
+  pdl_prologue(3);
   constexpr int KC = 16 * CN, NC = 16 * FN;
   __shared__ __align__(16) float As[16][KC];
   __shared__ __align__(16) float Ds[16][NC];
@@ -371,7 +372,7 @@ void launch_wgrad(const WgradArgs& a, cudaStream_t st) {
 // (grp, f) accumulates the (tap, c) combinations q = grp, grp + NG, ... for output channel f.
 template <int MAXQ>
 __global__ void __launch_bounds__(256) wgrad0_kernel(WgradArgs a) {
-  pdl_prologue();
+  pdl_prologue(4);
   extern __shared__ float smw[];
   const int task = blockIdx.y, chunk = blockIdx.x;
   const int tid = threadIdx.x;
@@ -455,7 +456,7 @@ void launch_wgrad0(const WgradArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 __global__ void prep_x_kernel(const float* __restrict__ x, float* __restrict__ xg, long long xg_task_stride, int n,
                               int C, int H, int W) {
-  pdl_prologue();
+  pdl_prologue(5);
   const int task = blockIdx.y;
   const long long total = (long long)n * H * W;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -477,3 +478,5 @@ void launch_prep_x(const float* x, float* xg, long long xg_task_stride, int task
   launch_pdl(prep_x_kernel, dim3(grid), dim3(256), (size_t)(0), st, x, xg, xg_task_stride, n, C, H, W);
   CUDA_CHECK_LAUNCH();
 }
+
+MAML_TRACE_SETTER(trace_set_conv)

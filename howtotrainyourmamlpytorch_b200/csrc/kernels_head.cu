@@ -15,7 +15,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
-  pdl_prologue();
+  pdl_prologue(14);
   // grid (row groups, tasks): everything except the weight gradient is row-local, so each CTA owns `rows_per_cta`
   // rows of the batch and writes its own chunk of (gW, gb); the parameter-space kernel sums the chunks in order.
   extern __shared__ float smh[];
@@ -143,3 +143,5 @@ void launch_head(const HeadArgs& a, cudaStream_t st) {
   launch_pdl(head_kernel, dim3(grid), dim3(256), (size_t)(smem), st, a);
   CUDA_CHECK_LAUNCH();
 }
+
+MAML_TRACE_SETTER(trace_set_head)

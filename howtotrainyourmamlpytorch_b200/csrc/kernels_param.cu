@@ -40,7 +40,7 @@ __device__ __forceinline__ long long internal_to_meta(const ParamLayout& pl, lon
 
 __global__ void import_theta_kernel(ParamLayout pl, const float* __restrict__ meta, float* __restrict__ theta0,
                                     long long stride, int tasks) {
-  pdl_prologue();
+  pdl_prologue(15);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pl.P) return;
   int seg;
@@ -71,7 +71,7 @@ __global__ void param_reduce_kernel(ParamLayout pl, PartialDesc pd, const float*
                                     float* __restrict__ g_out, float* __restrict__ tbar,
                                     const float* __restrict__ meta, int step, long long task_stride, long long i_lo,
                                     long long i_hi) {
-  pdl_prologue();
+  pdl_prologue(16);
   const long long i = i_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= i_hi) return;
   const int task = blockIdx.y;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) dots_u_kernel(ParamLayout pl, float* __re
                                                      const float* __restrict__ g, float* __restrict__ u,
                                                      double* __restrict__ abar, const float* __restrict__ meta, int step,
                                                      long long task_stride) {
-  pdl_prologue();
+  pdl_prologue(17);
   __shared__ double red[8];
   const int task = blockIdx.y;
   const long long lo = (long long)blockIdx.x * 2048, hi = min(pl.P, lo + 2048);
@@ -158,7 +158,7 @@ __device__ __forceinline__ const double* stat_ptr(const ExportArgs& a, int task,
 }
 
 __global__ void export_kernel(ExportArgs a) {
-  pdl_prologue();
+  pdl_prologue(18);
   const ParamLayout& pl = a.pl;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long LSF = (long long)pl.L * pl.S * pl.F;
@@ -284,7 +284,7 @@ struct SegEnds { long long e[32]; int n; };
 __global__ void adam_kernel(float* __restrict__ meta, const float* __restrict__ grad, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float bc1, float bc2, SegEnds se,
                             unsigned trainable_mask, unsigned clamp_mask) {
-  pdl_prologue();
+  pdl_prologue(19);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int seg = 0;
@@ -315,7 +315,7 @@ void launch_adam(float* meta, const float* grad, float* m, float* v, long long n
 
 __global__ void running_update_kernel(const float* __restrict__ pm, const float* __restrict__ pv, float* __restrict__ rm,
                                       float* __restrict__ rv, const float* __restrict__ decay, int L, int S, int F) {
-  pdl_prologue();
+  pdl_prologue(20);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= L * S * F) return;
   const int s = (i / F) % S;
@@ -331,3 +331,5 @@ void launch_running_update(const float* part_mean, const float* part_var, float*
   launch_pdl(running_update_kernel, dim3((n + 255) / 256), dim3(256), (size_t)(0), st, part_mean, part_var, rm, rv, decay_dev, L, S, F);
   CUDA_CHECK_LAUNCH();
 }
+
+MAML_TRACE_SETTER(trace_set_param)

@@ -97,10 +97,45 @@ __device__ __forceinline__ uint32_t dsmem_addr(uint32_t local, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
   return r;
 }
-__device__ __forceinline__ float dsmem_ld(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+__device__ __forceinline__ float4 dsmem_ld4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
+}
+
+// Split-K reduction of one output tile across the S CTAs of a cluster.  CTA `zrank` finishes rows [zrank * 128/S, ...):
+// every thread first issues ALL its distributed-shared-memory loads (S per float4 item, compile-time unrolled), then
+// sums them in rank order (deterministic), adds the bias and writes global memory + a local copy for the statistics.
+template <int NCOLS, int S>
+__device__ __forceinline__ void splitk_reduce(uint32_t tile_local, int zrank, int et, const float* __restrict__ bias,
+                                              float* __restrict__ tile2, float* __restrict__ out, int j0, int rows) {
+  constexpr int P4 = NCOLS + 4;                         // partial-tile pitch (floats), keeps rows 16-byte aligned
+  constexpr int ROWS = 128 / S;
+  constexpr int TOTAL4 = ROWS * (NCOLS / 4);
+  constexpr int ITEMS = (TOTAL4 + 127) / 128;
+  float4 v[ITEMS][S];
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int idx = et + it * 128;
+    const int rr = idx / (NCOLS / 4), c4 = idx - rr * (NCOLS / 4);
+    const uint32_t off = (uint32_t)(((zrank * ROWS + rr) * P4 + c4 * 4) * 4);
+#pragma unroll
+    for (int z = 0; z < S; ++z)
+      v[it][z] = (idx < TOTAL4) ? dsmem_ld4(dsmem_addr(tile_local + off, (uint32_t)z)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int idx = et + it * 128;
+    if (idx >= TOTAL4) continue;
+    const int rr = idx / (NCOLS / 4), c4 = idx - rr * (NCOLS / 4);
+    float4 acc = v[it][0];
+#pragma unroll
+    for (int z = 1; z < S; ++z) { acc.x += v[it][z].x; acc.y += v[it][z].y; acc.z += v[it][z].z; acc.w += v[it][z].w; }
+    if (bias) { acc.x += bias[c4 * 4]; acc.y += bias[c4 * 4 + 1]; acc.z += bias[c4 * 4 + 2]; acc.w += bias[c4 * 4 + 3]; }
+    *reinterpret_cast<float4*>(tile2 + rr * P4 + c4 * 4) = acc;
+    const int g = j0 + zrank * ROWS + rr;
+    if (g < rows) *reinterpret_cast<float4*>(out + (long long)g * NCOLS + c4 * 4) = acc;
+  }
 }
 
 __device__ __forceinline__ int tap_shift_tc(int tap, int gw) { return (tap / 3 - 1) * gw + (tap % 3 - 1); }
@@ -123,6 +158,7 @@ __device__ long long g_tc_timeline[16];
 template <int NCOLS>
 __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvArgs a) {
   pdl_trigger();
+  trace_mark(22);
   constexpr int B_BYTES = NCOLS * 128;
   constexpr int BSTAGE = 2 * B_BYTES;            // B_hi + B_lo of one (tap, k-chunk)
   constexpr int NACC = 5;                        // 4 x hi*hi (round-robin over k-steps) + 1 x (lo*hi + hi*lo)
@@ -313,39 +349,37 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
           for (int i = 0; i < 16; ++i) tile[r * PITCH + c0 + i] = o[i];
         }
       } else {
-        // split-K partial (no bias): parked in shared memory for the cluster reduction below
+        // split-K partial (no bias): parked in shared memory (16-byte aligned rows) for the cluster reduction below
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float big = (__uint_as_float(v0[i]) + __uint_as_float(v1[i])) + (__uint_as_float(v2[i]) + __uint_as_float(v3[i]));
-          tile[r * PITCH + c0 + i] = big + __uint_as_float(v4[i]);
+          o[i] = big + __uint_as_float(v4[i]);
         }
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(tile + r * (NCOLS + 4) + c0 + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
       }
     }
     if (et == 0) TC_MARK(7);
   }
 
   // rows [row_lo, row_lo + row_n) of the tile are finished by this CTA (all 128 without split-K)
-  int row_lo = 0, row_n = 128;
+  int row_lo = 0, row_n = 128, spitch = PITCH;
   const float* sbuf = reinterpret_cast<const float*>(smem);   // where those rows live (row index relative to row_lo)
   if (nsplit > 1) {
     __syncwarp();
     cluster_sync_all();                            // every CTA's partial tile is in its shared memory
-    row_n = 128 / nsplit; row_lo = zrank * row_n;
-    float* tile2 = reinterpret_cast<float*>(smem + 36 * 1024);
+    row_n = 128 / nsplit; row_lo = zrank * row_n; spitch = NCOLS + 4;
+    float* tile2 = reinterpret_cast<float*>(smem + 40 * 1024);
     sbuf = tile2;
     if (warp >= 2 && warp < 6) {
       const int et = threadIdx.x - 64;
       const uint32_t tile_local = smem_u32(smem);
-      for (int idx = et; idx < row_n * NCOLS; idx += 128) {
-        const int rr = idx / NCOLS, col = idx - rr * NCOLS;
-        const uint32_t off = (uint32_t)(((row_lo + rr) * PITCH + col) * 4);
-        float acc = 0.f;
-        for (int z = 0; z < nsplit; ++z) acc += dsmem_ld(dsmem_addr(tile_local + off, (uint32_t)z));   // fixed order: deterministic
-        acc += a.bias ? a.bias[(long long)task * a.bias_stride + col] : 0.f;
-        tile2[rr * PITCH + col] = acc;
-        const int g = j0 + row_lo + rr;
-        if (g < a.rows) a.out[(long long)task * a.out_stride + (long long)g * NCOLS + col] = acc;
-      }
+      const float* bias = a.bias ? a.bias + (long long)task * a.bias_stride : nullptr;
+      float* outp = a.out + (long long)task * a.out_stride;
+      if (nsplit == 2) splitk_reduce<NCOLS, 2>(tile_local, zrank, et, bias, tile2, outp, j0, a.rows);
+      else if (nsplit == 4) splitk_reduce<NCOLS, 4>(tile_local, zrank, et, bias, tile2, outp, j0, a.rows);
+      else splitk_reduce<NCOLS, 8>(tile_local, zrank, et, bias, tile2, outp, j0, a.rows);
     }
   }
 
@@ -361,7 +395,7 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
       if (part < PARTS) {
         for (int rr = part; rr < row_n; rr += PARTS) {
           if (row_ok[row_lo + rr]) {
-            const float v = sbuf[rr * PITCH + col];
+            const float v = sbuf[rr * spitch + col];
             if (a.mode == CONV_FWD_STATS) { s1 += (double)v; s2 += (double)v * (double)v; }
             else {
               const float zv = zh[(long long)(j0 + row_lo + rr) * NCOLS + col];
@@ -395,6 +429,7 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
   }
+  trace_mark(22 | 0x80);     // end of CTA (0,0,0)
 }
 
 }  // namespace
@@ -492,7 +527,7 @@ __device__ __forceinline__ float tf32_rna(float x) {
 
 __global__ void pack_weights_kernel(ParamLayout pl, const float* __restrict__ theta, long long theta_task_stride,
                                     float* __restrict__ pack, long long pack_task_stride, long long plane_stride) {
-  pdl_prologue();
+  pdl_prologue(21);
   const int task = blockIdx.y;
   const long long per_layer = 9LL * pl.F * pl.F;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -521,3 +556,5 @@ void launch_pack_weights(const ParamLayout& pl, const float* theta, long long th
   launch_pdl(pack_weights_kernel, dim3(grid), dim3(256), (size_t)(0), st, pl, theta, theta_task_stride, pack, pack_task_stride, plane_stride);
   CUDA_CHECK_LAUNCH();
 }
+
+MAML_TRACE_SETTER(trace_set_tc)

@@ -146,6 +146,13 @@ int maml_b200_profile(maml_b200_handle* h, int32_t enable);
 int maml_b200_profile_read(maml_b200_handle* h, double* ms_by_cat, double* flops_by_cat,
                            int64_t* launches_by_cat, int32_t ncat);
 
+/* Device-side launch trace (debug): while enabled, CTA (0,0,0) of every kernel appends (globaltimer ns << 8 | kernel
+ * id) to a device buffer -- the start-time sequence of the kernels of the following calls, also inside a replayed CUDA
+ * graph.  trace_read synchronises, copies at most `capacity` entries (start order), clears, and returns the count.
+ * Kernel ids: scripts/trace_kernel_ids.json. */
+int maml_b200_trace(maml_b200_handle* h, int32_t enable);
+int64_t maml_b200_trace_read(maml_b200_handle* h, uint64_t* out, int64_t capacity);
+
 /* Number of kernel launches issued by the last maml_b200_meta_batch_fwd_bwd call. */
 int64_t maml_b200_last_launch_count(const maml_b200_handle* h);
 

@@ -3,7 +3,7 @@
 3 first B stage landed, 4 B stage 9 landed, 5 last MMA issued, 6 accumulators complete (epilogue wakes),
 7 TMEM drained to smem, 8 epilogue done, 9 all warps joined."""
 import os, sys
-os.environ["MAML_B200_TC_TIMELINE"] = "1"
+os.environ["MAML_B200_TC_TIMELINE"] = sys.argv[3] if len(sys.argv) > 3 else "0"     # block to record (0 = any)
 os.environ["MAML_B200_NO_GRAPH"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -19,4 +19,4 @@ for _ in range(3):
     m._run(db, 0, mode == "train", False)
 torch.cuda.synchronize()
 t = m._engine.debug_read("tc_timeline")
-print(name, mode, "cycles since start:", [int(x) for x in t[:10]])
+print(name, mode, "block", os.environ["MAML_B200_TC_TIMELINE"], "cycles since start:", [int(x) for x in t[:10]])
