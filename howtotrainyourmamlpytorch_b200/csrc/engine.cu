@@ -93,7 +93,8 @@ struct maml_b200_handle {
   int last_tasks = 0;
   Profiler prof;
   // side streams / events for fork-join inside one iteration, CUDA-graph cache
-  cudaStream_t s_cap = nullptr, s_tgt = nullptr, s_wg = nullptr;
+  cudaStream_t s_cap = nullptr, s_tgt = nullptr, s_tgt2 = nullptr, s_wg = nullptr;
+  int tgt_slots = 1;       // target passes of consecutive steps are independent: double-buffered on two streams
   cudaEvent_t ev_fork = nullptr, ev_wg = nullptr, ev_pack = nullptr, ev_tgt[MAML_MAX_STEPS] = {};
   bool use_graphs = true;
   // results produced on s_wg (upper-block parameter reduction, weight packs) that the main chain has not joined yet:
@@ -170,8 +171,11 @@ static void plan_chunks(maml_b200_handle* h, int n, ChunkPlan* cp) {
     if (l == 0) {
       nch = (int)std::min<long long>(512, std::max<long long>(1, (rows + 63) / 64));
     } else {
-      static const int wg_rows = getenv("MAML_B200_WG_ROWS") ? atoi(getenv("MAML_B200_WG_ROWS")) : 128;
-      nch = (int)std::min<long long>(64, std::max<long long>(1, (rows + wg_rows - 1) / wg_rows));
+      // one full wave: wgrad_kernel<4,4> keeps 4 CTAs per SM resident (53 registers x 256 threads), so 9 taps x tasks x
+      // chunks should just fill 148 x 4 slots -- 720 CTAs (128-row chunks at 8 tasks) ran as 1.2 waves = 2x the time
+      static const int wg_slots = getenv("MAML_B200_WG_SLOTS") ? atoi(getenv("MAML_B200_WG_SLOTS")) : 148 * 4;
+      long long want = std::max<long long>(1, wg_slots / (9LL * h->maxT));
+      nch = (int)std::min<long long>(std::min<long long>(64, want), std::max<long long>(1, (rows + 15) / 16));
     }
     rpc = (int)rup((rows + nch - 1) / nch, 16);
     nch = (int)((rows + rpc - 1) / rpc);
@@ -286,7 +290,8 @@ static void carve_pass(maml_b200_handle* h, Bump& b, PassSet& ps, int n, int slo
 static void carve(maml_b200_handle* h, Bump& b) {
   const long long T = h->maxT;
   carve_pass(h, b, h->sup, h->n_s, h->S, true, true);
-  carve_pass(h, b, h->tgt, h->n_t, (h->cfg.reserved & 1) ? h->S : 1, true, true);   // reserved bit 0: keep every target pass (tests)
+  h->tgt_slots = std::min(h->S, getenv("MAML_B200_TGT_SLOTS") ? std::max(1, atoi(getenv("MAML_B200_TGT_SLOTS"))) : 2);
+  carve_pass(h, b, h->tgt, h->n_t, (h->cfg.reserved & 1) ? h->S : h->tgt_slots, true, true);   // reserved bit 0: keep every target pass (tests)
   carve_pass(h, b, h->tan, h->n_s, 1, false, true);
   h->theta = b.f((long long)(h->S + 1) * T * h->Ppad);
   h->g = b.f((long long)h->S * T * h->Ppad);
@@ -301,7 +306,7 @@ static void carve(maml_b200_handle* h, Bump& b) {
     h->pack_u = b.f(4 * h->pack_u_plane);
   }
   h->sup_partial = b.f(T * h->plan_sup.size);
-  h->tgt_partial = b.f(T * h->plan_tgt.size);
+  h->tgt_partial = b.f(T * h->plan_tgt.size * h->tgt_slots);
   h->st_layer_stride = (long long)h->F * 2;
   h->st_pass_stride = (long long)h->L * h->F * 2;
   h->stats_task_stride = (long long)PASS_KINDS * MAML_MAX_STEPS * h->st_pass_stride;
@@ -367,6 +372,7 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   const int p_main = use_prio ? prio_hi : 0, p_tgt = use_prio ? std::min(prio_lo, prio_hi + 1) : 0, p_wg = use_prio ? prio_lo : 0;
   bool ok = cudaStreamCreateWithPriority(&h->s_cap, cudaStreamNonBlocking, p_main) == cudaSuccess &&
             cudaStreamCreateWithPriority(&h->s_tgt, cudaStreamNonBlocking, p_tgt) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&h->s_tgt2, cudaStreamNonBlocking, p_tgt) == cudaSuccess &&
             cudaStreamCreateWithPriority(&h->s_wg, cudaStreamNonBlocking, p_wg) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->ev_wg, cudaEventDisableTiming) == cudaSuccess &&
@@ -382,6 +388,7 @@ extern "C" void maml_b200_destroy(maml_b200_handle* h) {
   for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (h->s_cap) cudaStreamDestroy(h->s_cap);
   if (h->s_tgt) cudaStreamDestroy(h->s_tgt);
+  if (h->s_tgt2) cudaStreamDestroy(h->s_tgt2);
   if (h->s_wg) cudaStreamDestroy(h->s_wg);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_wg) cudaEventDestroy(h->ev_wg);
@@ -529,7 +536,7 @@ static void forward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const
                          int bn_step, int stat_kind, int T, cudaStream_t st) {
   for (int l = 0; l < h->L; ++l) {
     const LayerGeom& g = h->geo[l];
-    if (l == 1 && st != h->s_tgt) join_pending(h, st);
+    if (l == 1 && st != h->s_tgt && st != h->s_tgt2) join_pending(h, st);
     if (l == 0) {
       Conv0Args a{};
       a.X = ps.xg; a.x_stride = ps.xg_stride;
@@ -772,6 +779,14 @@ static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it,
   const int T = it->n_tasks;
   const unsigned mask = it->target_mask & ((1u << it->num_steps) - 1u);
   const long long TP = (long long)h->maxT * h->Ppad;
+  // diagnostic (MAML_B200_ONE_STREAM=1): everything on one stream -> the device trace shows true kernel durations
+  struct StreamSwap {
+    maml_b200_handle* h; cudaStream_t tgt, tgt2, wg; bool on;
+    StreamSwap(maml_b200_handle* h_, cudaStream_t st) : h(h_), tgt(h_->s_tgt), tgt2(h_->s_tgt2), wg(h_->s_wg), on(getenv("MAML_B200_ONE_STREAM") != nullptr) {
+      if (on) { h->s_tgt = st; h->s_tgt2 = st; h->s_wg = st; }
+    }
+    ~StreamSwap() { if (on) { h->s_tgt = tgt; h->s_tgt2 = tgt2; h->s_wg = wg; } }
+  } stream_swap(h, st);
   int last_t = 0;
   for (int s = 0; s < it->num_steps; ++s) if (mask & (1u << s)) last_t = s;
 
@@ -811,11 +826,15 @@ static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it,
     ReduceSpec rs{PR_UPDATE, th, th_next, h->g + (long long)s * TP, nullptr, s, s + 1};
     backward_pass(h, h->sup, s, th, s, meta, s, PASS_SUP_FWD, PASS_SUP_BWD, h->sup_partial, h->plan_sup, T, st, true, &rs);
     if (mask & (1u << s)) {
-      cudaStream_t ts_ = h->s_tgt;
+      // target passes of different steps are independent (each only needs theta^{s+1}): alternate two streams and two
+      // buffer slots so that pass s+1 does not queue behind pass s (the target chain was the longest path of phase A)
+      const int tpar = (h->tgt_slots > 1) ? (s & 1) : 0;
+      cudaStream_t ts_ = tpar ? h->s_tgt2 : h->s_tgt;
+      float* tpart = h->tgt_partial + (long long)tpar * h->maxT * h->plan_tgt.size;
       CK(cudaEventRecord(h->ev_pack, st));
       CK(cudaStreamWaitEvent(ts_, h->ev_pack, 0));       // block-0 weights of theta^{s+1}
       CK(cudaStreamWaitEvent(ts_, h->ev_wg, 0));         // everything else + packs (side stream)
-      const int ts = (h->cfg.reserved & 1) ? s : 0;
+      const int ts = (h->cfg.reserved & 1) ? s : tpar;
       forward_pass(h, h->tgt, ts, th_next, s + 1, meta, s, PASS_TGT_FWD, T, ts_);
       HeadArgs a{};
       a.mode = HEAD_TARGET_FWD; a.n = h->n_t; a.N = h->N; a.D = h->D; a.scale = 1.f;
@@ -833,13 +852,13 @@ static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it,
         HeadArgs bqa = a;
         bqa.mode = HEAD_TARGET_BWD; bqa.scale = it->target_weight[s];
         bqa.logits_out = nullptr; bqa.correct_out = nullptr; bqa.loss_out = nullptr;
-        bqa.gW = h->tgt_partial + h->plan_tgt.pd.off[2 * h->L]; bqa.gb = h->tgt_partial + h->plan_tgt.pd.off[2 * h->L + 1];
+        bqa.gW = tpart + h->plan_tgt.pd.off[2 * h->L]; bqa.gb = tpart + h->plan_tgt.pd.off[2 * h->L + 1];
         bqa.g_stride = h->plan_tgt.pd.task_stride;
         bqa.g_chunk_stride = h->plan_tgt.pd.cstride[2 * h->L];
         bqa.df = DP(h->tgt, h->L - 1, ts); bqa.df_stride = STRIDE(h->tgt, dp, h->L - 1);
         launch_head(bqa, ts_);
-        backward_pass(h, h->tgt, ts, th_next, s + 1, meta, s, PASS_TGT_FWD, PASS_TGT_BWD, h->tgt_partial, h->plan_tgt, T, ts_, false);
-        launch_param_reduce(h->pl, h->plan_tgt.pd, h->tgt_partial, PR_STORE, nullptr, nullptr, h->tgrad + (long long)s * TP, nullptr,
+        backward_pass(h, h->tgt, ts, th_next, s + 1, meta, s, PASS_TGT_FWD, PASS_TGT_BWD, tpart, h->plan_tgt, T, ts_, false);
+        launch_param_reduce(h->pl, h->plan_tgt.pd, tpart, PR_STORE, nullptr, nullptr, h->tgrad + (long long)s * TP, nullptr,
                             meta, s, h->Ppad, T, ts_);
       }
       CK(cudaEventRecord(h->ev_tgt[s], ts_));
@@ -931,6 +950,7 @@ extern "C" int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200
     cudaError_t e = cudaStreamEndCapture(h->s_cap, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
     if (e != cudaSuccess) return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    if (const char* dot = getenv("MAML_B200_GRAPH_DOT")) cudaGraphDebugDotPrint(graph, dot, cudaGraphDebugDotFlagsKernelNodeParams);
     maml_b200_handle::GraphEntry ge;
     ge.it = *it; memcpy(ge.p, ptrs, sizeof(ptrs)); ge.exec = nullptr; ge.launches = g_launch_counter - launches0; ge.stamp = 0;
     e = cudaGraphInstantiate(&ge.exec, graph, 0);

@@ -1,7 +1,3 @@
-run() { echo "== $1"; env $1 timeout 200 python bench.py 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'])"; }
-run "X=1"
-run "MAML_B200_LAUNCH_PRIO=1"
-run "MAML_B200_WG_ROWS=256"
-run "MAML_B200_WG_ROWS=512"
-run "MAML_B200_WG_ROWS=512 MAML_B200_LAUNCH_PRIO=1"
-run "MAML_B200_WG_ROWS=1280 MAML_B200_LAUNCH_PRIO=1"
+# usage: bash scripts/ab_bench.sh "ENV1=.. ENV2=.." "ENV=.." ...   (one bench.py run per argument; prints ms/step, tasks/s)
+run() { echo "== $1"; env $1 timeout 200 python bench.py --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'])"; }
+for a in "$@"; do run "$a"; done
