@@ -89,6 +89,7 @@ struct BnActArgs {                // forward: z -> zh (in place), pooled activat
 
 struct BnActTanArgs {             // tangent forward: zdot -> zhdot (in place), pdot
   float* zdot; long long zdot_stride;
+  const float* zdot2;              // optional second addend of zdot (same stride): the u-weight conv computed on a side stream
   const float* zh; long long zh_stride;
   const double* stats_fwd; long long stats_fwd_stride;   // primal (sum z, sum z^2) -> r
   const double* stats_tan; long long stats_tan_stride;   // (sum zdot, sum zh*zdot)
@@ -112,6 +113,7 @@ struct BnBwdArgs {                // backward reduce / apply (primal)
 struct BnBwdTanArgs {             // backward reduce / apply (tangent)
   const float* dp; long long dp_stride;
   const float* dpdot; long long dpdot_stride;
+  const float* dpdot2;             // optional second addend of dpdot (same stride)
   const float* zh; long long zh_stride;
   const float* zhdot; long long zhdot_stride;
   const float* dz; long long dz_stride;

@@ -79,7 +79,7 @@ struct maml_b200_handle {
   std::vector<long long> seg_off, seg_size;
   // workspace
   char* ws = nullptr; long long ws_bytes = 0;
-  PassSet sup, tgt, tan;
+  PassSet sup, tgt, tan, tan2;      // tan2: second addends of the tangent pass (u-weight convs, computed on a side stream)
   float *theta = nullptr, *g = nullptr, *tgrad = nullptr, *tbar = nullptr, *u = nullptr;
   float *sup_partial = nullptr, *tgt_partial = nullptr;
   ChunkPlan plan_sup, plan_tgt;
@@ -96,6 +96,8 @@ struct maml_b200_handle {
   cudaStream_t s_cap = nullptr, s_tgt = nullptr, s_tgt2 = nullptr, s_wg = nullptr;
   int tgt_slots = 1;       // target passes of consecutive steps are independent: double-buffered on two streams
   cudaEvent_t ev_fork = nullptr, ev_wg = nullptr, ev_pack = nullptr, ev_tgt[MAML_MAX_STEPS] = {};
+  cudaEvent_t ev_pre[2 * MAML_MAX_LAYERS] = {};     // tangent pre-computed addends: [l] forward conv, [MAX_LAYERS + l] dgrad
+  bool tan_split = true;                              // env MAML_B200_TAN_SPLIT=0: two-source tangent convs on the main chain
   bool use_graphs = true;
   // results produced on s_wg (upper-block parameter reduction, weight packs) that the main chain has not joined yet:
   // consumed right before the first kernel that reads them (block 1's convolution / the head)
@@ -293,6 +295,7 @@ static void carve(maml_b200_handle* h, Bump& b) {
   h->tgt_slots = std::min(h->S, getenv("MAML_B200_TGT_SLOTS") ? std::max(1, atoi(getenv("MAML_B200_TGT_SLOTS"))) : 2);
   carve_pass(h, b, h->tgt, h->n_t, (h->cfg.reserved & 1) ? h->S : h->tgt_slots, true, true);   // reserved bit 0: keep every target pass (tests)
   carve_pass(h, b, h->tan, h->n_s, 1, false, true);
+  carve_pass(h, b, h->tan2, h->n_s, 1, false, true);
   h->theta = b.f((long long)(h->S + 1) * T * h->Ppad);
   h->g = b.f((long long)h->S * T * h->Ppad);
   h->tgrad = b.f((long long)h->S * T * h->Ppad);
@@ -378,6 +381,8 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
             cudaEventCreateWithFlags(&h->ev_wg, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming) == cudaSuccess;
   for (int s = 0; ok && s < MAML_MAX_STEPS; ++s) ok = cudaEventCreateWithFlags(&h->ev_tgt[s], cudaEventDisableTiming) == cudaSuccess;
+  for (int s = 0; ok && s < 2 * MAML_MAX_LAYERS; ++s) ok = cudaEventCreateWithFlags(&h->ev_pre[s], cudaEventDisableTiming) == cudaSuccess;
+  if (const char* ts = getenv("MAML_B200_TAN_SPLIT")) h->tan_split = atoi(ts) != 0;
   if (!ok) { maml_b200_destroy(h); return fail("stream / event creation failed"); }
   *out = h;
   return 0;
@@ -394,6 +399,7 @@ extern "C" void maml_b200_destroy(maml_b200_handle* h) {
   if (h->ev_wg) cudaEventDestroy(h->ev_wg);
   if (h->ev_pack) cudaEventDestroy(h->ev_pack);
   for (int s = 0; s < MAML_MAX_STEPS; ++s) if (h->ev_tgt[s]) cudaEventDestroy(h->ev_tgt[s]);
+  for (int s = 0; s < 2 * MAML_MAX_LAYERS; ++s) if (h->ev_pre[s]) cudaEventDestroy(h->ev_pre[s]);
   if (h->ws) cudaFree(h->ws);
   if (h->pinned) cudaFreeHost(h->pinned);
   delete h;
@@ -637,7 +643,26 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
 // forward-mode tangent of (support forward + support backward) at step s in direction u  =>  H u into `partial`
 static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const float* u, const float* meta,
                          const long long* y_support, int T, cudaStream_t st, const ReduceSpec& rs) {
-  const PassSet& sp = h->sup; const PassSet& tn = h->tan;
+  const PassSet& sp = h->sup; const PassSet& tn = h->tan; const PassSet& t2 = h->tan2;
+  // Tangent convs of blocks >= 1 have two operand pairs; the pair (primal activation, u weights) depends only on u and
+  // on what phase A saved, not on the tangent chain.  It is computed up front on the side stream (right behind the
+  // u packs) into the tan2 buffers -- BatchNorm statistics contributions included, they are linear -- and the
+  // consumers (bnact_tan / bnbwd_tan) add the two addends.  The main chain keeps the single-pair half: 18 instead of
+  // 36 stages per tile on the critical path.
+  const bool split = h->use_tc && h->tan_split;
+  if (split) {
+    for (int l = 1; l < h->L; ++l) {
+      TcOp op = tc_op_ain(h, sp, l, s, h->u_map, 0, +1, 2);          // conv(a_in, u_W) + u_b
+      tc_conv(h, l, sp.n, 1, &op, u + h->pl.b_off[l], h->Ppad, ZH(t2, l, 0), STRIDE(t2, zh, l), CONV_TAN_STATS, ZH(sp, l, s),
+              STRIDE(sp, zh, l), stat_at(h, PASS_TAN_FWD, s, l), T, h->s_wg);
+      cudaEventRecord(h->ev_pre[l], h->s_wg);
+    }
+    for (int l = h->L - 1; l >= 1; --l) {
+      TcOp op = tc_op_dz(h, sp, l, s, h->u_map, 0, -1, 0);           // dgrad(u_W, dz)
+      tc_conv(h, l, sp.n, 1, &op, nullptr, 0, DP(t2, l - 1, 0), STRIDE(t2, dp, l - 1), CONV_PLAIN, nullptr, 0, nullptr, T, h->s_wg);
+      cudaEventRecord(h->ev_pre[MAML_MAX_LAYERS + l], h->s_wg);
+    }
+  }
   for (int l = 0; l < h->L; ++l) {
     const LayerGeom& g = h->geo[l];
     if (l == 1) join_pending(h, st);
@@ -652,6 +677,11 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
       a.stats = stat_at(h, PASS_TAN_FWD, s, 0); a.stats_stride = h->stats_task_stride; a.tasks = T;
       a.alg_flops = conv_flops(h, 0, sp.n, T, 1);
       launch_conv0(a, st);
+    } else if (split) {
+      TcOp op = tc_op_ain(h, tn, l, 0, h->theta_map, s, +1, 2);       // conv(a_in_dot, W); the other addend is in tan2
+      tc_conv(h, l, sp.n, 1, &op, nullptr, 0, ZH(tn, l, 0), STRIDE(tn, zh, l), CONV_TAN_STATS, ZH(sp, l, s),
+              STRIDE(sp, zh, l), stat_at(h, PASS_TAN_FWD, s, l), T, st);
+      cudaStreamWaitEvent(st, h->ev_pre[l], 0);
     } else if (h->use_tc) {
       TcOp ops[2];
       ops[0] = tc_op_ain(h, sp, l, s, h->u_map, 0, +1, 2);          // conv(a_in, u_W)
@@ -675,6 +705,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
     }
     BnActTanArgs b{};
     b.zdot = ZH(tn, l, 0); b.zdot_stride = STRIDE(tn, zh, l);
+    if (split && l >= 1) b.zdot2 = ZH(t2, l, 0);
     b.zh = ZH(sp, l, s); b.zh_stride = STRIDE(sp, zh, l);
     b.stats_fwd = stat_at(h, PASS_SUP_FWD, s, l); b.stats_fwd_stride = h->stats_task_stride;
     b.stats_tan = stat_at(h, PASS_TAN_FWD, s, l); b.stats_tan_stride = h->stats_task_stride;
@@ -705,6 +736,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
     BnBwdTanArgs b{};
     b.dp = DP(sp, l, s); b.dp_stride = STRIDE(sp, dp, l);
     b.dpdot = DP(tn, l, 0); b.dpdot_stride = STRIDE(tn, dp, l);
+    if (split && l + 1 < h->L) { b.dpdot2 = DP(t2, l, 0); cudaStreamWaitEvent(st, h->ev_pre[MAML_MAX_LAYERS + l + 1], 0); }
     b.zh = ZH(sp, l, s); b.zh_stride = STRIDE(sp, zh, l);
     b.zhdot = ZH(tn, l, 0); b.zhdot_stride = STRIDE(tn, zh, l);
     b.dz = DZ(sp, l, s); b.dz_stride = STRIDE(sp, dz, l);
@@ -737,7 +769,10 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
       w.A[1] = AIN(tn, l, 0); w.a_stride[1] = STRIDE(tn, ain, l);
       w.D[1] = DZ(sp, l, s); w.d_stride[1] = STRIDE(sp, dz, l);
       w.alg_flops = conv_flops(h, l, sp.n, T, 2);
-      if (h->use_tc) {
+      if (split) {
+        TcOp op = tc_op_dz(h, tn, l, 0, h->theta_map, s, -1, 0);      // dgrad(W, dz_dot); the other addend is in tan2
+        tc_conv(h, l, sp.n, 1, &op, nullptr, 0, DP(tn, l - 1, 0), STRIDE(tn, dp, l - 1), CONV_PLAIN, nullptr, 0, nullptr, T, st);
+      } else if (h->use_tc) {
         TcOp ops[2];
         ops[0] = tc_op_dz(h, tn, l, 0, h->theta_map, s, -1, 0);     // dgrad(W, dz_dot)
         ops[1] = tc_op_dz(h, sp, l, s, h->u_map, 0, -1, 0);         // dgrad(u_W, dz)

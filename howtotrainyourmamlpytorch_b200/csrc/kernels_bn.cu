@@ -403,6 +403,7 @@ __global__ void __launch_bounds__(256) bnact_tan_kernel(BnActTanArgs a) {
   if (it.lane >= it.WPB) return;
   const float4 r = ld4s(s_r, it.q), ga = ld4s(s_g, it.q), be = ld4s(s_b, it.q), md = ld4s(s_md, it.q), qq = ld4s(s_q, it.q);
   float* zd = a.zdot + (long long)task * a.zdot_stride;
+  const float* zd2 = a.zdot2 ? a.zdot2 + (long long)task * a.zdot_stride : nullptr;
   const float* zhp = a.zh + (long long)task * a.zh_stride;
   float* pd = a.pdot + (long long)task * a.pdot_stride;
   for (int wi = blockIdx.x * it.WPB + it.lane; wi < it.NW; wi += gridDim.x * it.WPB) {
@@ -416,7 +417,8 @@ __global__ void __launch_bounds__(256) bnact_tan_kernel(BnActTanArgs a) {
       if (yy < g.h && xx < g.w) {
         const long long idx = ((long long)img * g.G + (yy + 1) * g.gw + (xx + 1)) * g.F + it.q * 4;
         const float4 zh = ld4(zhp + idx);
-        const float4 zv = ld4(zd + idx);
+        float4 zv = ld4(zd + idx);
+        if (zd2) { const float4 z2 = ld4(zd2 + idx); zv.x += z2.x; zv.y += z2.y; zv.z += z2.z; zv.w += z2.w; }
         float4 zhd;
         zhd.x = r.x * (zv.x - md.x - zh.x * qq.x); zhd.y = r.y * (zv.y - md.y - zh.y * qq.y);
         zhd.z = r.z * (zv.z - md.z - zh.z * qq.z); zhd.w = r.w * (zv.w - md.w - zh.w * qq.w);
@@ -469,7 +471,12 @@ __device__ __forceinline__ void bnbwd_tan_reduce_phase(const BnBwdTanArgs& a, co
     float4 zh[4]; long long idx[4]; int4 arg; float4 sl;
     argmax_window(zhp, g, img, wy, wx, it.q, ga, be, zh, idx, arg, sl);
     const long long pidx = ((long long)img * g.pG + (wy + g.pb) * g.pgw + (wx + g.pb)) * g.F + it.q * 4;
-    const float4 d = ld4(dp + pidx), dd = ld4(dpd + pidx);
+    const float4 d = ld4(dp + pidx);
+    float4 dd = ld4(dpd + pidx);
+    if (a.dpdot2) {
+      const float4 d2 = ld4(a.dpdot2 + (long long)task * a.dpdot_stride + pidx);
+      dd.x += d2.x; dd.y += d2.y; dd.z += d2.z; dd.w += d2.w;
+    }
     const int ar[4] = {arg.x, arg.y, arg.z, arg.w};
     const float slv[4] = {sl.x, sl.y, sl.z, sl.w};
     const float dv[4] = {d.x, d.y, d.z, d.w};
@@ -531,7 +538,12 @@ __device__ __forceinline__ void bnbwd_tan_apply_phase(const BnBwdTanArgs& a, con
     if (full) {
       float4 zh[4]; long long idx[4]; float4 sl;
       argmax_window(zhp, g, img, wy, wx, it.q, ga, be, zh, idx, arg, sl);
-      const float4 dd = ld4(dpd + ((long long)img * g.pG + (wy + g.pb) * g.pgw + (wx + g.pb)) * g.F + it.q * 4);
+      const long long pidx = ((long long)img * g.pG + (wy + g.pb) * g.pgw + (wx + g.pb)) * g.F + it.q * 4;
+      float4 dd = ld4(dpd + pidx);
+      if (a.dpdot2) {
+        const float4 d2 = ld4(a.dpdot2 + (long long)task * a.dpdot_stride + pidx);
+        dd.x += d2.x; dd.y += d2.y; dd.z += d2.z; dd.w += d2.w;
+      }
       dyd = make_float4(dd.x * sl.x, dd.y * sl.y, dd.z * sl.z, dd.w * sl.w);
     }
 #pragma unroll
