@@ -173,10 +173,11 @@ static void plan_chunks(maml_b200_handle* h, int n, ChunkPlan* cp) {
     if (l == 0) {
       nch = (int)std::min<long long>(512, std::max<long long>(1, (rows + 63) / 64));
     } else {
-      // one full wave: wgrad_kernel<4,4> keeps 4 CTAs per SM resident (53 registers x 256 threads), so 9 taps x tasks x
+      // one full wave: wgrad_row_kernel<4,4> keeps 2 CTAs per SM resident (105 registers x 256 threads), so 3 filter rows x tasks x
       // chunks should just fill 148 x 4 slots -- 720 CTAs (128-row chunks at 8 tasks) ran as 1.2 waves = 2x the time
-      static const int wg_slots = getenv("MAML_B200_WG_SLOTS") ? atoi(getenv("MAML_B200_WG_SLOTS")) : 148 * 4;
-      long long want = std::max<long long>(1, wg_slots / (9LL * h->maxT));
+      static const int wg_slots = getenv("MAML_B200_WG_SLOTS") ? atoi(getenv("MAML_B200_WG_SLOTS")) : 148 * 2;
+      static const int wg_per_chunk = (getenv("MAML_B200_WGRAD_ROW") && atoi(getenv("MAML_B200_WGRAD_ROW")) == 0) ? 9 : 3;
+      long long want = std::max<long long>(1, wg_slots / ((long long)wg_per_chunk * h->maxT));
       nch = (int)std::min<long long>(std::min<long long>(64, want), std::max<long long>(1, (rows + 15) / 16));
     }
     rpc = (int)rup((rows + nch - 1) / nch, 16);
@@ -347,6 +348,7 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   if (const char* bo = getenv("MAML_B200_TC_BO")) h->tc_bo_mode = atoi(bo);
   if (const char* sp = getenv("MAML_B200_TC_SPLIT")) tc_conv_set_split(atoi(sp));
   g_launch_prio = getenv("MAML_B200_LAUNCH_PRIO") ? 1 : 0;
+  if (const char* wr = getenv("MAML_B200_WGRAD_ROW")) wgrad_set_row_variant(atoi(wr));
   if (const char* bf = getenv("MAML_B200_BN_FUSE")) bn_set_fuse(atoi(bf));
   for (int l = 1; l < h->L && h->use_tc; ++l)
     if (tc_conv_rpad(h->geo[l].gw) > 256 || tc_conv_ring(h->F, h->geo[l].gw) < 2) h->use_tc = false;   // image too wide for one halo box      // F in {16, 32, 48, 64}: ragged K chunks are zero-filled by TMA

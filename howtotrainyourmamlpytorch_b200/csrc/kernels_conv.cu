@@ -358,10 +358,132 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
   if (tap == 4 && tid < NC) P[(long long)9 * KC * NC + tid] = bacc;
 }
 
+// Filter-row variant: one CTA handles the three taps (ky, kx = -1, 0, +1) of a chunk.  Their A rows are CONSECUTIVE
+// (shifts s-1, s, s+1), so while a thread walks the rows of a K step it keeps a sliding window of three A rows in
+// registers: per row 2 x LDS.128 feed 3 x CN x FN FMAs (the one-tap kernel above needs 2 x LDS.128 per CN x FN), the
+// dz tile is staged once for three taps and the number of barriers per FMA drops 3x.  grid (nchunks * 3, tasks).
+template <int CN, int FN>
+__global__ void __launch_bounds__(256) wgrad_row_kernel(WgradArgs a) {
+  pdl_prologue(3);
+  constexpr int KC = 16 * CN, NC = 16 * FN;
+  constexpr int A4 = 18 * KC / 4;                  // float4 loads of the 18-row A window
+  __shared__ __align__(16) float As[18][KC];
+  __shared__ __align__(16) float Ds[16][NC];
+  const int task = blockIdx.y;
+  const int chunk = blockIdx.x / 3, ky = blockIdx.x - chunk * 3;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int sh = (ky - 1) * a.gw - 1;              // A window row 0 = output row + sh  (tap kx = -1)
+  const int r_begin = chunk * a.rows_per_chunk;
+  const int r_end = min(a.rows, r_begin + a.rows_per_chunk);
+  const int guard = a.gw + 2;
+
+  float acc[3][CN][FN];
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int i = 0; i < CN; ++i)
+#pragma unroll
+      for (int jn = 0; jn < FN; ++jn) acc[t][i][jn] = 0.f;
+  float bacc = 0.f;
+
+  const int steps = (r_end > r_begin) ? (r_end - r_begin + 15) / 16 : 0;
+  const int nit = steps * a.nsrc;
+  float4 ra0 = make_float4(0.f, 0.f, 0.f, 0.f), ra1 = ra0, rd = ra0;
+
+  auto fetch = [&](int it) {
+    const int s = it / steps;
+    const int r0 = r_begin + (it - s * steps) * 16;
+    const float* A = a.A[s] + (long long)task * a.a_stride[s];
+    {
+      const int r = tid / (KC / 4), c4 = tid - r * (KC / 4);
+      const int jr = r0 + sh + r;
+      ra0 = (r < 18 && jr >= -guard && jr < a.rows + guard) ? *reinterpret_cast<const float4*>(A + (long long)jr * KC + c4 * 4)
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (tid + 256 < A4) {
+      const int e = tid + 256;
+      const int r = e / (KC / 4), c4 = e - r * (KC / 4);
+      const int jr = r0 + sh + r;
+      ra1 = (jr >= -guard && jr < a.rows + guard) ? *reinterpret_cast<const float4*>(A + (long long)jr * KC + c4 * 4)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (tid < 4 * NC) {
+      const int r = tid / (NC / 4), f4 = tid - r * (NC / 4);
+      const int jr = r0 + r;
+      rd = (jr < r_end) ? *reinterpret_cast<const float4*>(a.D[s] + (long long)task * a.d_stride[s] + (long long)jr * NC + f4 * 4)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+
+  if (nit > 0) fetch(0);
+  for (int it = 0; it < nit; ++it) {
+    {
+      const int r = tid / (KC / 4), c4 = tid - r * (KC / 4);
+      if (r < 18) *reinterpret_cast<float4*>(&As[r][c4 * 4]) = ra0;
+    }
+    if (tid + 256 < A4) {
+      const int e = tid + 256;
+      const int r = e / (KC / 4), c4 = e - r * (KC / 4);
+      *reinterpret_cast<float4*>(&As[r][c4 * 4]) = ra1;
+    }
+    if (tid < 4 * NC) {
+      const int r = tid / (NC / 4), f4 = tid - r * (NC / 4);
+      *reinterpret_cast<float4*>(&Ds[r][f4 * 4]) = rd;
+    }
+    __syncthreads();
+    const bool bias_src = (it / steps) == 0;
+    if (it + 1 < nit) fetch(it + 1);
+    float w0[CN], w1[CN], w2[CN];
+#pragma unroll
+    for (int i = 0; i < CN; ++i) { w0[i] = As[0][ty * CN + i]; w1[i] = As[1][ty * CN + i]; }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      float b[FN];
+#pragma unroll
+      for (int i = 0; i < CN; ++i) w2[i] = As[r + 2][ty * CN + i];
+#pragma unroll
+      for (int jn = 0; jn < FN; ++jn) b[jn] = Ds[r][tx * FN + jn];
+#pragma unroll
+      for (int i = 0; i < CN; ++i)
+#pragma unroll
+        for (int jn = 0; jn < FN; ++jn) {
+          acc[0][i][jn] = fmaf(w0[i], b[jn], acc[0][i][jn]);
+          acc[1][i][jn] = fmaf(w1[i], b[jn], acc[1][i][jn]);
+          acc[2][i][jn] = fmaf(w2[i], b[jn], acc[2][i][jn]);
+        }
+#pragma unroll
+      for (int i = 0; i < CN; ++i) { w0[i] = w1[i]; w1[i] = w2[i]; }
+    }
+    if (ky == 1 && bias_src && tid < NC) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) bacc += Ds[r][tid];
+    }
+    __syncthreads();
+  }
+
+  float* P = a.partial + (long long)task * a.partial_task_stride + (long long)chunk * a.chunk_stride;
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int i = 0; i < CN; ++i)
+#pragma unroll
+      for (int jn = 0; jn < FN; ++jn) P[(long long)((ky * 3 + t) * KC + ty * CN + i) * NC + tx * FN + jn] = acc[t][i][jn];
+  if (ky == 1 && tid < NC) P[(long long)9 * KC * NC + tid] = bacc;
+}
+
+static int g_wgrad_rows3 = 1;            // env MAML_B200_WGRAD_ROW=0 -> one tap per CTA
+void wgrad_set_row_variant(int on) { g_wgrad_rows3 = on; }
+
 void launch_wgrad(const WgradArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_WGRAD, a.alg_flops, st);
-  dim3 grid(a.nchunks * 9, a.tasks);
   const int cn = a.kc / 16, fn = a.ncols / 16;
+  if (g_wgrad_rows3) {
+    dim3 grid(a.nchunks * 3, a.tasks);
+#define WGR_CASE(C, F_) if (cn == C && fn == F_) { launch_pdl(wgrad_row_kernel<C, F_>, dim3(grid), dim3(256), (size_t)(0), st, a); CUDA_CHECK_LAUNCH(); return; }
+    WGR_CASE(1, 1) WGR_CASE(2, 2) WGR_CASE(3, 3) WGR_CASE(4, 4)
+#undef WGR_CASE
+  }
+  dim3 grid(a.nchunks * 9, a.tasks);
 #define WG_CASE(C, F_) if (cn == C && fn == F_) { launch_pdl(wgrad_kernel<C, F_>, dim3(grid), dim3(256), (size_t)(0), st, a); CUDA_CHECK_LAUNCH(); return; }
   WG_CASE(1, 1) WG_CASE(2, 2) WG_CASE(3, 3) WG_CASE(4, 4)
 #undef WG_CASE
