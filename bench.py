@@ -321,10 +321,10 @@ def main():
         except Exception:
             pass
         roofline = {
-            "bound": "tensor", "kernel": "3x3 implicit-GEMM conv: conv_tc_kernel (tcgen05, 3xTF32) + wgrad_kernel (FFMA)",
+            "bound": "tensor", "kernel": "3x3 implicit-GEMM conv: conv_tc_kernel (tcgen05, 3xTF32, cluster split-K) + wgrad_row_kernel (FFMA)",
             "achieved": achieved, "peak": peak_3x, "unit": "TFLOP/s", "frac": achieved / peak_3x,
             "traffic": traffic,
-            "traffic_note": "dram__bytes_read+write of one conv_tc_kernel launch (ncu --set full, cold cache; profiles/ncu_summary_r1.json)",
+            "traffic_note": "dram__bytes_read+write of one block-1 conv_tc_kernel launch, grid (10,8,1) (ncu --set full, cold cache; profiles/ncu_summary_r1.json)",
             "peak_source": peak_src + ": bf16_tflops %.1f / 2 (tf32) / 3 (3xTF32 split)" % peaks["bf16_tflops"],
             "launches_profiled": int(dom_n), "mean_launch_us": 1e3 * dom_ms / max(dom_n, 1),
             "share_of_step": dom_ms / tot_prof_ms if tot_prof_ms > 0 else None,
