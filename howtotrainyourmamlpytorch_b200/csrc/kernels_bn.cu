@@ -176,44 +176,53 @@ __device__ __forceinline__ void block_reduce_stats(double (&s1)[4], double (&s2)
 __device__ __forceinline__ void bn_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void bn_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t bn_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t bn_cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ double bn_dsmem_ld_f64(const double* local, uint32_t rank) {
+__device__ __forceinline__ void bn_dsmem_st_f64(double* local, uint32_t rank, double v) {
   const uint32_t la = (uint32_t)__cvta_generic_to_shared(local);
-  uint32_t ra; double v;
+  uint32_t ra;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
-  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
-  return v;
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
 }
-// CTA totals of the per-thread partials into shared memory (fixed summation order)
-__device__ __forceinline__ void block_reduce_to_smem(double (&s1)[4], double (&s2)[4], const WinIter& it, double* tot, int F) {
+// CTA totals of the per-thread partials (fixed summation order): thread o < 2F returns the total of (channel o/2,
+// sum o%2); other threads return 0
+__device__ __forceinline__ double block_reduce_totals(double (&s1)[4], double (&s2)[4], const WinIter& it, int F) {
   __shared__ double red2[256 * 8];
   const int tid = threadIdx.x;
 #pragma unroll
   for (int c = 0; c < 4; ++c) { red2[tid * 8 + c * 2] = s1[c]; red2[tid * 8 + c * 2 + 1] = s2[c]; }
   __syncthreads();
-  for (int o = tid; o < F * 2; o += blockDim.x) {
-    const int ch = o >> 1, which = o & 1;
-    const int q = ch >> 2, comp = ch & 3;
-    double t = 0.0;
-    for (int l = 0; l < it.WPB; ++l) t += red2[(l * it.F4 + q) * 8 + comp * 2 + which];
-    tot[o] = t;
-  }
-}
-// sum the CTA totals of all CTAs of the cluster (rank order), publish sums / m in shared memory and (rank 0) the raw
-// sums in the global statistics arena
-__device__ __forceinline__ void cluster_allreduce_stats(const double* tot, int F, double m, float* s_a, float* s_b2, double* gstats) {
-  __syncthreads();
-  bn_cluster_sync();
-  const uint32_t n = bn_cluster_size();
-  const int tid = threadIdx.x;
+  double t = 0.0;
   if (tid < F * 2) {
-    double t = 0.0;
-    for (uint32_t z = 0; z < n; ++z) t += bn_dsmem_ld_f64(tot + tid, z);
-    ((tid & 1) ? s_b2 : s_a)[tid >> 1] = (float)(t / m);
-    if (bn_cluster_rank() == 0) gstats[tid] = t;
+    const int ch = tid >> 1, which = tid & 1;
+    const int q = ch >> 2, comp = ch & 3;
+    for (int l = 0; l < it.WPB; ++l) t += red2[(l * it.F4 + q) * 8 + comp * 2 + which];
   }
+  return t;
+}
+// All-reduce of the CTA totals over the cluster with ONE barrier: every CTA pushes its totals into slot [own rank] of
+// every CTA's `gather` array (remote shared-memory stores), barrier.cluster (release / acquire), then each CTA sums its
+// local copy in rank order (deterministic).  Nobody touches remote shared memory after the barrier, so CTAs may exit
+// independently.  Publishes sums / m in shared memory and (rank 0) the raw sums in the global statistics arena.
+__device__ __forceinline__ void cluster_allreduce_stats(double t, double (*gather)[128], int F, double m, float* s_a, float* s_b2,
+                                                        double* gstats) {
+  const uint32_t n = bn_cluster_size(), me = bn_cluster_rank();
+  const int tid = threadIdx.x;
+  // completes the barrier phase opened by bn_cluster_arrive() at kernel start: every CTA of the cluster is running,
+  // so its shared memory may be written remotely
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (tid < F * 2)
+    for (uint32_t z = 0; z < n; ++z) bn_dsmem_st_f64(&gather[me][tid], z, t);
+  __syncwarp();
   bn_cluster_sync();
+  if (tid < F * 2) {
+    double tt = 0.0;
+    for (uint32_t z = 0; z < n; ++z) tt += gather[z][tid];
+    ((tid & 1) ? s_b2 : s_a)[tid >> 1] = (float)(tt / m);
+    if (me == 0) gstats[tid] = tt;
+  }
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------- backward: reduce
@@ -329,8 +338,9 @@ __global__ void __launch_bounds__(256) bnbwd_apply_kernel(BnBwdArgs a) {
 // fused: one cluster of CTAs per task does reduce -> all-reduce through distributed shared memory -> apply
 __global__ void __launch_bounds__(256) bnbwd_fused_kernel(BnBwdArgs a) {
   pdl_prologue(9);
+  bn_cluster_arrive();
   __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_c1[64], s_c2[64];
-  __shared__ double tot[128];
+  __shared__ double gather[8][128];
   const BnGeom g = a.g;
   const int task = blockIdx.y;
   const double m = (double)g.n * g.h * g.w;
@@ -339,8 +349,8 @@ __global__ void __launch_bounds__(256) bnbwd_fused_kernel(BnBwdArgs a) {
   WinIter it(g);
   double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
   bnbwd_reduce_phase(a, g, task, blockIdx.x, gridDim.x, it, s_g, s_b, s1, s2);
-  block_reduce_to_smem(s1, s2, it, tot, g.F);
-  cluster_allreduce_stats(tot, g.F, m, s_c1, s_c2, a.stats_bwd + (long long)task * a.stats_bwd_stride);
+  const double tot = block_reduce_totals(s1, s2, it, g.F);
+  cluster_allreduce_stats(tot, gather, g.F, m, s_c1, s_c2, a.stats_bwd + (long long)task * a.stats_bwd_stride);
   bnbwd_apply_phase(a, g, task, blockIdx.x, gridDim.x, it, s_r, s_g, s_b, s_c1, s_c2);
 }
 
@@ -594,8 +604,9 @@ __global__ void __launch_bounds__(256) bnbwd_tan_apply_kernel(BnBwdTanArgs a) {
 
 __global__ void __launch_bounds__(256) bnbwd_tan_fused_kernel(BnBwdTanArgs a) {
   pdl_prologue(13);
+  bn_cluster_arrive();
   __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_q[64], s_c2[64], s_t1[64], s_t2[64];
-  __shared__ double tot[128];
+  __shared__ double gather[8][128];
   const BnGeom g = a.g;
   const int task = blockIdx.y;
   const double m = (double)g.n * g.h * g.w;
@@ -604,8 +615,8 @@ __global__ void __launch_bounds__(256) bnbwd_tan_fused_kernel(BnBwdTanArgs a) {
   WinIter it(g);
   double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
   bnbwd_tan_reduce_phase(a, g, task, blockIdx.x, gridDim.x, it, s_g, s_b, s1, s2);
-  block_reduce_to_smem(s1, s2, it, tot, g.F);
-  cluster_allreduce_stats(tot, g.F, m, s_t1, s_t2, a.stats_tbwd + (long long)task * a.stats_tbwd_stride);
+  const double tot = block_reduce_totals(s1, s2, it, g.F);
+  cluster_allreduce_stats(tot, gather, g.F, m, s_t1, s_t2, a.stats_tbwd + (long long)task * a.stats_tbwd_stride);
   bnbwd_tan_apply_phase(a, g, task, blockIdx.x, gridDim.x, it, s_r, s_g, s_b, s_q, s_c2, s_t1, s_t2);
 }
 
