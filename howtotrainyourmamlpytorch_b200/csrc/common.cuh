@@ -1,9 +1,9 @@
 // Shared declarations for the B200 MAML engine (sm_100a only).
 //
 // Activation layout ("padded pixel grid"): every activation-like tensor of block l lives as a
-// row-major matrix [n * G_l, C] with G_l = (h_l + 2) * (w_l + 2): one row per position of the
+// row-major matrix [n * G_l, C] with G_l = (h_l + 1) * (w_l + 1) (zero padding shared between neighbours): one row per position of the
 // zero-padded image, channels innermost (NHWC with an explicit border).  Row index of pixel
-// (img, y, x) is img*G + (y+1)*gw + (x+1), gw = w+2.  With that layout a 3x3 / pad-1
+// (img, y, x) is img*G + (y+1)*gw + (x+1), gw = w+1.  With that layout a 3x3 / pad-1
 // convolution is a GEMM whose A operand for tap (ky,kx) is the SAME matrix shifted by
 // s_tap = (ky-1)*gw + (kx-1) rows -- plain 2-D tiles, which is what TMA wants.  Border rows of
 // conv inputs are zero and are never written; border rows of conv outputs are garbage and are
@@ -20,7 +20,7 @@
 struct LayerGeom {
   int h, w;        // conv output (= input) spatial size of this block
   int cin;         // input channels
-  int gw, G;       // padded grid: gw = w + 2, G = (h + 2) * (w + 2)
+  int gw, G;       // padded grid with shared padding: gw = w + 1, G = (h + 1) * (w + 1)
   int ph, pw;      // pooled size (floor)
   int pgw, pG, pb; // grid the pooled output is written to: pitch, rows per image, border (1 or 0)
   int guard;       // guard rows before/after a conv-input matrix on this grid (gw + 2)

@@ -121,9 +121,12 @@ static void build_geometry(maml_b200_handle* h) {
   for (int l = 0; l < h->L; ++l) {
     LayerGeom& g = h->geo[l];
     g.h = hh; g.w = ww; g.cin = cin;
-    g.gw = ww + 2; g.G = (hh + 2) * (ww + 2);
+    // shared zero padding: column 0 of a grid row is the left pad of that row AND the right pad of the row above,
+    // row 0 of an image block is its top pad AND the bottom pad of the image before it (the guard rows close the last
+    // image) -> (h+1)(w+1) rows per image instead of (h+2)(w+2); tap shifts are unchanged ((ky-1) gw + (kx-1))
+    g.gw = ww + 1; g.G = (hh + 1) * (ww + 1);
     g.ph = hh / 2; g.pw = ww / 2;
-    if (l < h->L - 1) { g.pgw = g.pw + 2; g.pG = (g.ph + 2) * (g.pw + 2); g.pb = 1; }
+    if (l < h->L - 1) { g.pgw = g.pw + 1; g.pG = (g.ph + 1) * (g.pw + 1); g.pb = 1; }
     else { g.pgw = g.pw; g.pG = g.ph * g.pw; g.pb = 0; }
     g.guard = g.gw + 2;
     hh = g.ph; ww = g.pw; cin = h->F;

@@ -586,7 +586,7 @@ __global__ void prep_x_kernel(const float* __restrict__ x, float* __restrict__ x
   const int xx = (int)(i % W);
   const int yy = (int)((i / W) % H);
   const int img = (int)(i / ((long long)W * H));
-  const int gw = W + 2, G = (H + 2) * (W + 2);
+  const int gw = W + 1, G = (H + 1) * (W + 1);      // shared-padding grid (engine.cu build_geometry)
   const float* src = x + ((long long)task * n + img) * C * H * W + (long long)yy * W + xx;
   float* dst = xg + (long long)task * xg_task_stride + ((long long)img * G + (yy + 1) * gw + (xx + 1)) * C;
   for (int c = 0; c < C; ++c) dst[c] = src[(long long)c * H * W];

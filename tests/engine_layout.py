@@ -13,8 +13,9 @@ def geometry(args):
 
 
 def grid_to_nchw(buf, n, h, w, F):
-    """[n*(h+2)*(w+2), F] padded pixel grid -> [n, F, h, w]."""
-    a = np.asarray(buf).reshape(n, h + 2, w + 2, F)[:, 1:h + 1, 1:w + 1, :]
+    """[n*(h+1)*(w+1), F] padded pixel grid (row 0 / column 0 of every image block are the shared zero padding)
+    -> [n, F, h, w]."""
+    a = np.asarray(buf).reshape(n, h + 1, w + 1, F)[:, 1:h + 1, 1:w + 1, :]
     return torch.from_numpy(np.ascontiguousarray(a.transpose(0, 3, 1, 2)))
 
 
