@@ -282,7 +282,7 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
-    h2d = sum(t.numel() * 4 for t in host_batches[0])
+    h2d = sum(t.numel() * (8 if j >= 2 else 4) for j, t in enumerate(host_batches[0]))   # images fp32, labels int64 on the device
     n_t = args.num_classes_per_set * args.num_target_samples
     d2h = 2 * 4 + B * n_t * args.num_classes_per_set * 4
 

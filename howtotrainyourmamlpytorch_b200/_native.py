@@ -146,10 +146,18 @@ class Engine(object):
 
     def fwd_bwd(self, n_tasks, task_offset, tasks_global, num_steps, second_order, training, target_mask,
                 target_weight, meta, xs, ys, xt, yt, result, last_logits):
-        it = IterArgs(n_tasks=n_tasks, task_offset=task_offset, tasks_global=tasks_global, num_steps=num_steps,
-                      second_order=int(bool(second_order)), training=int(bool(training)), target_mask=target_mask)
-        for i in range(MAX_STEPS):
-            it.target_weight[i] = float(target_weight[i]) if i < len(target_weight) else 0.0
+        key = (n_tasks, task_offset, tasks_global, num_steps, bool(second_order), bool(training), target_mask,
+               tuple(float(w) for w in target_weight))
+        cache = self.__dict__.setdefault("_iter_args", {})
+        it = cache.get(key)
+        if it is None:
+            it = IterArgs(n_tasks=n_tasks, task_offset=task_offset, tasks_global=tasks_global, num_steps=num_steps,
+                          second_order=int(bool(second_order)), training=int(bool(training)), target_mask=target_mask)
+            for i in range(MAX_STEPS):
+                it.target_weight[i] = float(target_weight[i]) if i < len(target_weight) else 0.0
+            if len(cache) > 64:
+                cache.clear()
+            cache[key] = it
         rc = self.lib.maml_b200_meta_batch_fwd_bwd(
             self.h, ctypes.byref(it), meta.data_ptr(), xs.data_ptr(), ys.data_ptr(), xt.data_ptr(), yt.data_ptr(),
             result.data_ptr(), last_logits.data_ptr() if last_logits is not None else None, self._stream())

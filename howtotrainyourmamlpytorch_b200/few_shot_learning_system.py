@@ -231,6 +231,18 @@ class MAMLFewShotClassifier(nn.Module):
         return (1 + math.cos(math.pi * epoch / T)) / (1 + math.cos(math.pi * (epoch - 1) / T)) * (lr - eta_min) + eta_min
 
     def _schedule(self, epoch, training_phase):
+        """Memoised ``_schedule_uncached`` (it only depends on the epochs and the phase; host time between two
+        iterations is GPU idle time in the end-to-end loop)."""
+        key = (int(epoch), int(self.current_epoch), bool(training_phase))
+        cache = self.__dict__.setdefault("_sched_cache", {})
+        hit = cache.get(key)
+        if hit is None:
+            if len(cache) > 64:
+                cache.clear()
+            hit = cache[key] = self._schedule_uncached(epoch, training_phase)
+        return hit
+
+    def _schedule_uncached(self, epoch, training_phase):
         """(num_steps, second_order, target_mask, target_weights) -- reference :232-244, :304-305, :318-321."""
         S = int(self.args.number_of_training_steps_per_iter)
         if training_phase:
@@ -307,25 +319,58 @@ class MAMLFewShotClassifier(nn.Module):
         buf[1].copy_(buf[0], non_blocking=True)
         return buf[1]
 
+    def _stage_batch(self, data_batch):
+        """Host episode batch -> device: the four tensors are packed into ONE pinned staging block and moved with ONE
+        asynchronous H2D copy into a persistent device block (typed views of it are what the engine sees).  Batches that
+        already live on the device go through ``_stage`` tensor by tensor."""
+        want = (torch.float32, torch.float32, torch.int64, torch.int64)
+        ts = [t if torch.is_tensor(t) else torch.as_tensor(np.asarray(t)) for t in data_batch]
+        if any(t.device.type == "cuda" for t in ts):
+            return tuple(self._stage(k, t, d) for k, t, d in zip(("xs", "xt", "ys", "yt"), ts, want))
+        conv = []
+        for t, d in zip(ts, want):
+            if d == torch.int64:
+                t = t.to(torch.float32).long() if t.is_floating_point() else t.long()      # reference :357-358
+            else:
+                t = t.to(d)
+            conv.append(t)
+        key = tuple(tuple(t.shape) for t in conv)
+        st = self._staging.get("batch")
+        if st is None or st[0] != key:
+            offs, total = [], 0
+            for t in conv:
+                offs.append(total)
+                total += (t.numel() * t.element_size() + 15) // 16 * 16
+            pin = torch.empty(total, dtype=torch.uint8).pin_memory()
+            dev = torch.empty(total, dtype=torch.uint8, device=self.device)
+
+            def views(block):
+                return [block[o:o + t.numel() * t.element_size()].view(t.dtype).view(t.shape) for o, t in zip(offs, conv)]
+            st = (key, pin, dev, views(pin), views(dev))
+            self._staging["batch"] = st
+        _, pin, dev, pin_views, dev_views = st
+        for v, t in zip(pin_views, conv):
+            v.copy_(t)
+        dev.copy_(pin, non_blocking=True)
+        return tuple(dev_views)
+
     def _run(self, data_batch, epoch, training_phase, apply_update):
-        x_support, x_target, y_support, y_target = data_batch
         if self.device.type != "cuda":
             raise _native.NativeLibraryError(
                 "MAMLFewShotClassifier needs a CUDA (sm_100a) device: the hot path has no CPU fallback")
-        xs = self._stage("xs", x_support, torch.float32)
-        xt = self._stage("xt", x_target, torch.float32)
-        ys = self._stage("ys", y_support, torch.int64)
-        yt = self._stage("yt", y_target, torch.int64)
+        xs, xt, ys, yt = self._stage_batch(data_batch)
         B = xs.shape[0]
         n_t = xt.shape[1] * xt.shape[2]
         N = int(self.args.num_classes_per_set)
         eng = self._ensure_engine(B)
         num_steps, second, mask, weights, w_msl = self._schedule(epoch, training_phase)
         task_offset, B_global = sharding.shard_of(self.rank, self.world_size, B)
-        logits = self._staging.get(("logits", B))
-        if logits is None:
-            logits = torch.empty(B, n_t, N, dtype=torch.float32, device=self.device)
-            self._staging[("logits", B)] = logits
+        out = self._staging.get(("out", B))
+        if out is None:
+            # [loss, n_correct | logits]: one device block, so that _finish needs ONE device-to-host read
+            out = torch.empty(2 + B * n_t * N, dtype=torch.float32, device=self.device)
+            self._staging[("out", B)] = out
+        logits = out[2:].view(B, n_t, N)
         with torch.cuda.device(self.device):
             eng.fwd_bwd(n_tasks=B, task_offset=task_offset, tasks_global=B_global, num_steps=num_steps,
                         second_order=second, training=training_phase, target_mask=mask, target_weight=weights,
@@ -333,7 +378,8 @@ class MAMLFewShotClassifier(nn.Module):
             if self.world_size > 1:
                 torch.distributed.all_reduce(self._result, op=torch.distributed.ReduceOp.SUM)
             ms = eng.meta_size
-            head = self._result[ms:ms + 2].clone()
+            out[:2].copy_(self._result[ms:ms + 2])
+            head = out
             if training_phase and apply_update:
                 self.optimizer.step_count += 1
                 eng.adam_step(self._flat, self._result, self._exp_avg, self._exp_avg_sq, lr=self._current_lr,
@@ -347,8 +393,9 @@ class MAMLFewShotClassifier(nn.Module):
 
     def _finish(self, head, logits, w_msl, B_global, n_t):
         """One D2H read of (loss, n_correct, logits) -- the reference syncs per task (:246,:249,:261)."""
-        head_h = head.cpu()
-        preds = logits.cpu().numpy()
+        host = head.cpu()                      # [loss, n_correct | logits] in one read
+        head_h = host[:2]
+        preds = host[2:].view(logits.shape).numpy()
         losses = {"loss": head_h[0].clone(), "accuracy": float(head_h[1]) / float(B_global * n_t)}
         for i, item in enumerate(w_msl):
             losses["loss_importance_vector_{}".format(i)] = item.numpy()
