@@ -382,3 +382,49 @@ def test_functional_network_operator(case, cuda_device):
     ref0 = O._net_forward(x, {n: state[n] for n in inner}, state, a, 0)
     got0 = m.classifier.forward(x.to(cuda_device), num_step=0)
     assert float((got0.cpu() - ref0).abs().max()) <= 2e-5 * float(ref0.abs().max()) + 1e-6
+
+
+def test_fused_and_cluster_paths_match_plain_paths(cuda_device):
+    """The scheduling / fusion variants (cluster split-K convs, fused BatchNorm backward, tangent conv split,
+    double-buffered target passes, filter-row wgrad) against the plain one-kernel-per-op paths they replaced
+    (selected through the diagnostic environment switches, read when the engine handle is created)."""
+    g = load_golden("tiny_pp")
+    batch, epoch = g.batch(0), g.iters[0][0]
+    plain = {"MAML_B200_TC_SPLIT": "1", "MAML_B200_BN_FUSE": "0", "MAML_B200_TAN_SPLIT": "0", "MAML_B200_TGT_SLOTS": "1",
+             "MAML_B200_WGRAD_ROW": "0"}
+    saved = {k: os.environ.get(k) for k in plain}
+    try:
+        os.environ.update(plain)
+        m0 = _model(g, cuda_device)
+        l0, p0, g0 = m0.meta_gradient(batch, epoch)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    m1 = _model(g, cuda_device)
+    l1, p1, g1 = m1.meta_gradient(batch, epoch)
+    assert abs(float(l0["loss"]) - float(l1["loss"])) <= 1e-6 * abs(float(l0["loss"]))
+    for n in g0:
+        if "conv.bias" in n or "conv-bias" in n:
+            assert float((g0[n] - g1[n]).abs().max()) <= 1e-5
+        else:
+            assert rel_err(g1[n], g0[n]) <= 2e-5, (n, rel_err(g1[n], g0[n]))
+
+
+def test_device_trace(cuda_device):
+    """maml_b200_trace: one entry per kernel start of an iteration (also inside the replayed CUDA graph)."""
+    g = load_golden("tiny_pp")
+    m = _model(g, cuda_device)
+    batch, epoch = g.batch(0), g.iters[0][0]
+    m.meta_gradient(batch, epoch)
+    m.meta_gradient(batch, epoch)                 # second call replays the captured graph
+    eng = m._engine
+    eng.trace(True)
+    m.meta_gradient(batch, epoch)
+    tr = eng.trace_read()
+    eng.trace(False)
+    starts = [t for t, k in tr if not (k & 0x80)]
+    assert len(starts) == eng.last_launch_count()
+    assert max(starts) - min(starts) < 1e9           # nanoseconds: one tiny iteration spans far less than a second
