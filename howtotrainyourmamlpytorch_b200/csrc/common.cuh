@@ -194,6 +194,9 @@ void launch_bnbwd_tan_apply(const BnBwdTanArgs& a, cudaStream_t st);
 void launch_bnbwd(const BnBwdArgs& a, cudaStream_t st);          // reduce + apply (one cluster kernel for small blocks)
 void launch_bnbwd_tan(const BnBwdTanArgs& a, cudaStream_t st);
 void bn_set_fuse(int on);
+bool tail_fusable(const BnGeom& g, int n_rows, int rows_per_cta);
+void launch_tail_fused(const BnActArgs& fa, const HeadArgs& ha, const BnBwdArgs& ba, cudaStream_t st);
+void launch_tail_tan_fused(const BnActTanArgs& fa, const HeadArgs& ha, const BnBwdTanArgs& ba, cudaStream_t st);
 void launch_head(const HeadArgs& a, cudaStream_t st);
 
 void launch_import_theta(const ParamLayout& pl, const float* meta, float* theta0, long long theta_task_stride,

@@ -97,6 +97,7 @@ struct maml_b200_handle {
   int tgt_slots = 1;       // target passes of consecutive steps are independent: double-buffered on two streams
   cudaEvent_t ev_fork = nullptr, ev_wg = nullptr, ev_pack = nullptr, ev_tgt[MAML_MAX_STEPS] = {};
   cudaEvent_t ev_pre[2 * MAML_MAX_LAYERS] = {};     // tangent pre-computed addends: [l] forward conv, [MAX_LAYERS + l] dgrad
+  bool tail_fuse = true;                              // env MAML_B200_TAIL_FUSE=0: last block / head / its BN backward as separate kernels
   bool tan_split = true;                              // env MAML_B200_TAN_SPLIT=0: two-source tangent convs on the main chain
   bool use_graphs = true;
   // results produced on s_wg (upper-block parameter reduction, weight packs) that the main chain has not joined yet:
@@ -388,6 +389,7 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   for (int s = 0; ok && s < MAML_MAX_STEPS; ++s) ok = cudaEventCreateWithFlags(&h->ev_tgt[s], cudaEventDisableTiming) == cudaSuccess;
   for (int s = 0; ok && s < 2 * MAML_MAX_LAYERS; ++s) ok = cudaEventCreateWithFlags(&h->ev_pre[s], cudaEventDisableTiming) == cudaSuccess;
   if (const char* ts = getenv("MAML_B200_TAN_SPLIT")) h->tan_split = atoi(ts) != 0;
+  if (const char* tf = getenv("MAML_B200_TAIL_FUSE")) h->tail_fuse = atoi(tf) != 0;
   if (!ok) { maml_b200_destroy(h); return fail("stream / event creation failed"); }
   *out = h;
   return 0;
@@ -544,7 +546,7 @@ static void tc_conv(maml_b200_handle* h, int l, int n, int nsrc, const TcOp* ops
 
 // primal forward of one pass: conv -> stats -> BN/leaky/pool for every block
 static void forward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const float* theta, int th_step, const float* meta,
-                         int bn_step, int stat_kind, int T, cudaStream_t st) {
+                         int bn_step, int stat_kind, int T, cudaStream_t st, BnActArgs* defer_last = nullptr) {
   for (int l = 0; l < h->L; ++l) {
     const LayerGeom& g = h->geo[l];
     if (l == 1 && st != h->s_tgt && st != h->s_tgt2) join_pending(h, st);
@@ -581,14 +583,16 @@ static void forward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const
     b.p = AIN(ps, l + 1, slot); b.p_stride = STRIDE(ps, ain, l + 1);
     if (h->use_tc && l + 1 < h->L) { b.p_hi = AIN_HI(ps, l + 1, slot); b.p_lo = AIN_LO(ps, l + 1, slot); }
     b.g = bn_geom(h, l, ps.n); b.tasks = T;
-    launch_bnact(b, st);
+    if (defer_last && l == h->L - 1) *defer_last = b;      // launched by the fused last-block kernel
+    else launch_bnact(b, st);
   }
 }
 
 // primal backward of one pass (dp[L-1] already written by the head): BN backward, wgrad, dgrad
 static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const float* theta, int th_step, const float* meta,
                           int bn_step, int kind_fwd, int kind_bwd, float* partial, const ChunkPlan& cp, int T, cudaStream_t st,
-                          bool fork_wgrad, const ReduceSpec* rs = nullptr) {
+                          bool fork_wgrad, const ReduceSpec* rs = nullptr, const BnActArgs* fused_act = nullptr,
+                          const HeadArgs* fused_head = nullptr) {
   // wgrad of block l >= 1 only feeds the parameter-space reduction: it runs on a side stream, concurrently with
   // dgrad(l) and the BatchNorm backward of block l-1.  With a ReduceSpec the reduction itself is split (see
   // reduce_upper_on_side); without one the caller reduces after this function returns.
@@ -605,7 +609,8 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
     b.dz = DZ(ps, l, slot); b.dz_stride = STRIDE(ps, dz, l);
     if (h->use_tc && l >= 1) { b.dz_hi = DZ_HI(ps, l, slot); b.dz_lo = DZ_LO(ps, l, slot); }
     b.g = bn_geom(h, l, ps.n); b.tasks = T;
-    launch_bnbwd(b, st);
+    if (fused_head && l == h->L - 1) launch_tail_fused(*fused_act, *fused_head, b, st);
+    else launch_bnbwd(b, st);
     if (fork_wgrad) { cudaEventRecord(h->ev_fork, st); cudaStreamWaitEvent(h->s_wg, h->ev_fork, 0); }
 
     WgradArgs w{};
@@ -647,7 +652,7 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
 
 // forward-mode tangent of (support forward + support backward) at step s in direction u  =>  H u into `partial`
 static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const float* u, const float* meta,
-                         const long long* y_support, int T, cudaStream_t st, const ReduceSpec& rs) {
+                         const long long* y_support, int T, cudaStream_t st, const ReduceSpec& rs, cudaStream_t spre) {
   const PassSet& sp = h->sup; const PassSet& tn = h->tan; const PassSet& t2 = h->tan2;
   // Tangent convs of blocks >= 1 have two operand pairs; the pair (primal activation, u weights) depends only on u and
   // on what phase A saved, not on the tangent chain.  It is computed up front on the side stream (right behind the
@@ -655,17 +660,20 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
   // consumers (bnact_tan / bnbwd_tan) add the two addends.  The main chain keeps the single-pair half: 18 instead of
   // 36 stages per tile on the critical path.
   const bool split = h->use_tc && h->tan_split;
+  const bool fuse_tail = h->tail_fuse && tail_fusable(bn_geom(h, h->L - 1, sp.n), sp.n, HEAD_ROWS_PER_CTA);
+  BnActTanArgs last_act{};
+  HeadArgs hd{};
   if (split) {
     for (int l = 1; l < h->L; ++l) {
       TcOp op = tc_op_ain(h, sp, l, s, h->u_map, 0, +1, 2);          // conv(a_in, u_W) + u_b
       tc_conv(h, l, sp.n, 1, &op, u + h->pl.b_off[l], h->Ppad, ZH(t2, l, 0), STRIDE(t2, zh, l), CONV_TAN_STATS, ZH(sp, l, s),
-              STRIDE(sp, zh, l), stat_at(h, PASS_TAN_FWD, s, l), T, h->s_wg);
-      cudaEventRecord(h->ev_pre[l], h->s_wg);
+              STRIDE(sp, zh, l), stat_at(h, PASS_TAN_FWD, s, l), T, spre);
+      cudaEventRecord(h->ev_pre[l], spre);
     }
     for (int l = h->L - 1; l >= 1; --l) {
       TcOp op = tc_op_dz(h, sp, l, s, h->u_map, 0, -1, 0);           // dgrad(u_W, dz)
-      tc_conv(h, l, sp.n, 1, &op, nullptr, 0, DP(t2, l - 1, 0), STRIDE(t2, dp, l - 1), CONV_PLAIN, nullptr, 0, nullptr, T, h->s_wg);
-      cudaEventRecord(h->ev_pre[MAML_MAX_LAYERS + l], h->s_wg);
+      tc_conv(h, l, sp.n, 1, &op, nullptr, 0, DP(t2, l - 1, 0), STRIDE(t2, dp, l - 1), CONV_PLAIN, nullptr, 0, nullptr, T, spre);
+      cudaEventRecord(h->ev_pre[MAML_MAX_LAYERS + l], spre);
     }
   }
   for (int l = 0; l < h->L; ++l) {
@@ -718,12 +726,13 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
     b.pdot = AIN(tn, l + 1, 0); b.pdot_stride = STRIDE(tn, ain, l + 1);
     if (h->use_tc && l + 1 < h->L) { b.pdot_hi = AIN_HI(tn, l + 1, 0); b.pdot_lo = AIN_LO(tn, l + 1, 0); }
     b.g = bn_geom(h, l, sp.n); b.tasks = T;
-    launch_bnact_tan(b, st);
+    if (fuse_tail && l == h->L - 1) last_act = b;
+    else launch_bnact_tan(b, st);
   }
   const ChunkPlan& cp = h->plan_sup;
   join_pending(h, st);
   {
-    HeadArgs a{};
+    HeadArgs& a = hd;
     a.mode = HEAD_TANGENT; a.n = h->n_s; a.N = h->N; a.D = h->D; a.scale = 1.f;
     a.f = AIN(sp, h->L, s); a.f_stride = STRIDE(sp, ain, h->L);
     a.fdot = AIN(tn, h->L, 0); a.fdot_stride = STRIDE(tn, ain, h->L);
@@ -734,7 +743,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
     a.g_chunk_stride = cp.pd.cstride[2 * h->L]; a.rows_per_cta = HEAD_ROWS_PER_CTA;
     a.df = DP(tn, h->L - 1, 0); a.df_stride = STRIDE(tn, dp, h->L - 1);
     a.tasks = T;
-    launch_head(a, st);
+    if (!fuse_tail) launch_head(a, st);
   }
   for (int l = h->L - 1; l >= 0; --l) {
     const LayerGeom& g = h->geo[l];
@@ -753,7 +762,8 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
     b.dzdot = DZ(tn, l, 0); b.dzdot_stride = STRIDE(tn, dz, l);
     if (h->use_tc && l >= 1) { b.dzdot_hi = DZ_HI(tn, l, 0); b.dzdot_lo = DZ_LO(tn, l, 0); }
     b.g = bn_geom(h, l, sp.n); b.tasks = T;
-    launch_bnbwd_tan(b, st);
+    if (fuse_tail && l == h->L - 1) launch_tail_tan_fused(last_act, hd, b, st);
+    else launch_bnbwd_tan(b, st);
     cudaEventRecord(h->ev_fork, st); cudaStreamWaitEvent(h->s_wg, h->ev_fork, 0);
 
     WgradArgs w{};
@@ -846,10 +856,13 @@ static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it,
   for (int s = 0; s < it->num_steps; ++s) {
     const float* th = h->theta + (long long)s * TP;
     float* th_next = h->theta + (long long)(s + 1) * TP;
-    forward_pass(h, h->sup, s, th, s, meta, s, PASS_SUP_FWD, T, st);
+    const bool fuse_tail = h->tail_fuse && tail_fusable(bn_geom(h, h->L - 1, h->n_s), h->n_s, HEAD_ROWS_PER_CTA);
+    BnActArgs last_act{};
+    forward_pass(h, h->sup, s, th, s, meta, s, PASS_SUP_FWD, T, st, fuse_tail ? &last_act : nullptr);
     join_pending(h, st);
+    HeadArgs hd{};
     {
-      HeadArgs a{};
+      HeadArgs& a = hd;
       a.mode = HEAD_SUPPORT; a.n = h->n_s; a.N = h->N; a.D = h->D; a.scale = 1.f;
       a.f = AIN(h->sup, h->L, s); a.f_stride = STRIDE(h->sup, ain, h->L);
       a.Wfc = th + h->pl.fcw_off; a.bfc = th + h->pl.fcb_off; a.theta_stride = h->Ppad;
@@ -859,12 +872,13 @@ static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it,
       a.g_chunk_stride = h->plan_sup.pd.cstride[2 * h->L]; a.rows_per_cta = HEAD_ROWS_PER_CTA;
       a.df = DP(h->sup, h->L - 1, s); a.df_stride = STRIDE(h->sup, dp, h->L - 1);
       a.tasks = T;
-      launch_head(a, st);
+      if (!fuse_tail) launch_head(a, st);
     }
     // LSLR update theta^{s+1} = theta^s - alpha[.][s] * g and the tensor-core packs of theta^{s+1}: blocks >= 1 and the
     // linear layer on the side stream, block 0 at the end of the main chain
     ReduceSpec rs{PR_UPDATE, th, th_next, h->g + (long long)s * TP, nullptr, s, s + 1};
-    backward_pass(h, h->sup, s, th, s, meta, s, PASS_SUP_FWD, PASS_SUP_BWD, h->sup_partial, h->plan_sup, T, st, true, &rs);
+    backward_pass(h, h->sup, s, th, s, meta, s, PASS_SUP_FWD, PASS_SUP_BWD, h->sup_partial, h->plan_sup, T, st, true, &rs,
+                  fuse_tail ? &last_act : nullptr, fuse_tail ? &hd : nullptr);
     if (mask & (1u << s)) {
       // target passes of different steps are independent (each only needs theta^{s+1}): alternate two streams and two
       // buffer slots so that pass s+1 does not queue behind pass s (the target chain was the longest path of phase A)
@@ -917,13 +931,16 @@ static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it,
       if (it->second_order) {
         // the tensor-core packs of u are first needed by block 1 of the tangent forward: pack on the side stream
         // while the main chain runs block 0
+        // ... on a target stream (idle in phase B) when the u-weight convs are pre-computed there too, so that they do
+        // not queue in front of the weight gradients on the wgrad stream
+        cudaStream_t spre = (h->use_tc && h->tan_split && !getenv("MAML_B200_PRE_ON_WG")) ? h->s_tgt : h->s_wg;
         CK(cudaEventRecord(h->ev_fork, st));
-        CK(cudaStreamWaitEvent(h->s_wg, h->ev_fork, 0));
-        pack_u(h, T, h->s_wg);
-        CK(cudaEventRecord(h->ev_wg, h->s_wg));
+        CK(cudaStreamWaitEvent(spre, h->ev_fork, 0));
+        pack_u(h, T, spre);
+        CK(cudaEventRecord(h->ev_wg, spre));
         h->wg_pending = true;
         ReduceSpec rs{PR_SUB, nullptr, nullptr, nullptr, h->tbar, s, -1};
-        tangent_pass(h, s, th, h->u, meta, ys, T, st, rs);
+        tangent_pass(h, s, th, h->u, meta, ys, T, st, rs, spre);
       }
     }
     join_pending(h, st);

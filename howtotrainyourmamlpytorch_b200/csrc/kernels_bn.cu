@@ -9,6 +9,7 @@
 // windows on the odd last row/column are "partial": they produce no pooled value and receive no
 // pooled gradient, but their positions still take part in BatchNorm.
 #include "common.cuh"
+#include "head_body.cuh"
 
 struct Chan4 { float4 mu, r, g, b; };
 
@@ -59,19 +60,13 @@ struct WinIter {
 };
 
 // ------------------------------------------------------------------------------- forward
-__global__ void __launch_bounds__(256) bnact_kernel(BnActArgs a) {
-  pdl_prologue(6);
-  __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64];
-  const BnGeom g = a.g;
-  const int task = blockIdx.y;
-  chan_setup(a.stats + (long long)task * a.stats_stride, a.gamma, a.beta, (double)g.n * g.h * g.w, g.F, s_mu, s_r, s_g, s_b);
-  __syncthreads();
-  WinIter it(g);
+__device__ __forceinline__ void bnact_phase(const BnActArgs& a, const BnGeom& g, int task, int cta, int ncta, const WinIter& it,
+                                            const float* s_mu, const float* s_r, const float* s_g, const float* s_b) {
   if (it.lane >= it.WPB) return;
   const float4 mu = ld4s(s_mu, it.q), r = ld4s(s_r, it.q), ga = ld4s(s_g, it.q), be = ld4s(s_b, it.q);
   float* z = a.z + (long long)task * a.z_stride;
   float* p = a.p + (long long)task * a.p_stride;
-  for (int wi = blockIdx.x * it.WPB + it.lane; wi < it.NW; wi += gridDim.x * it.WPB) {
+  for (int wi = cta * it.WPB + it.lane; wi < it.NW; wi += ncta * it.WPB) {
     const int img = wi / (it.hc * it.wc);
     const int rem = wi - img * it.hc * it.wc;
     const int wy = rem / it.wc, wx = rem - wy * it.wc;
@@ -102,6 +97,17 @@ __global__ void __launch_bounds__(256) bnact_kernel(BnActArgs a) {
       if (a.p_hi) st4_split(a.p_hi + (long long)task * a.p_stride, a.p_lo + (long long)task * a.p_stride, pidx, best);
     }
   }
+}
+
+__global__ void __launch_bounds__(256) bnact_kernel(BnActArgs a) {
+  pdl_prologue(6);
+  __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64];
+  const BnGeom g = a.g;
+  const int task = blockIdx.y;
+  chan_setup(a.stats + (long long)task * a.stats_stride, a.gamma, a.beta, (double)g.n * g.h * g.w, g.F, s_mu, s_r, s_g, s_b);
+  __syncthreads();
+  WinIter it(g);
+  bnact_phase(a, g, task, blockIdx.x, gridDim.x, it, s_mu, s_r, s_g, s_b);
 }
 
 static inline dim3 bn_grid(const BnGeom& g, int tasks, int* block) {
@@ -396,27 +402,26 @@ void launch_bnbwd_apply(const BnBwdArgs& a, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------- tangent forward
 // zhdot = r * (zdot - mean(zdot) - zh * mean(zh * zdot));  pdot = slope * gamma * zhdot at the arg-max
-__global__ void __launch_bounds__(256) bnact_tan_kernel(BnActTanArgs a) {
-  pdl_prologue(10);
-  __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_md[64], s_q[64];
-  const BnGeom g = a.g;
-  const int task = blockIdx.y;
-  const double m = (double)g.n * g.h * g.w;
+__device__ __forceinline__ void bnact_tan_setup(const BnActTanArgs& a, const BnGeom& g, int task, double m, float* s_mu, float* s_r,
+                                                float* s_g, float* s_b, float* s_md, float* s_q) {
   chan_setup(a.stats_fwd + (long long)task * a.stats_fwd_stride, a.gamma, a.beta, m, g.F, s_mu, s_r, s_g, s_b);
   if (threadIdx.x < g.F) {
     const double* stt = a.stats_tan + (long long)task * a.stats_tan_stride;
     s_md[threadIdx.x] = (float)(stt[threadIdx.x * 2] / m);
     s_q[threadIdx.x] = (float)(stt[threadIdx.x * 2 + 1] / m);
   }
-  __syncthreads();
-  WinIter it(g);
+}
+
+__device__ __forceinline__ void bnact_tan_phase(const BnActTanArgs& a, const BnGeom& g, int task, int cta, int ncta, const WinIter& it,
+                                                const float* s_r, const float* s_g, const float* s_b, const float* s_md,
+                                                const float* s_q) {
   if (it.lane >= it.WPB) return;
   const float4 r = ld4s(s_r, it.q), ga = ld4s(s_g, it.q), be = ld4s(s_b, it.q), md = ld4s(s_md, it.q), qq = ld4s(s_q, it.q);
   float* zd = a.zdot + (long long)task * a.zdot_stride;
   const float* zd2 = a.zdot2 ? a.zdot2 + (long long)task * a.zdot_stride : nullptr;
   const float* zhp = a.zh + (long long)task * a.zh_stride;
   float* pd = a.pdot + (long long)task * a.pdot_stride;
-  for (int wi = blockIdx.x * it.WPB + it.lane; wi < it.NW; wi += gridDim.x * it.WPB) {
+  for (int wi = cta * it.WPB + it.lane; wi < it.NW; wi += ncta * it.WPB) {
     const int img = wi / (it.hc * it.wc);
     const int rem = wi - img * it.hc * it.wc;
     const int wy = rem / it.wc, wx = rem - wy * it.wc;
@@ -453,6 +458,17 @@ __global__ void __launch_bounds__(256) bnact_tan_kernel(BnActTanArgs a) {
       if (a.pdot_hi) st4_split(a.pdot_hi + (long long)task * a.pdot_stride, a.pdot_lo + (long long)task * a.pdot_stride, pidx, pbest);
     }
   }
+}
+
+__global__ void __launch_bounds__(256) bnact_tan_kernel(BnActTanArgs a) {
+  pdl_prologue(10);
+  __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_md[64], s_q[64];
+  const BnGeom g = a.g;
+  const int task = blockIdx.y;
+  bnact_tan_setup(a, g, task, (double)g.n * g.h * g.w, s_mu, s_r, s_g, s_b, s_md, s_q);
+  __syncthreads();
+  WinIter it(g);
+  bnact_tan_phase(a, g, task, blockIdx.x, gridDim.x, it, s_r, s_g, s_b, s_md, s_q);
 }
 
 void launch_bnact_tan(const BnActTanArgs& a, cudaStream_t st) {
@@ -633,6 +649,87 @@ void launch_bnbwd_tan(const BnBwdTanArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; bn_grid(a.g, a.tasks, &block);
   launch_cluster(bnbwd_tan_fused_kernel, a, cl, a.tasks, block, st);
+  CUDA_CHECK_LAUNCH();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused last block + head: when the last block of a task is tiny (<= 4 pooling windows per thread, <= 16 rows), its
+// BatchNorm/activation/pool, the classifier head (logits, loss gradient, weight-gradient chunk, feature gradient) and
+// the BatchNorm backward of the same block are ONE kernel with one CTA per task: the three stages exchange their data
+// through global memory written and re-read by the same CTA (visible after __syncthreads), the backward sums need no
+// cluster.  Replaces three dependent launches (5 + 7 + 7 us) on the critical path of every support / tangent pass.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tail_fused_kernel(BnActArgs fa, HeadArgs ha, BnBwdArgs ba) {
+  pdl_prologue(23);
+  extern __shared__ float smh[];
+  __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_c1[64], s_c2[64];
+  __shared__ float s_rowloss[64], s_rowcorrect[64];
+  const BnGeom g = fa.g;
+  const int task = blockIdx.y;
+  const double m = (double)g.n * g.h * g.w;
+  chan_setup(fa.stats + (long long)task * fa.stats_stride, fa.gamma, fa.beta, m, g.F, s_mu, s_r, s_g, s_b);
+  __syncthreads();
+  WinIter it(g);
+  bnact_phase(fa, g, task, 0, 1, it, s_mu, s_r, s_g, s_b);
+  __syncthreads();
+  head_body(ha, task, 0, smh, s_rowloss, s_rowcorrect);
+  __syncthreads();
+  double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  bnbwd_reduce_phase(ba, g, task, 0, 1, it, s_g, s_b, s1, s2);
+  const double t = block_reduce_totals(s1, s2, it, g.F);
+  if (threadIdx.x < g.F * 2) {
+    ((threadIdx.x & 1) ? s_c2 : s_c1)[threadIdx.x >> 1] = (float)(t / m);
+    (ba.stats_bwd + (long long)task * ba.stats_bwd_stride)[threadIdx.x] = t;
+  }
+  __syncthreads();
+  bnbwd_apply_phase(ba, g, task, 0, 1, it, s_r, s_g, s_b, s_c1, s_c2);
+}
+
+__global__ void __launch_bounds__(256) tail_tan_fused_kernel(BnActTanArgs fa, HeadArgs ha, BnBwdTanArgs ba) {
+  pdl_prologue(24);
+  extern __shared__ float smh[];
+  __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_md[64], s_q[64], s_c2[64], s_t1[64], s_t2[64];
+  __shared__ float s_rowloss[64], s_rowcorrect[64];
+  const BnGeom g = fa.g;
+  const int task = blockIdx.y;
+  const double m = (double)g.n * g.h * g.w;
+  bnact_tan_setup(fa, g, task, m, s_mu, s_r, s_g, s_b, s_md, s_q);
+  if (threadIdx.x < g.F) s_c2[threadIdx.x] = (float)((ba.stats_bwd + (long long)task * ba.stats_bwd_stride)[threadIdx.x * 2 + 1] / m);
+  __syncthreads();
+  WinIter it(g);
+  bnact_tan_phase(fa, g, task, 0, 1, it, s_r, s_g, s_b, s_md, s_q);
+  __syncthreads();
+  head_body(ha, task, 0, smh, s_rowloss, s_rowcorrect);
+  __syncthreads();
+  double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  bnbwd_tan_reduce_phase(ba, g, task, 0, 1, it, s_g, s_b, s1, s2);
+  const double t = block_reduce_totals(s1, s2, it, g.F);
+  if (threadIdx.x < g.F * 2) {
+    ((threadIdx.x & 1) ? s_t2 : s_t1)[threadIdx.x >> 1] = (float)(t / m);
+    (ba.stats_tbwd + (long long)task * ba.stats_tbwd_stride)[threadIdx.x] = t;
+  }
+  __syncthreads();
+  bnbwd_tan_apply_phase(ba, g, task, 0, 1, it, s_r, s_g, s_b, s_q, s_c2, s_t1, s_t2);
+}
+
+// the last block of `n` images is small enough for the fused kernels
+bool tail_fusable(const BnGeom& g, int n_rows, int rows_per_cta) {
+  const int F4 = g.F / 4, wpb = 256 / F4;
+  const int NW = g.n * ((g.h + 1) / 2) * ((g.w + 1) / 2);
+  return g_bn_fuse && g.F <= 64 && n_rows <= rows_per_cta && NW <= 4 * wpb;
+}
+
+void launch_tail_fused(const BnActArgs& fa, const HeadArgs& ha, const BnBwdArgs& ba, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_HEAD, 0.0, st);
+  const size_t smem = (size_t)5 * ha.rows_per_cta * ha.N * sizeof(float);
+  launch_pdl(tail_fused_kernel, dim3(1, fa.tasks), dim3(256), smem, st, fa, ha, ba);
+  CUDA_CHECK_LAUNCH();
+}
+
+void launch_tail_tan_fused(const BnActTanArgs& fa, const HeadArgs& ha, const BnBwdTanArgs& ba, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_HEAD, 0.0, st);
+  const size_t smem = (size_t)5 * ha.rows_per_cta * ha.N * sizeof(float);
+  launch_pdl(tail_tan_fused_kernel, dim3(1, fa.tasks), dim3(256), smem, st, fa, ha, ba);
   CUDA_CHECK_LAUNCH();
 }
 
