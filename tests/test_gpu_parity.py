@@ -386,12 +386,12 @@ def test_functional_network_operator(case, cuda_device):
 
 def test_fused_and_cluster_paths_match_plain_paths(cuda_device):
     """The scheduling / fusion variants (cluster split-K convs, fused BatchNorm backward, tangent conv split,
-    double-buffered target passes, filter-row wgrad) against the plain one-kernel-per-op paths they replaced
+    double-buffered target passes, filter-row wgrad, fused last block + head) against the plain one-kernel-per-op paths they replaced
     (selected through the diagnostic environment switches, read when the engine handle is created)."""
     g = load_golden("tiny_pp")
     batch, epoch = g.batch(0), g.iters[0][0]
     plain = {"MAML_B200_TC_SPLIT": "1", "MAML_B200_BN_FUSE": "0", "MAML_B200_TAN_SPLIT": "0", "MAML_B200_TGT_SLOTS": "1",
-             "MAML_B200_WGRAD_ROW": "0"}
+             "MAML_B200_WGRAD_ROW": "0", "MAML_B200_TAIL_FUSE": "0"}
     saved = {k: os.environ.get(k) for k in plain}
     try:
         os.environ.update(plain)
