@@ -168,6 +168,43 @@ def cpu_port_tasks_per_sec(args, iters, warmup, threads=None):
     return args.batch_size / med, threads, sample, times
 
 
+def torch_gpu_port_tasks_per_sec(args, dev, iters=3, warmup=1):
+    """SURVEY.md section 8d "library kernels to beat": the same call-for-call restatement of the reference
+    (torch.nn.functional convs / batch_norm / max_pool2d + autograd.grad(create_graph) + one reverse sweep), but on the
+    GPU through PyTorch's own CUDA kernels (cuDNN / ATen), strict fp32 (TF32 off).  This is what the reference does when
+    it sees a GPU (few_shot_learning_system.py:73-81).  A baseline beside the line, never the thing measured."""
+    import torch
+    from oracle import maml_oracle as O
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        state = {k: v.to(dev) for k, v in O.init_state(args).items()}
+        names = O.trainable_names(args)
+        m = {n: torch.zeros_like(state[n]) for n in names}
+        v = {n: torch.zeros_like(state[n]) for n in names}
+        step, times = 0, []
+        for it in range(warmup + iters):
+            batch = tuple(t.to(dev) for t in O.synthetic_batch(args, iteration=it))
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            res = O.autograd_train_iter(state, args, batch, 0)
+            clamp = [n for n in names if n.startswith("classifier.")] if "imagenet" in args.dataset_name else None
+            newp, m, v, step = O.adam_step({n: state[n] for n in names}, res["grads"], m, v, step, O.cosine_lr(args, 0), clamp=clamp)
+            state.update(newp)
+            state.update(res["running"])
+            torch.cuda.synchronize(dev)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        times.sort()
+        med = times[len(times) // 2]
+        return {"value": args.batch_size / med, "unit": "tasks/s", "ms_per_step": 1e3 * med,
+                "kind": "port on PyTorch CUDA library kernels (cuDNN / ATen eager autograd), fp32, inputs resident",
+                "sample": "%d timed iterations of %d tasks (median), %d warm-up" % (iters, args.batch_size, warmup)}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
 def run_reference_arm(cli, args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port) on the host cores."""
     if rank != 0:
@@ -347,6 +384,10 @@ def main():
             "last_loss": float(losses["loss"]),
         }
         if not cli.no_cpu_baseline and world == 1:
+            try:
+                line["torch_gpu_baseline"] = torch_gpu_port_tasks_per_sec(args, dev)
+            except Exception as exc:      # a baseline must never take the measurement down
+                line["torch_gpu_baseline"] = {"unavailable": repr(exc)[:200]}
             tps, cores, sample, _ = cpu_port_tasks_per_sec(args, iters=8, warmup=2)
             line["cpu_baseline"] = {"value": tps, "unit": "tasks/s", "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
