@@ -195,6 +195,7 @@ void launch_bnbwd(const BnBwdArgs& a, cudaStream_t st);          // reduce + app
 void launch_bnbwd_tan(const BnBwdTanArgs& a, cudaStream_t st);
 void bn_set_fuse(int on);
 bool tail_fusable(const BnGeom& g, int n_rows, int rows_per_cta);
+void tail_set_onchip(int on);
 void launch_tail_fused(const BnActArgs& fa, const HeadArgs& ha, const BnBwdArgs& ba, cudaStream_t st);
 void launch_tail_tan_fused(const BnActTanArgs& fa, const HeadArgs& ha, const BnBwdTanArgs& ba, cudaStream_t st);
 void launch_head(const HeadArgs& a, cudaStream_t st);

@@ -390,6 +390,7 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   for (int s = 0; ok && s < 2 * MAML_MAX_LAYERS; ++s) ok = cudaEventCreateWithFlags(&h->ev_pre[s], cudaEventDisableTiming) == cudaSuccess;
   if (const char* ts = getenv("MAML_B200_TAN_SPLIT")) h->tan_split = atoi(ts) != 0;
   if (const char* tf = getenv("MAML_B200_TAIL_FUSE")) h->tail_fuse = atoi(tf) != 0;
+  if (const char* tf = getenv("MAML_B200_TAIL_ONCHIP")) tail_set_onchip(atoi(tf));
   if (!ok) { maml_b200_destroy(h); return fail("stream / event creation failed"); }
   *out = h;
   return 0;

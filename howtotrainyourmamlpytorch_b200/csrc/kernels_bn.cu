@@ -712,6 +712,148 @@ __global__ void __launch_bounds__(256) tail_tan_fused_kernel(BnActTanArgs fa, He
   bnbwd_tan_apply_phase(ba, g, task, 0, 1, it, s_r, s_g, s_b, s_q, s_c2, s_t1, s_t2);
 }
 
+// On-chip variant of tail_fused_kernel (primal): what the three stages exchange stays in shared memory / registers.
+//   stage 1  every thread owns <= MAXI (pooling window, channel quad) items: loads z once, keeps zh[4], the arg-max and
+//            the leaky slope in REGISTERS, writes zh / p to global for later passes and p into shared memory (features);
+//   stage 2  head_body runs on shared-memory copies of the features, W_fc, b_fc and leaves df in shared memory;
+//   stage 3  BatchNorm backward of the same items from registers + shared df: block reduction -> c1, c2 -> dz.
+// One global round trip (z, statistics, W_fc in parallel) instead of ~8 dependent ones.
+template <int MAXI>
+__global__ void __launch_bounds__(256) tail_onchip_kernel(BnActArgs fa, HeadArgs ha, BnBwdArgs ba) {
+  pdl_prologue(25);
+  extern __shared__ float smh[];                  // [head scratch 5*R*N | f n*D | df n*D | W N*D | b N]
+  __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_c1[64], s_c2[64];
+  __shared__ float s_rowloss[64], s_rowcorrect[64];
+  const BnGeom g = fa.g;
+  const int task = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int n = ha.n, N = ha.N, D = ha.D;
+  float* s_f = smh + 5 * ha.rows_per_cta * N;
+  float* s_df = s_f + n * D;
+  float* s_W = s_df + n * D;
+  float* s_bfc = s_W + N * D;
+  const double m = (double)g.n * g.h * g.w;
+  chan_setup(fa.stats + (long long)task * fa.stats_stride, fa.gamma, fa.beta, m, g.F, s_mu, s_r, s_g, s_b);
+  {
+    const float* W = ha.Wfc + (long long)task * ha.theta_stride;
+    const float* bb = ha.bfc + (long long)task * ha.theta_stride;
+    for (int o = tid; o < N * D; o += 256) s_W[o] = W[o];
+    if (tid < N) s_bfc[tid] = bb[tid];
+  }
+  __syncthreads();
+  WinIter it(g);
+  const bool worker = it.lane < it.WPB;
+  float4 zh[MAXI][4]; int4 arg[MAXI]; float4 sl[MAXI]; int wy_[MAXI], wx_[MAXI], img_[MAXI]; bool have[MAXI], full[MAXI];
+  float4 mu, r, ga, be;
+  if (worker) { mu = ld4s(s_mu, it.q); r = ld4s(s_r, it.q); ga = ld4s(s_g, it.q); be = ld4s(s_b, it.q); }
+  float* z = fa.z + (long long)task * fa.z_stride;
+  float* pg = fa.p + (long long)task * fa.p_stride;
+  // ---------------- stage 1: BatchNorm + leaky-ReLU + max-pool (first max wins)
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    const int wi = it.lane + i * it.WPB;
+    have[i] = worker && wi < it.NW;
+    full[i] = false;
+    if (!have[i]) continue;
+    const int img = wi / (it.hc * it.wc);
+    const int rem = wi - img * it.hc * it.wc;
+    const int wy = rem / it.wc, wx = rem - wy * it.wc;
+    img_[i] = img; wy_[i] = wy; wx_[i] = wx;
+    float4 best = make_float4(0.f, 0.f, 0.f, 0.f), ybest = best;
+    int4 am = make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = 2 * wy + (k >> 1), xx = 2 * wx + (k & 1);
+      zh[i][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (yy < g.h && xx < g.w) {
+        const long long idx = ((long long)img * g.G + (yy + 1) * g.gw + (xx + 1)) * g.F + it.q * 4;
+        const float4 zv = ld4(z + idx);
+        float4 zz, y, act;
+        zz.x = (zv.x - mu.x) * r.x; zz.y = (zv.y - mu.y) * r.y; zz.z = (zv.z - mu.z) * r.z; zz.w = (zv.w - mu.w) * r.w;
+        st4(z + idx, zz);
+        zh[i][k] = zz;
+        y.x = fmaf(ga.x, zz.x, be.x); y.y = fmaf(ga.y, zz.y, be.y); y.z = fmaf(ga.z, zz.z, be.z); y.w = fmaf(ga.w, zz.w, be.w);
+        act.x = leaky(y.x); act.y = leaky(y.y); act.z = leaky(y.z); act.w = leaky(y.w);
+        if (k == 0) { best = act; ybest = y; }
+        else {
+          if (act.x > best.x) { best.x = act.x; ybest.x = y.x; am.x = k; }
+          if (act.y > best.y) { best.y = act.y; ybest.y = y.y; am.y = k; }
+          if (act.z > best.z) { best.z = act.z; ybest.z = y.z; am.z = k; }
+          if (act.w > best.w) { best.w = act.w; ybest.w = y.w; am.w = k; }
+        }
+      }
+    }
+    arg[i] = am;
+    sl[i] = make_float4(slope_of(ybest.x), slope_of(ybest.y), slope_of(ybest.z), slope_of(ybest.w));
+    full[i] = (wy < g.ph && wx < g.pw);
+    if (full[i]) {
+      const long long pidx = ((long long)img * g.pG + (wy + g.pb) * g.pgw + (wx + g.pb)) * g.F + it.q * 4;
+      st4(pg + pidx, best);
+      st4(s_f + pidx, best);                       // pb = 0 on the last block: pidx is the feature index img * D + ...
+    }
+  }
+  __syncthreads();
+  // ---------------- stage 2: classifier head on the shared-memory copies
+  {
+    HeadArgs hs = ha;
+    hs.f = s_f; hs.f_stride = 0;
+    hs.Wfc = s_W; hs.bfc = s_bfc; hs.theta_stride = 0;
+    hs.df = s_df; hs.df_stride = 0;
+    head_body(hs, task, 0, smh, s_rowloss, s_rowcorrect);
+  }
+  __syncthreads();
+  {
+    float* dfg = ha.df + (long long)task * ha.df_stride;     // phase B reads the primal df again
+    for (int o = tid; o < n * D; o += 256) dfg[o] = s_df[o];
+  }
+  // ---------------- stage 3: BatchNorm backward of the same items
+  double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  float4 dyv[MAXI];
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    dyv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!have[i] || !full[i]) continue;
+    const long long pidx = ((long long)img_[i] * g.pG + (wy_[i] + g.pb) * g.pgw + (wx_[i] + g.pb)) * g.F + it.q * 4;
+    const float4 d = ld4(s_df + pidx);
+    dyv[i] = make_float4(d.x * sl[i].x, d.y * sl[i].y, d.z * sl[i].z, d.w * sl[i].w);
+    s1[0] += dyv[i].x; s2[0] += (double)dyv[i].x * (double)pick(zh[i], arg[i].x, 0);
+    s1[1] += dyv[i].y; s2[1] += (double)dyv[i].y * (double)pick(zh[i], arg[i].y, 1);
+    s1[2] += dyv[i].z; s2[2] += (double)dyv[i].z * (double)pick(zh[i], arg[i].z, 2);
+    s1[3] += dyv[i].w; s2[3] += (double)dyv[i].w * (double)pick(zh[i], arg[i].w, 3);
+  }
+  const double t = block_reduce_totals(s1, s2, it, g.F);
+  if (tid < g.F * 2) {
+    ((tid & 1) ? s_c2 : s_c1)[tid >> 1] = (float)(t / m);
+    (ba.stats_bwd + (long long)task * ba.stats_bwd_stride)[tid] = t;
+  }
+  __syncthreads();
+  if (!worker) return;
+  const float4 c1 = ld4s(s_c1, it.q), c2 = ld4s(s_c2, it.q);
+  const float4 rg = make_float4(r.x * ga.x, r.y * ga.y, r.z * ga.z, r.w * ga.w);
+  float* dz = ba.dz + (long long)task * ba.dz_stride;
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    if (!have[i]) continue;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = 2 * wy_[i] + (k >> 1), xx = 2 * wx_[i] + (k & 1);
+      if (yy < g.h && xx < g.w) {
+        const long long idx = ((long long)img_[i] * g.G + (yy + 1) * g.gw + (xx + 1)) * g.F + it.q * 4;
+        float4 o;
+        o.x = rg.x * ((full[i] && arg[i].x == k ? dyv[i].x : 0.f) - c1.x - zh[i][k].x * c2.x);
+        o.y = rg.y * ((full[i] && arg[i].y == k ? dyv[i].y : 0.f) - c1.y - zh[i][k].y * c2.y);
+        o.z = rg.z * ((full[i] && arg[i].z == k ? dyv[i].z : 0.f) - c1.z - zh[i][k].z * c2.z);
+        o.w = rg.w * ((full[i] && arg[i].w == k ? dyv[i].w : 0.f) - c1.w - zh[i][k].w * c2.w);
+        st4(dz + idx, o);
+        if (ba.dz_hi) st4_split(ba.dz_hi + (long long)task * ba.dz_stride, ba.dz_lo + (long long)task * ba.dz_stride, idx, o);
+      }
+    }
+  }
+}
+
+static int g_tail_onchip = 1;          // env MAML_B200_TAIL_ONCHIP=0: tail_fused_kernel (stages exchange data through L2)
+void tail_set_onchip(int on) { g_tail_onchip = on; }
+
 // the last block of `n` images is small enough for the fused kernels
 bool tail_fusable(const BnGeom& g, int n_rows, int rows_per_cta) {
   const int F4 = g.F / 4, wpb = 256 / F4;
@@ -721,6 +863,17 @@ bool tail_fusable(const BnGeom& g, int n_rows, int rows_per_cta) {
 
 void launch_tail_fused(const BnActArgs& fa, const HeadArgs& ha, const BnBwdArgs& ba, cudaStream_t st) {
   ProfScope prof_scope__(PROF_HEAD, 0.0, st);
+  {
+    const int F4 = fa.g.F / 4, wpb = 256 / F4;
+    const int NW = fa.g.n * ((fa.g.h + 1) / 2) * ((fa.g.w + 1) / 2);
+    const size_t words = (size_t)5 * ha.rows_per_cta * ha.N + 2 * (size_t)ha.n * ha.D + (size_t)ha.N * ha.D + ha.N;
+    if (g_tail_onchip && fa.g.pb == 0 && fa.p_hi == nullptr && NW <= 2 * wpb && words * sizeof(float) <= 40 * 1024) {
+      if (NW <= wpb) launch_pdl(tail_onchip_kernel<1>, dim3(1, fa.tasks), dim3(256), words * sizeof(float), st, fa, ha, ba);
+      else launch_pdl(tail_onchip_kernel<2>, dim3(1, fa.tasks), dim3(256), words * sizeof(float), st, fa, ha, ba);
+      CUDA_CHECK_LAUNCH();
+      return;
+    }
+  }
   const size_t smem = (size_t)5 * ha.rows_per_cta * ha.N * sizeof(float);
   launch_pdl(tail_fused_kernel, dim3(1, fa.tasks), dim3(256), smem, st, fa, ha, ba);
   CUDA_CHECK_LAUNCH();
