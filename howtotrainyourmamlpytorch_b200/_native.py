@@ -184,12 +184,13 @@ class Engine(object):
         _check(self.lib, self.lib.maml_b200_trace(self.h, int(bool(enable))), "maml_b200_trace")
 
     def trace_read(self, capacity=4096):
-        """[(t_ns, kernel_id)] of every kernel started since trace(True) / the last read, in start order."""
+        """[(t_ns, kernel_id, launch_tag)] of every kernel started since trace(True) / the last read, in start order
+        (launch_tag = launch sequence number inside the iteration = kernel-node order of the captured graph)."""
         buf = (ctypes.c_uint64 * capacity)()
         n = self.lib.maml_b200_trace_read(self.h, buf, capacity)
         if n < 0:
             raise RuntimeError("maml_b200_trace_read: " + self.lib.maml_b200_last_error().decode())
-        return [(int(buf[i]) >> 8, int(buf[i]) & 0xff) for i in range(n)]
+        return [(int(buf[i]) >> 20, int(buf[i]) & 0xff, (int(buf[i]) >> 8) & 0xfff) for i in range(n)]
 
     def profile(self, enable):
         _check(self.lib, self.lib.maml_b200_profile(self.h, int(bool(enable))), "maml_b200_profile")

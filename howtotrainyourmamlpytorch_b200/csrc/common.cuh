@@ -51,6 +51,7 @@ struct ConvArgs {
   double* stats; long long stats_stride;       // [task][ncols][2]
   int tasks;
   double alg_flops;                            // algorithmic FLOPs of this launch (valid pixels only; profiling)
+  int tag;          // launch sequence number inside the iteration (device trace)
 };
 
 struct Conv0Args {                             // first block: K = 9 * C0 is tiny, direct conv
@@ -63,6 +64,7 @@ struct Conv0Args {                             // first block: K = 9 * C0 is tin
   double* stats; long long stats_stride;
   int tasks;
   double alg_flops;
+  int tag;          // launch sequence number inside the iteration (device trace)
 };
 
 struct WgradArgs {
@@ -74,6 +76,7 @@ struct WgradArgs {
   float* partial; long long partial_task_stride; long long chunk_stride;  // [task][chunk][9*kc*ncols + ncols]
   int tasks;
   double alg_flops;
+  int tag;          // launch sequence number inside the iteration (device trace)
 };
 
 struct BnGeom { int n, h, w, gw, G, ph, pw, pgw, pG, pb, F; };
@@ -85,6 +88,7 @@ struct BnActArgs {                // forward: z -> zh (in place), pooled activat
   float* p; long long p_stride;
   float* p_hi; float* p_lo;                         // nullable: TF32 hi/lo planes of p (same stride)
   BnGeom g; int tasks;
+  int tag;          // launch sequence number inside the iteration (device trace)
 };
 
 struct BnActTanArgs {             // tangent forward: zdot -> zhdot (in place), pdot
@@ -97,6 +101,7 @@ struct BnActTanArgs {             // tangent forward: zdot -> zhdot (in place), 
   float* pdot; long long pdot_stride;
   float* pdot_hi; float* pdot_lo;
   BnGeom g; int tasks;
+  int tag;          // launch sequence number inside the iteration (device trace)
 };
 
 struct BnBwdArgs {                // backward reduce / apply (primal)
@@ -108,6 +113,7 @@ struct BnBwdArgs {                // backward reduce / apply (primal)
   float* dz; long long dz_stride;
   float* dz_hi; float* dz_lo;
   BnGeom g; int tasks;
+  int tag;          // launch sequence number inside the iteration (device trace)
 };
 
 struct BnBwdTanArgs {             // backward reduce / apply (tangent)
@@ -125,6 +131,7 @@ struct BnBwdTanArgs {             // backward reduce / apply (tangent)
   float* dzdot; long long dzdot_stride;
   float* dzdot_hi; float* dzdot_lo;
   BnGeom g; int tasks;
+  int tag;          // launch sequence number inside the iteration (device trace)
 };
 
 enum { HEAD_SUPPORT = 0, HEAD_TARGET_FWD = 1, HEAD_TARGET_BWD = 2, HEAD_TANGENT = 3 };
@@ -146,6 +153,7 @@ struct HeadArgs {
   float* logits_out; long long logits_stride;     // nullable [n][N]
   float* correct_out; long long correct_stride;   // nullable per-task count
   int tasks;
+  int tag;          // launch sequence number inside the iteration (device trace)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -223,6 +231,7 @@ struct ExportArgs {
   int n_s, n_t;
   int hw[MAML_MAX_LAYERS];                           // h*w per block
   float* result;
+  int tag;          // launch sequence number inside the iteration (device trace)
 };
 void launch_export(const ExportArgs& a, cudaStream_t st);
 
@@ -252,13 +261,14 @@ extern int g_launch_prio;
 static __device__ unsigned long long* t_trace_buf = nullptr;
 #define MAML_TRACE_SETTER(fn) void fn(unsigned long long* p) { cudaMemcpyToSymbol(t_trace_buf, &p, sizeof(p)); }
 #define MAML_TRACE_CAP 4094
-__device__ __forceinline__ void trace_mark(int kid) {
+__device__ __forceinline__ void trace_mark(int kid, int tag = 0) {
   unsigned long long* t = t_trace_buf;
   if (t != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
     unsigned long long now;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
     const unsigned long long slot = atomicAdd(t, 1ULL);
-    if (slot < MAML_TRACE_CAP) t[1 + slot] = (now << 8) | (unsigned long long)(kid & 0xff);
+    // entry: [63:20] globaltimer ns (44 bits), [19:8] launch tag, [7:0] kernel id (bit 7 = end-of-CTA mark)
+    if (slot < MAML_TRACE_CAP) t[1 + slot] = (now << 20) | ((unsigned long long)(tag & 0xfff) << 8) | (unsigned long long)(kid & 0xff);
   }
 }
 void trace_set_conv(unsigned long long* p);
@@ -267,8 +277,8 @@ void trace_set_head(unsigned long long* p);
 void trace_set_param(unsigned long long* p);
 void trace_set_tc(unsigned long long* p);
 
-__device__ __forceinline__ void pdl_prologue(int kid = 0) {
-  trace_mark(kid);
+__device__ __forceinline__ void pdl_prologue(int kid = 0, int tag = 0) {
+  trace_mark(kid, tag);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
@@ -292,6 +302,9 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 }
 
 extern long long g_launch_counter;   // bumped by every launcher
+extern long long g_launch_base;      // value of g_launch_counter when the current iteration started to be enqueued
+inline int launch_tag() { return (int)(g_launch_counter - g_launch_base); }
+template <class A> inline A tagged(const A& a) { A t = a; t.tag = launch_tag(); return t; }
 
 #define CUDA_CHECK_LAUNCH() do { g_launch_counter++; } while (0)
 

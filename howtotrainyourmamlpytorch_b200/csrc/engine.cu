@@ -827,6 +827,7 @@ static void pack_u(maml_b200_handle* h, int T, cudaStream_t st) {
 static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it, const float* meta, const float* x_support,
                              const long long* ys, const float* x_target, const long long* yt, float* result, float* last_logits,
                              cudaStream_t st) {
+  g_launch_base = g_launch_counter;      // launch tags (device trace) count from the start of the iteration
   const int T = it->n_tasks;
   const unsigned mask = it->target_mask & ((1u << it->num_steps) - 1u);
   const long long TP = (long long)h->maxT * h->Ppad;
@@ -1122,7 +1123,7 @@ extern "C" int maml_b200_trace(maml_b200_handle* h, int32_t enable) {
   CK(cudaDeviceSynchronize());
   return 0;
 }
-// out[i] = (globaltimer_ns << 8) | kernel id, in start order; returns the number of entries (<0: error); clears the trace
+// out[i] = (globaltimer_ns << 20) | (launch tag << 8) | kernel id, in start order; returns the number of entries (<0: error); clears the trace
 extern "C" int64_t maml_b200_trace_read(maml_b200_handle* h, uint64_t* out, int64_t capacity) {
   if (!h || !out || !g_trace_dev) { fail("trace is not enabled"); return -1; }
   if (cudaDeviceSynchronize() != cudaSuccess) { fail("device error"); return -1; }

@@ -100,7 +100,7 @@ __device__ __forceinline__ void bnact_phase(const BnActArgs& a, const BnGeom& g,
 }
 
 __global__ void __launch_bounds__(256) bnact_kernel(BnActArgs a) {
-  pdl_prologue(6);
+  pdl_prologue(6, a.tag);
   __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64];
   const BnGeom g = a.g;
   const int task = blockIdx.y;
@@ -124,7 +124,7 @@ static inline dim3 bn_grid(const BnGeom& g, int tasks, int* block) {
 void launch_bnact(const BnActArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
-  launch_pdl(bnact_kernel, dim3(grid), dim3(block), (size_t)(0), st, a);
+  launch_pdl(bnact_kernel, dim3(grid), dim3(block), (size_t)(0), st, tagged(a));
   CUDA_CHECK_LAUNCH();
 }
 
@@ -255,7 +255,7 @@ __device__ __forceinline__ void bnbwd_reduce_phase(const BnBwdArgs& a, const BnG
 }
 
 __global__ void __launch_bounds__(256) bnbwd_reduce_kernel(BnBwdArgs a) {
-  pdl_prologue(7);
+  pdl_prologue(7, a.tag);
   __shared__ float s_g[64], s_b[64];
   const BnGeom g = a.g;
   const int task = blockIdx.y;
@@ -271,7 +271,7 @@ void launch_bnbwd_reduce(const BnBwdArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
   if (grid.x > 148) grid.x = 148;
-  launch_pdl(bnbwd_reduce_kernel, dim3(grid), dim3(block), (size_t)(0), st, a);
+  launch_pdl(bnbwd_reduce_kernel, dim3(grid), dim3(block), (size_t)(0), st, tagged(a));
   CUDA_CHECK_LAUNCH();
 }
 
@@ -325,7 +325,7 @@ __device__ __forceinline__ void bnbwd_apply_phase(const BnBwdArgs& a, const BnGe
 }
 
 __global__ void __launch_bounds__(256) bnbwd_apply_kernel(BnBwdArgs a) {
-  pdl_prologue(8);
+  pdl_prologue(8, a.tag);
   __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_c1[64], s_c2[64];
   const BnGeom g = a.g;
   const int task = blockIdx.y;
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(256) bnbwd_apply_kernel(BnBwdArgs a) {
 
 // fused: one cluster of CTAs per task does reduce -> all-reduce through distributed shared memory -> apply
 __global__ void __launch_bounds__(256) bnbwd_fused_kernel(BnBwdArgs a) {
-  pdl_prologue(9);
+  pdl_prologue(9, a.tag);
   bn_cluster_arrive();
   __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_c1[64], s_c2[64];
   __shared__ double gather[8][128];
@@ -389,14 +389,14 @@ void launch_bnbwd(const BnBwdArgs& a, cudaStream_t st) {
   if (cl == 0) { launch_bnbwd_reduce(a, st); launch_bnbwd_apply(a, st); return; }
   ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; bn_grid(a.g, a.tasks, &block);
-  launch_cluster(bnbwd_fused_kernel, a, cl, a.tasks, block, st);
+  launch_cluster(bnbwd_fused_kernel, tagged(a), cl, a.tasks, block, st);
   CUDA_CHECK_LAUNCH();
 }
 
 void launch_bnbwd_apply(const BnBwdArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
-  launch_pdl(bnbwd_apply_kernel, dim3(grid), dim3(block), (size_t)(0), st, a);
+  launch_pdl(bnbwd_apply_kernel, dim3(grid), dim3(block), (size_t)(0), st, tagged(a));
   CUDA_CHECK_LAUNCH();
 }
 
@@ -461,7 +461,7 @@ __device__ __forceinline__ void bnact_tan_phase(const BnActTanArgs& a, const BnG
 }
 
 __global__ void __launch_bounds__(256) bnact_tan_kernel(BnActTanArgs a) {
-  pdl_prologue(10);
+  pdl_prologue(10, a.tag);
   __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_md[64], s_q[64];
   const BnGeom g = a.g;
   const int task = blockIdx.y;
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(256) bnact_tan_kernel(BnActTanArgs a) {
 void launch_bnact_tan(const BnActTanArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
-  launch_pdl(bnact_tan_kernel, dim3(grid), dim3(block), (size_t)(0), st, a);
+  launch_pdl(bnact_tan_kernel, dim3(grid), dim3(block), (size_t)(0), st, tagged(a));
   CUDA_CHECK_LAUNCH();
 }
 
@@ -519,7 +519,7 @@ __device__ __forceinline__ void bnbwd_tan_reduce_phase(const BnBwdTanArgs& a, co
 }
 
 __global__ void __launch_bounds__(256) bnbwd_tan_reduce_kernel(BnBwdTanArgs a) {
-  pdl_prologue(11);
+  pdl_prologue(11, a.tag);
   __shared__ float s_g[64], s_b[64];
   const BnGeom g = a.g;
   const int task = blockIdx.y;
@@ -535,7 +535,7 @@ void launch_bnbwd_tan_reduce(const BnBwdTanArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
   if (grid.x > 148) grid.x = 148;
-  launch_pdl(bnbwd_tan_reduce_kernel, dim3(grid), dim3(block), (size_t)(0), st, a);
+  launch_pdl(bnbwd_tan_reduce_kernel, dim3(grid), dim3(block), (size_t)(0), st, tagged(a));
   CUDA_CHECK_LAUNCH();
 }
 
@@ -601,7 +601,7 @@ __device__ __forceinline__ void bnbwd_tan_setup(const BnBwdTanArgs& a, const BnG
 }
 
 __global__ void __launch_bounds__(256) bnbwd_tan_apply_kernel(BnBwdTanArgs a) {
-  pdl_prologue(12);
+  pdl_prologue(12, a.tag);
   __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_q[64], s_c2[64], s_t1[64], s_t2[64];
   const BnGeom g = a.g;
   const int task = blockIdx.y;
@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(256) bnbwd_tan_apply_kernel(BnBwdTanArgs a) {
 }
 
 __global__ void __launch_bounds__(256) bnbwd_tan_fused_kernel(BnBwdTanArgs a) {
-  pdl_prologue(13);
+  pdl_prologue(13, a.tag);
   bn_cluster_arrive();
   __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_q[64], s_c2[64], s_t1[64], s_t2[64];
   __shared__ double gather[8][128];
@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(256) bnbwd_tan_fused_kernel(BnBwdTanArgs a) {
 void launch_bnbwd_tan_apply(const BnBwdTanArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; dim3 grid = bn_grid(a.g, a.tasks, &block);
-  launch_pdl(bnbwd_tan_apply_kernel, dim3(grid), dim3(block), (size_t)(0), st, a);
+  launch_pdl(bnbwd_tan_apply_kernel, dim3(grid), dim3(block), (size_t)(0), st, tagged(a));
   CUDA_CHECK_LAUNCH();
 }
 
@@ -648,7 +648,7 @@ void launch_bnbwd_tan(const BnBwdTanArgs& a, cudaStream_t st) {
   if (cl == 0) { launch_bnbwd_tan_reduce(a, st); launch_bnbwd_tan_apply(a, st); return; }
   ProfScope prof_scope__(PROF_BN, 0.0, st);
   int block; bn_grid(a.g, a.tasks, &block);
-  launch_cluster(bnbwd_tan_fused_kernel, a, cl, a.tasks, block, st);
+  launch_cluster(bnbwd_tan_fused_kernel, tagged(a), cl, a.tasks, block, st);
   CUDA_CHECK_LAUNCH();
 }
 
@@ -660,7 +660,7 @@ void launch_bnbwd_tan(const BnBwdTanArgs& a, cudaStream_t st) {
 // cluster.  Replaces three dependent launches (5 + 7 + 7 us) on the critical path of every support / tangent pass.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tail_fused_kernel(BnActArgs fa, HeadArgs ha, BnBwdArgs ba) {
-  pdl_prologue(23);
+  pdl_prologue(23, fa.tag);
   extern __shared__ float smh[];
   __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_c1[64], s_c2[64];
   __shared__ float s_rowloss[64], s_rowcorrect[64];
@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(256) tail_fused_kernel(BnActArgs fa, HeadArgs 
 }
 
 __global__ void __launch_bounds__(256) tail_tan_fused_kernel(BnActTanArgs fa, HeadArgs ha, BnBwdTanArgs ba) {
-  pdl_prologue(24);
+  pdl_prologue(24, fa.tag);
   extern __shared__ float smh[];
   __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_md[64], s_q[64], s_c2[64], s_t1[64], s_t2[64];
   __shared__ float s_rowloss[64], s_rowcorrect[64];
@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(256) tail_tan_fused_kernel(BnActTanArgs fa, He
 // One global round trip (z, statistics, W_fc in parallel) instead of ~8 dependent ones.
 template <int MAXI>
 __global__ void __launch_bounds__(256) tail_onchip_kernel(BnActArgs fa, HeadArgs ha, BnBwdArgs ba) {
-  pdl_prologue(25);
+  pdl_prologue(25, fa.tag);
   extern __shared__ float smh[];                  // [head scratch 5*R*N | f n*D | df n*D | W N*D | b N]
   __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_c1[64], s_c2[64];
   __shared__ float s_rowloss[64], s_rowcorrect[64];
@@ -868,21 +868,21 @@ void launch_tail_fused(const BnActArgs& fa, const HeadArgs& ha, const BnBwdArgs&
     const int NW = fa.g.n * ((fa.g.h + 1) / 2) * ((fa.g.w + 1) / 2);
     const size_t words = (size_t)5 * ha.rows_per_cta * ha.N + 2 * (size_t)ha.n * ha.D + (size_t)ha.N * ha.D + ha.N;
     if (g_tail_onchip && fa.g.pb == 0 && fa.p_hi == nullptr && NW <= 2 * wpb && words * sizeof(float) <= 40 * 1024) {
-      if (NW <= wpb) launch_pdl(tail_onchip_kernel<1>, dim3(1, fa.tasks), dim3(256), words * sizeof(float), st, fa, ha, ba);
-      else launch_pdl(tail_onchip_kernel<2>, dim3(1, fa.tasks), dim3(256), words * sizeof(float), st, fa, ha, ba);
+      if (NW <= wpb) launch_pdl(tail_onchip_kernel<1>, dim3(1, fa.tasks), dim3(256), words * sizeof(float), st, tagged(fa), ha, ba);
+      else launch_pdl(tail_onchip_kernel<2>, dim3(1, fa.tasks), dim3(256), words * sizeof(float), st, tagged(fa), ha, ba);
       CUDA_CHECK_LAUNCH();
       return;
     }
   }
   const size_t smem = (size_t)5 * ha.rows_per_cta * ha.N * sizeof(float);
-  launch_pdl(tail_fused_kernel, dim3(1, fa.tasks), dim3(256), smem, st, fa, ha, ba);
+  launch_pdl(tail_fused_kernel, dim3(1, fa.tasks), dim3(256), smem, st, tagged(fa), ha, ba);
   CUDA_CHECK_LAUNCH();
 }
 
 void launch_tail_tan_fused(const BnActTanArgs& fa, const HeadArgs& ha, const BnBwdTanArgs& ba, cudaStream_t st) {
   ProfScope prof_scope__(PROF_HEAD, 0.0, st);
   const size_t smem = (size_t)5 * ha.rows_per_cta * ha.N * sizeof(float);
-  launch_pdl(tail_tan_fused_kernel, dim3(1, fa.tasks), dim3(256), smem, st, fa, ha, ba);
+  launch_pdl(tail_tan_fused_kernel, dim3(1, fa.tasks), dim3(256), smem, st, tagged(fa), ha, ba);
   CUDA_CHECK_LAUNCH();
 }
 

@@ -9,6 +9,7 @@
 #include "common.cuh"
 
 long long g_launch_counter = 0;
+long long g_launch_base = 0;
 int g_use_pdl = 0;
 int g_launch_prio = 0;
 
@@ -94,7 +95,7 @@ __device__ __forceinline__ void conv_epilogue(float (&acc)[4][FN], int j0, int r
 // ---------------------------------------------------------------------------------------------
 template <int FN>
 __global__ void __launch_bounds__(256) conv_rows_kernel(ConvArgs a) {
-  pdl_prologue(1);
+  pdl_prologue(1, a.tag);
   constexpr int NC = 16 * FN;
   __shared__ __align__(16) float As[16][68];
   __shared__ __align__(16) float Ws[16][NC];
@@ -190,10 +191,10 @@ void launch_conv_rows(const ConvArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_CONV, a.alg_flops, st);
   dim3 grid((a.rows + 63) / 64, a.tasks);
   switch (a.ncols / 16) {
-    case 1: launch_pdl(conv_rows_kernel<1>, dim3(grid), dim3(256), (size_t)(0), st, a); break;
-    case 2: launch_pdl(conv_rows_kernel<2>, dim3(grid), dim3(256), (size_t)(0), st, a); break;
-    case 3: launch_pdl(conv_rows_kernel<3>, dim3(grid), dim3(256), (size_t)(0), st, a); break;
-    default: launch_pdl(conv_rows_kernel<4>, dim3(grid), dim3(256), (size_t)(0), st, a); break;
+    case 1: launch_pdl(conv_rows_kernel<1>, dim3(grid), dim3(256), (size_t)(0), st, tagged(a)); break;
+    case 2: launch_pdl(conv_rows_kernel<2>, dim3(grid), dim3(256), (size_t)(0), st, tagged(a)); break;
+    case 3: launch_pdl(conv_rows_kernel<3>, dim3(grid), dim3(256), (size_t)(0), st, tagged(a)); break;
+    default: launch_pdl(conv_rows_kernel<4>, dim3(grid), dim3(256), (size_t)(0), st, tagged(a)); break;
   }
   CUDA_CHECK_LAUNCH();
 }
@@ -203,7 +204,7 @@ void launch_conv_rows(const ConvArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 template <int FN>
 __global__ void __launch_bounds__(256) conv0_kernel(Conv0Args a) {
-  pdl_prologue(2);
+  pdl_prologue(2, a.tag);
   constexpr int NC = 16 * FN;
   extern __shared__ float sm0[];
   __shared__ double sred[8 * NC * 2];
@@ -259,10 +260,10 @@ void launch_conv0(const Conv0Args& a, cudaStream_t st) {
   dim3 grid((a.rows + 63) / 64, a.tasks);
   const size_t smem = (size_t)(9 * a.c0 * a.ncols + (64 + 2 * (a.gw + 1)) * a.c0) * sizeof(float);
   switch (a.ncols / 16) {
-    case 1: launch_pdl(conv0_kernel<1>, dim3(grid), dim3(256), (size_t)(smem), st, a); break;
-    case 2: launch_pdl(conv0_kernel<2>, dim3(grid), dim3(256), (size_t)(smem), st, a); break;
-    case 3: launch_pdl(conv0_kernel<3>, dim3(grid), dim3(256), (size_t)(smem), st, a); break;
-    default: launch_pdl(conv0_kernel<4>, dim3(grid), dim3(256), (size_t)(smem), st, a); break;
+    case 1: launch_pdl(conv0_kernel<1>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a)); break;
+    case 2: launch_pdl(conv0_kernel<2>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a)); break;
+    case 3: launch_pdl(conv0_kernel<3>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a)); break;
+    default: launch_pdl(conv0_kernel<4>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a)); break;
   }
   CUDA_CHECK_LAUNCH();
 }
@@ -275,7 +276,7 @@ void launch_conv0(const Conv0Args& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 template <int CN, int FN>
 __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
-  pdl_prologue(3);
+  pdl_prologue(3, a.tag);
   constexpr int KC = 16 * CN, NC = 16 * FN;
   __shared__ __align__(16) float As[16][KC];
   __shared__ __align__(16) float Ds[16][NC];
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
 // dz tile is staged once for three taps and the number of barriers per FMA drops 3x.  grid (nchunks * 3, tasks).
 template <int CN, int FN>
 __global__ void __launch_bounds__(256) wgrad_row_kernel(WgradArgs a) {
-  pdl_prologue(3);
+  pdl_prologue(3, a.tag);
   constexpr int KC = 16 * CN, NC = 16 * FN;
   constexpr int A4 = 18 * KC / 4;                  // float4 loads of the 18-row A window
   __shared__ __align__(16) float As[18][KC];
@@ -479,12 +480,12 @@ void launch_wgrad(const WgradArgs& a, cudaStream_t st) {
   const int cn = a.kc / 16, fn = a.ncols / 16;
   if (g_wgrad_rows3) {
     dim3 grid(a.nchunks * 3, a.tasks);
-#define WGR_CASE(C, F_) if (cn == C && fn == F_) { launch_pdl(wgrad_row_kernel<C, F_>, dim3(grid), dim3(256), (size_t)(0), st, a); CUDA_CHECK_LAUNCH(); return; }
+#define WGR_CASE(C, F_) if (cn == C && fn == F_) { launch_pdl(wgrad_row_kernel<C, F_>, dim3(grid), dim3(256), (size_t)(0), st, tagged(a)); CUDA_CHECK_LAUNCH(); return; }
     WGR_CASE(1, 1) WGR_CASE(2, 2) WGR_CASE(3, 3) WGR_CASE(4, 4)
 #undef WGR_CASE
   }
   dim3 grid(a.nchunks * 9, a.tasks);
-#define WG_CASE(C, F_) if (cn == C && fn == F_) { launch_pdl(wgrad_kernel<C, F_>, dim3(grid), dim3(256), (size_t)(0), st, a); CUDA_CHECK_LAUNCH(); return; }
+#define WG_CASE(C, F_) if (cn == C && fn == F_) { launch_pdl(wgrad_kernel<C, F_>, dim3(grid), dim3(256), (size_t)(0), st, tagged(a)); CUDA_CHECK_LAUNCH(); return; }
   WG_CASE(1, 1) WG_CASE(2, 2) WG_CASE(3, 3) WG_CASE(4, 4)
 #undef WG_CASE
 }
@@ -494,7 +495,7 @@ void launch_wgrad(const WgradArgs& a, cudaStream_t st) {
 // (grp, f) accumulates the (tap, c) combinations q = grp, grp + NG, ... for output channel f.
 template <int MAXQ>
 __global__ void __launch_bounds__(256) wgrad0_kernel(WgradArgs a) {
-  pdl_prologue(4);
+  pdl_prologue(4, a.tag);
   extern __shared__ float smw[];
   const int task = blockIdx.y, chunk = blockIdx.x;
   const int tid = threadIdx.x;
@@ -566,10 +567,10 @@ void launch_wgrad0(const WgradArgs& a, cudaStream_t st) {
   dim3 grid(a.nchunks, a.tasks);
   const size_t smem = (size_t)(64 * a.ncols + (64 + 2 * (a.gw + 1)) * a.kc) * sizeof(float);
   const int need = (9 * a.kc + (256 / a.ncols) - 1) / (256 / a.ncols);      // (tap, c) combinations per thread
-  if (need <= 3) launch_pdl(wgrad0_kernel<3>, dim3(grid), dim3(256), (size_t)(smem), st, a);
-  else if (need <= 6) launch_pdl(wgrad0_kernel<6>, dim3(grid), dim3(256), (size_t)(smem), st, a);
-  else if (need <= 9) launch_pdl(wgrad0_kernel<9>, dim3(grid), dim3(256), (size_t)(smem), st, a);
-  else launch_pdl(wgrad0_kernel<36>, dim3(grid), dim3(256), (size_t)(smem), st, a);
+  if (need <= 3) launch_pdl(wgrad0_kernel<3>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a));
+  else if (need <= 6) launch_pdl(wgrad0_kernel<6>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a));
+  else if (need <= 9) launch_pdl(wgrad0_kernel<9>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a));
+  else launch_pdl(wgrad0_kernel<36>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a));
   CUDA_CHECK_LAUNCH();
 }
 
@@ -577,8 +578,8 @@ void launch_wgrad0(const WgradArgs& a, cudaStream_t st) {
 // image NCHW [tasks][n][C][H][W] -> padded-grid matrix [tasks][n*G][C] (valid positions only)
 // ---------------------------------------------------------------------------------------------
 __global__ void prep_x_kernel(const float* __restrict__ x, float* __restrict__ xg, long long xg_task_stride, int n,
-                              int C, int H, int W) {
-  pdl_prologue(5);
+                              int C, int H, int W, int tag) {
+  pdl_prologue(5, tag);
   const int task = blockIdx.y;
   const long long total = (long long)n * H * W;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -597,7 +598,7 @@ void launch_prep_x(const float* x, float* xg, long long xg_task_stride, int task
   ProfScope prof_scope__(PROF_PARAM, 0.0, st);
   const long long total = (long long)n * H * W;
   dim3 grid((unsigned)((total + 255) / 256), tasks);
-  launch_pdl(prep_x_kernel, dim3(grid), dim3(256), (size_t)(0), st, x, xg, xg_task_stride, n, C, H, W);
+  launch_pdl(prep_x_kernel, dim3(grid), dim3(256), (size_t)(0), st, x, xg, xg_task_stride, n, C, H, W, launch_tag());
   CUDA_CHECK_LAUNCH();
 }
 

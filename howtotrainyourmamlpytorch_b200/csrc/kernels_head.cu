@@ -11,7 +11,7 @@
 #include "head_body.cuh"
 
 __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
-  pdl_prologue(14);
+  pdl_prologue(14, a.tag);
   extern __shared__ float smh[];
   __shared__ float s_rowloss[64];
   __shared__ float s_rowcorrect[64];
@@ -22,7 +22,7 @@ void launch_head(const HeadArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_HEAD, 0.0, st);
   const size_t smem = (size_t)5 * a.rows_per_cta * a.N * sizeof(float);
   dim3 grid((a.n + a.rows_per_cta - 1) / a.rows_per_cta, a.tasks);
-  launch_pdl(head_kernel, dim3(grid), dim3(256), (size_t)(smem), st, a);
+  launch_pdl(head_kernel, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a));
   CUDA_CHECK_LAUNCH();
 }
 

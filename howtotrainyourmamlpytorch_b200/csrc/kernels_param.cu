@@ -39,8 +39,8 @@ __device__ __forceinline__ long long internal_to_meta(const ParamLayout& pl, lon
 }
 
 __global__ void import_theta_kernel(ParamLayout pl, const float* __restrict__ meta, float* __restrict__ theta0,
-                                    long long stride, int tasks) {
-  pdl_prologue(15);
+                                    long long stride, int tasks, int tag) {
+  pdl_prologue(15, tag);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pl.P) return;
   int seg;
@@ -51,7 +51,7 @@ __global__ void import_theta_kernel(ParamLayout pl, const float* __restrict__ me
 void launch_import_theta(const ParamLayout& pl, const float* meta, float* theta0, long long stride, int tasks,
                          cudaStream_t st) {
   ProfScope prof_scope__(PROF_PARAM, 0.0, st);
-  launch_pdl(import_theta_kernel, dim3((unsigned)((pl.P + 255) / 256)), dim3(256), (size_t)(0), st, pl, meta, theta0, stride, tasks);
+  launch_pdl(import_theta_kernel, dim3((unsigned)((pl.P + 255) / 256)), dim3(256), (size_t)(0), st, pl, meta, theta0, stride, tasks, launch_tag());
   CUDA_CHECK_LAUNCH();
 }
 
@@ -70,8 +70,8 @@ __global__ void param_reduce_kernel(ParamLayout pl, PartialDesc pd, const float*
                                     const float* __restrict__ theta_in, float* __restrict__ theta_out,
                                     float* __restrict__ g_out, float* __restrict__ tbar,
                                     const float* __restrict__ meta, int step, long long task_stride, long long i_lo,
-                                    long long i_hi) {
-  pdl_prologue(16);
+                                    long long i_hi, int tag) {
+  pdl_prologue(16, tag);
   const long long i = i_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= i_hi) return;
   const int task = blockIdx.y;
@@ -102,7 +102,7 @@ void launch_param_reduce(const ParamLayout& pl, const PartialDesc& pd, const flo
   const long long i_hi = seg_hi == pl.nseg_inner ? pl.P : pl.seg_off[seg_hi];
   ProfScope prof_scope__(PROF_PARAM, 0.0, st);
   dim3 grid((unsigned)((i_hi - i_lo + 255) / 256), tasks);
-  launch_pdl(param_reduce_kernel, dim3(grid), dim3(256), (size_t)(0), st, pl, pd, partial, mode, theta_in, theta_out, g_out, tbar, meta, step, task_stride, i_lo, i_hi);
+  launch_pdl(param_reduce_kernel, dim3(grid), dim3(256), (size_t)(0), st, pl, pd, partial, mode, theta_in, theta_out, g_out, tbar, meta, step, task_stride, i_lo, i_hi, launch_tag());
   CUDA_CHECK_LAUNCH();
 }
 
@@ -111,8 +111,8 @@ void launch_param_reduce(const ParamLayout& pl, const PartialDesc& pd, const flo
 __global__ void __launch_bounds__(256) dots_u_kernel(ParamLayout pl, float* __restrict__ tbar, const float* __restrict__ tgrad,
                                                      const float* __restrict__ g, float* __restrict__ u,
                                                      double* __restrict__ abar, const float* __restrict__ meta, int step,
-                                                     long long task_stride) {
-  pdl_prologue(17);
+                                                     long long task_stride, int tag) {
+  pdl_prologue(17, tag);
   __shared__ double red[8];
   const int task = blockIdx.y;
   const long long lo = (long long)blockIdx.x * 2048, hi = min(pl.P, lo + 2048);
@@ -145,7 +145,7 @@ void launch_dots_u(const ParamLayout& pl, float* tbar, const float* tgrad, const
                    const float* meta, int step, long long task_stride, int tasks, cudaStream_t st) {
   ProfScope prof_scope__(PROF_PARAM, 0.0, st);
   dim3 grid((unsigned)((pl.P + 2047) / 2048), tasks);
-  launch_pdl(dots_u_kernel, dim3(grid), dim3(256), (size_t)(0), st, pl, tbar, tgrad, g, u, abar, meta, step, task_stride);
+  launch_pdl(dots_u_kernel, dim3(grid), dim3(256), (size_t)(0), st, pl, tbar, tgrad, g, u, abar, meta, step, task_stride, launch_tag());
   CUDA_CHECK_LAUNCH();
 }
 
@@ -158,7 +158,7 @@ __device__ __forceinline__ const double* stat_ptr(const ExportArgs& a, int task,
 }
 
 __global__ void export_kernel(ExportArgs a) {
-  pdl_prologue(18);
+  pdl_prologue(18, a.tag);
   const ParamLayout& pl = a.pl;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long LSF = (long long)pl.L * pl.S * pl.F;
@@ -272,7 +272,7 @@ __global__ void export_kernel(ExportArgs a) {
 void launch_export(const ExportArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_PARAM, 0.0, st);
   const long long total = a.pl.meta_size + 2 + (a.pl.per_step_bn ? 2LL * a.pl.L * a.pl.S * a.pl.F : 0);
-  launch_pdl(export_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st, a);
+  launch_pdl(export_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st, tagged(a));
   CUDA_CHECK_LAUNCH();
 }
 
@@ -283,8 +283,8 @@ struct SegEnds { long long e[32]; int n; };
 
 __global__ void adam_kernel(float* __restrict__ meta, const float* __restrict__ grad, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float bc1, float bc2, SegEnds se,
-                            unsigned trainable_mask, unsigned clamp_mask) {
-  pdl_prologue(19);
+                            unsigned trainable_mask, unsigned clamp_mask, int tag) {
+  pdl_prologue(19, tag);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int seg = 0;
@@ -309,13 +309,13 @@ void launch_adam(float* meta, const float* grad, float* m, float* v, long long n
   SegEnds se;
   se.n = nseg - 1;
   for (int k = 0; k < nseg - 1 && k < 32; ++k) se.e[k] = seg_end_host[k];
-  launch_pdl(adam_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), st, meta, grad, m, v, n, lr, bc1, bc2, se, trainable_mask, clamp_mask);
+  launch_pdl(adam_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), st, meta, grad, m, v, n, lr, bc1, bc2, se, trainable_mask, clamp_mask, launch_tag());
   CUDA_CHECK_LAUNCH();
 }
 
 __global__ void running_update_kernel(const float* __restrict__ pm, const float* __restrict__ pv, float* __restrict__ rm,
-                                      float* __restrict__ rv, const float* __restrict__ decay, int L, int S, int F) {
-  pdl_prologue(20);
+                                      float* __restrict__ rv, const float* __restrict__ decay, int L, int S, int F, int tag) {
+  pdl_prologue(20, tag);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= L * S * F) return;
   const int s = (i / F) % S;
@@ -328,7 +328,7 @@ void launch_running_update(const float* part_mean, const float* part_var, float*
                            int L, int S, int F, cudaStream_t st) {
   ProfScope prof_scope__(PROF_PARAM, 0.0, st);
   const int n = L * S * F;
-  launch_pdl(running_update_kernel, dim3((n + 255) / 256), dim3(256), (size_t)(0), st, part_mean, part_var, rm, rv, decay_dev, L, S, F);
+  launch_pdl(running_update_kernel, dim3((n + 255) / 256), dim3(256), (size_t)(0), st, part_mean, part_var, rm, rv, decay_dev, L, S, F, launch_tag());
   CUDA_CHECK_LAUNCH();
 }
 

@@ -158,7 +158,7 @@ __device__ long long g_tc_timeline[16];
 template <int NCOLS>
 __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcConvArgs a) {
   pdl_trigger();
-  trace_mark(22);
+  trace_mark(22, a.tag);
   constexpr int B_BYTES = NCOLS * 128;
   constexpr int BSTAGE = 2 * B_BYTES;            // B_hi + B_lo of one (tap, k-chunk)
   constexpr int NACC = 5;                        // 4 x hi*hi (round-robin over k-steps) + 1 x (lo*hi + hi*lo)
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
   }
-  trace_mark(22 | 0x80);     // end of CTA (0,0,0)
+  trace_mark(22 | 0x80, a.tag);     // end of CTA (0,0,0)
 }
 
 }  // namespace
@@ -490,7 +490,7 @@ static void launch_conv_tc_n(const TcMaps& maps, const TcConvArgs& a, size_t sme
   }
   dim3 grid((a.rows + 127) / 128, a.tasks, S);
   if (S == 1) {
-    launch_pdl(conv_tc_kernel<NCOLS>, grid, dim3(224), smem, st, maps, a);
+    launch_pdl(conv_tc_kernel<NCOLS>, grid, dim3(224), smem, st, maps, tagged(a));
     return;
   }
   cudaLaunchConfig_t cfg{};
@@ -499,7 +499,7 @@ static void launch_conv_tc_n(const TcMaps& maps, const TcConvArgs& a, size_t sme
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = S;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, conv_tc_kernel<NCOLS>, maps, a);
+  cudaLaunchKernelEx(&cfg, conv_tc_kernel<NCOLS>, maps, tagged(a));
 }
 
 void tc_conv_set_split(int max_split) { g_tc_split_max = max_split < 1 ? 1 : (max_split > 8 ? 8 : max_split); }
@@ -526,8 +526,8 @@ __device__ __forceinline__ float tf32_rna(float x) {
 }
 
 __global__ void pack_weights_kernel(ParamLayout pl, const float* __restrict__ theta, long long theta_task_stride,
-                                    float* __restrict__ pack, long long pack_task_stride, long long plane_stride) {
-  pdl_prologue(21);
+                                    float* __restrict__ pack, long long pack_task_stride, long long plane_stride, int tag) {
+  pdl_prologue(21, tag);
   const int task = blockIdx.y;
   const long long per_layer = 9LL * pl.F * pl.F;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -553,7 +553,7 @@ void launch_pack_weights(const ParamLayout& pl, const float* theta, long long th
   const long long n = 9LL * pl.F * pl.F * (pl.L - 1);
   if (n <= 0) return;
   dim3 grid((unsigned)((n + 255) / 256), tasks);
-  launch_pdl(pack_weights_kernel, dim3(grid), dim3(256), (size_t)(0), st, pl, theta, theta_task_stride, pack, pack_task_stride, plane_stride);
+  launch_pdl(pack_weights_kernel, dim3(grid), dim3(256), (size_t)(0), st, pl, theta, theta_task_stride, pack, pack_task_stride, plane_stride, launch_tag());
   CUDA_CHECK_LAUNCH();
 }
 

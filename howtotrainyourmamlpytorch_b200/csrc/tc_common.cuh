@@ -20,6 +20,7 @@ struct TcConvArgs {
   const float* zh; long long zh_stride;
   double* stats; long long stats_stride;
   double alg_flops;
+  int tag;          // launch sequence number inside the iteration (device trace)
 };
 
 int tc_conv_rpad(int gw);

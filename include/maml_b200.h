@@ -146,8 +146,8 @@ int maml_b200_profile(maml_b200_handle* h, int32_t enable);
 int maml_b200_profile_read(maml_b200_handle* h, double* ms_by_cat, double* flops_by_cat,
                            int64_t* launches_by_cat, int32_t ncat);
 
-/* Device-side launch trace (debug): while enabled, CTA (0,0,0) of every kernel appends (globaltimer ns << 8 | kernel
- * id) to a device buffer -- the start-time sequence of the kernels of the following calls, also inside a replayed CUDA
+/* Device-side launch trace (debug): while enabled, CTA (0,0,0) of every kernel appends (globaltimer ns << 20 | launch
+ * tag << 8 | kernel id; tag = launch sequence number inside the iteration = kernel-node order of the captured graph) to a device buffer -- the start-time sequence of the kernels of the following calls, also inside a replayed CUDA
  * graph.  trace_read synchronises, copies at most `capacity` entries (start order), clears, and returns the count.
  * Kernel ids: scripts/trace_kernel_ids.json. */
 int maml_b200_trace(maml_b200_handle* h, int32_t enable);

@@ -36,15 +36,15 @@ def main():
     eng.trace(False)
     t0 = tr[0][0]
     rows = []
-    for i, (t, k) in enumerate(tr):
+    for i, (t, k, tag) in enumerate(tr):
         nm = names.get(k & 0x7f, str(k)) + (":end" if k & 0x80 else "")
         nxt = tr[i + 1][0] - t if i + 1 < len(tr) else 0
-        rows.append((t - t0, nm, nxt))
+        rows.append((t - t0, nm, nxt, tag))
     if "--full" in sys.argv:
-        for off, nm, nxt in rows:
-            print("%9.2f us  %-22s +%.2f" % (off / 1e3, nm, nxt / 1e3))
+        for off, nm, nxt, tag in rows:
+            print("%9.2f us  %-22s +%.2f  #%d" % (off / 1e3, nm, nxt / 1e3, tag))
     agg = collections.OrderedDict()
-    for off, nm, nxt in rows:
+    for off, nm, nxt, tag in rows:
         c, s = agg.get(nm, (0, 0.0))
         agg[nm] = (c + 1, s + nxt / 1e3)
     total = (tr[-1][0] - t0) / 1e3
@@ -54,7 +54,7 @@ def main():
     # conv_tc CTA-0 durations
     durs = []
     open_t = None
-    for t, k in tr:
+    for t, k, tag in tr:
         if k == 22:
             open_t = t
         elif k == (22 | 0x80) and open_t is not None:

@@ -425,6 +425,7 @@ def test_device_trace(cuda_device):
     m.meta_gradient(batch, epoch)
     tr = eng.trace_read()
     eng.trace(False)
-    starts = [t for t, k in tr if not (k & 0x80)]
+    starts = [t for t, k, tag in tr if not (k & 0x80)]
     assert len(starts) == eng.last_launch_count()
+    assert sorted(tag for t, k, tag in tr if not (k & 0x80)) == list(range(len(starts)))     # one entry per graph node
     assert max(starts) - min(starts) < 1e9           # nanoseconds: one tiny iteration spans far less than a second
