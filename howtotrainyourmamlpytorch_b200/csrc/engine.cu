@@ -177,9 +177,11 @@ static void plan_chunks(maml_b200_handle* h, int n, ChunkPlan* cp) {
     if (l == 0) {
       nch = (int)std::min<long long>(512, std::max<long long>(1, (rows + 63) / 64));
     } else {
-      // one full wave: wgrad_row_kernel<4,4> keeps 2 CTAs per SM resident (105 registers x 256 threads), so 3 filter rows x tasks x
+      // ONE wgrad CTA per SM (wgrad_row_kernel<4,4>: 105 registers x 256 threads; its 48 independent accumulators per thread keep
+      // the FMA pipe fed with 8 warps): a second CTA per SM would take the register file away from the main chain's kernels
+      // running beside it (measured 3.057 -> 3.038 ms per iteration); 3 filter rows x tasks x
       // chunks should just fill 148 x 4 slots -- 720 CTAs (128-row chunks at 8 tasks) ran as 1.2 waves = 2x the time
-      static const int wg_slots = getenv("MAML_B200_WG_SLOTS") ? atoi(getenv("MAML_B200_WG_SLOTS")) : 148 * 2;
+      static const int wg_slots = getenv("MAML_B200_WG_SLOTS") ? atoi(getenv("MAML_B200_WG_SLOTS")) : 148;
       static const int wg_per_chunk = (getenv("MAML_B200_WGRAD_ROW") && atoi(getenv("MAML_B200_WGRAD_ROW")) == 0) ? 9 : 3;
       long long want = std::max<long long>(1, wg_slots / ((long long)wg_per_chunk * h->maxT));
       nch = (int)std::min<long long>(std::min<long long>(64, want), std::max<long long>(1, (rows + 15) / 16));
