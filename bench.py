@@ -33,6 +33,7 @@ if ROOT not in sys.path:
 
 METRIC = "meta-tasks/sec (5-way, 5 inner steps, second order)"
 DEFAULT_CONFIG = "omniglot_mamlpp_5w1s"          # BASELINE.json configs[1]: the 1xB200 headline workload
+SCALING = {}                                      # config -> "weak" / "strong" (filled by main from the CLI)
 
 
 def workload_desc(name, args, n_gpus):
@@ -205,26 +206,210 @@ def torch_gpu_port_tasks_per_sec(args, dev, iters=3, warmup=1):
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
 
 
+def _visible_gpu_token(local_rank):
+    """What CUDA_VISIBLE_DEVICES must be for a child process to see exactly this rank's GPU."""
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        toks = [t.strip() for t in vis.split(",") if t.strip()]
+        if local_rank < len(toks):
+            return toks[local_rank]
+    return str(local_rank)
+
+
+def run_unmodified_reference(config, batch_size, device, steps, warmup, local_rank=0, tune=True, max_seconds=240.0):
+    """Run ``baseline/run_reference.py`` (the UNMODIFIED reference staged under baseline/_ref, its own public API and
+    stock code path) in a child process and return its JSON dict, or {"unavailable": why}."""
+    script = os.path.join(ROOT, "baseline", "run_reference.py")
+    cmd = [sys.executable, script, "--config", config, "--device", device, "--steps", str(steps), "--warmup", str(warmup),
+           "--max-seconds", str(max_seconds)]
+    if batch_size:
+        cmd += ["--batch-size", str(batch_size)]
+    if tune and device == "cpu":
+        cmd += ["--tune-threads"]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS", "TORCHELASTIC_RUN_ID"):
+        env.pop(k, None)                    # the reference is a single-process program; torchrun pins OMP_NUM_THREADS=1
+    env["CUDA_VISIBLE_DEVICES"] = "" if device == "cpu" else _visible_gpu_token(local_rank)
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=max_seconds + 600)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": "reference run timed out"}
+    for line in reversed(r.stdout.strip().splitlines()):
+        line = line.strip()
+        if line.startswith("{"):
+            try:
+                return json.loads(line)
+            except ValueError:
+                continue
+    return {"unavailable": ("reference run failed (rc %d): %s" % (r.returncode, (r.stderr or r.stdout)[-300:])).replace("\n", " | ")}
+
+
+def reference_cpu_baseline(cli, args, steps, warmup):
+    """cpu_baseline dict (+ raw run) from the unmodified reference on the host cores; falls back to the oracle port
+    (stated in ``kind``) only when baseline/_ref was not staged."""
+    ref = run_unmodified_reference(cli.config, int(args.batch_size), "cpu", steps, warmup)
+    if "unavailable" not in ref:
+        sample = "%d timed iterations of %d tasks (median), %d warm-up, %d of %d host threads (1 probe iteration each at 8/16/32/64/all, fastest kept)" % (
+            len(ref["times_s"]), ref["batch_size"], ref["warmup"], ref["threads"], ref["host_threads"])
+        return {"value": ref["tasks_per_sec"], "unit": "tasks/s", "cores": ref["threads"], "kind": "reference",
+                "sample": sample, "cpu_model": ref["cpu_model"], "host_threads": ref["host_threads"],
+                "reference_commit": ref.get("commit"), "ms_per_step": ref["ms_per_iter"],
+                "thread_probe_s": ref.get("thread_probe_s")}, ref
+    tps, cores, sample, times = cpu_port_tasks_per_sec(args, iters=min(steps, 8), warmup=min(warmup, 2))
+    return {"value": tps, "unit": "tasks/s", "cores": cores, "kind": "port",
+            "sample": sample + " -- FALLBACK: " + ref["unavailable"], "ms_per_step": 1e3 * sorted(times)[len(times) // 2]}, ref
+
+
 def run_reference_arm(cli, args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (oracle port) on the host cores."""
+    """--impl reference: the reference's own CPU implementation of the path (unmodified, baseline/_ref) on the host
+    cores, same config / metric / unit; rank 0 only."""
     if rank != 0:
         return
-    steps = max(1, cli.steps)
+    steps = max(1, min(cli.steps, 20))
     warm = max(1, min(cli.warmup, 2))
-    # bounded: one step = one meta-batch on the CPU (about 1 s for the Omniglot workload); cap the total work
-    t_probe0 = time.perf_counter()
-    tps, cores, sample, times = cpu_port_tasks_per_sec(args, iters=min(steps, 20), warmup=warm)
+    t0 = time.perf_counter()
+    cb, raw = reference_cpu_baseline(cli, args, steps, warm)
+    n_timed = len(raw["times_s"]) if "times_s" in raw else steps
     line = {
-        "impl": "reference", "metric": METRIC, "value": tps, "unit": "tasks/s", "n_gpus": world, "steps": len(times),
-        "warmup": warm, "ms_per_step": 1e3 * sorted(times)[len(times) // 2], "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "tasks/s", "n_gpus": world, "steps": n_timed,
+        "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": SCALING.get(cli.config, "weak"),
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": workload_desc(cli.config, args, 1),
-        "cpu_baseline": {"value": tps, "unit": "tasks/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": tps, "unit": "tasks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "tasks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference = PyTorch eager CPU path restated call for call (oracle/maml_oracle.py autograd_train_iter); "
-                "the Python reference itself cannot travel to the GPU box; wall %.1f s" % (time.perf_counter() - t_probe0),
+        "note": "reference = the unmodified reference's run_train_iter (few_shot_learning_system.py:338-369) imported from "
+                "baseline/_ref with CUDA_VISIBLE_DEVICES='' (BASELINE.md section 4); one step = one meta-batch of %d tasks; "
+                "wall %.1f s" % (int(args.batch_size), time.perf_counter() - t0),
     }
     print(json.dumps(line), flush=True)
+
+
+def _stats(xs):
+    xs = sorted(xs)
+    return {"min": xs[0], "median": xs[len(xs) // 2], "max": xs[-1]}
+
+
+def measure_device_loop(model, args, dev, rank, world, K, W, flush, n_pool=8, sampler=None, sync_each_step=False):
+    """`value` leg: K steps with the episode tensors resident in HBM, no host sync inside the loop, L2 flushed between
+    steps (outside the per-step CUDA-event pair).  Returns per-rank timing; the caller takes the max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from howtotrainyourmamlpytorch_b200 import synthetic_batch
+    host_batches = [synthetic_batch(args, iteration=1000 * rank + i) for i in range(n_pool)]
+    dev_batches = [(hb[0].to(dev), hb[1].to(dev), hb[2].long().to(dev), hb[3].long().to(dev)) for hb in host_batches]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step(i):
+        model._current_lr = model._cosine_lr(0)
+        return model._run(dev_batches[i % n_pool], 0, training_phase=True, apply_update=True)
+
+    for i in range(max(W, 4)):      # warm-up: >= W steps, and both staging slots (one CUDA graph per slot) captured
+        device_step(i)
+    barrier()
+    if sampler is not None:
+        sampler.start()
+        time.sleep(0.3)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    loop0, loop1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    wall0 = time.perf_counter()
+    loop0.record()
+    for i in range(K):
+        if flush is not None:
+            flush.zero_()
+        ev[i][0].record()
+        device_step(W + i)
+        ev[i][1].record()
+        if sync_each_step:
+            torch.cuda.synchronize()
+    loop1.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    return {"step_ms": step_ms, "sum_ms": sum(step_ms), "loop_ms": loop0.elapsed_time(loop1), "wall_s": wall,
+            "host_batches": host_batches, "device_step": device_step, "barrier": barrier}
+
+
+def gather_rank_stats(step_ms, loop_ms, coll_us, dev, world):
+    """[per rank: min / median / max step ms, loop ms, median collective us] on every rank (tiny all_gather)."""
+    import torch
+    import torch.distributed as dist
+    st = _stats(step_ms)
+    t = torch.tensor([st["min"], st["median"], st["max"], loop_ms, coll_us], dtype=torch.float64, device=dev)
+    if world == 1:
+        return [t.tolist()]
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [o.tolist() for o in out]
+
+
+def roofline_from_profile(prof, prof_steps, peaks, peak_src, value, fpt, world, traffic):
+    conv_ms, conv_fl, conv_n = prof["conv_igemm"]
+    wg_ms, wg_fl, wg_n = prof["wgrad"]
+    c0_ms, c0_fl, c0_n = prof["conv_first_block"]
+    w0_ms, w0_fl, w0_n = prof["wgrad_first_block"]
+    tot_prof_ms = sum(v[0] for v in prof.values())
+    # dominant kernel class = every 3x3 conv contraction of blocks >= 1 (forward / tangent / dgrad implicit GEMMs + wgrad)
+    dom_ms, dom_fl, dom_n = conv_ms + wg_ms, conv_fl + wg_fl, conv_n + wg_n
+    tf32_peak = peaks["bf16_tflops"] / 2.0            # dense TF32 = half of dense bf16 (measured burst)
+    peak_3x = tf32_peak / 3.0                         # fp32-faithful 3xTF32 operand split
+    achieved = dom_fl / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    all_ms, all_fl = dom_ms + c0_ms + w0_ms, dom_fl + c0_fl + w0_fl
+    return {
+        "bound": "tensor", "kernel": "3x3 conv contractions of blocks >= 1: conv_tc_kernel (tcgen05, 3xTF32, cluster split-K) + wgrad kernels",
+        "achieved": achieved, "peak": peak_3x, "unit": "TFLOP/s", "frac": achieved / peak_3x,
+        "traffic": traffic,
+        "peak_source": peak_src + ": bf16_tflops %.1f / 2 (tf32) / 3 (3xTF32 split)" % peaks["bf16_tflops"],
+        "launches_profiled": int(dom_n), "mean_launch_us": 1e3 * dom_ms / max(dom_n, 1),
+        "share_of_step": dom_ms / tot_prof_ms if tot_prof_ms > 0 else None,
+        "all_convs_incl_first_block": {"achieved": all_fl / (all_ms * 1e-3) / 1e12 if all_ms > 0 else 0.0,
+                                       "share_of_step": all_ms / tot_prof_ms if tot_prof_ms > 0 else None},
+        "whole_iteration": {"alg_tflops": value * fpt / 1e12, "frac_of_peak": value * fpt / 1e12 / (peak_3x * world)},
+        "by_class_ms_per_step": {k: v[0] / prof_steps for k, v in prof.items()},
+        "by_class_tflops": {k: (v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 and v[1] > 0 else None) for k, v in prof.items()},
+    }
+
+
+def profile_classes(model, device_step, steps=3):
+    eng = model._engine
+    eng.profile(True)
+    for i in range(steps):
+        device_step(i)
+    prof = eng.profile_read()
+    eng.profile(False)
+    return prof
+
+
+def extra_config_line(name, tasks_per_gpu, scaling, dev, rank, world, local_rank, flush, peaks, peak_src, K=6, W=3):
+    """Short measurement of another BASELINE configuration (value + roofline by kernel class), same method as the
+    headline's `value` leg."""
+    import torch
+    from howtotrainyourmamlpytorch_b200 import MAMLFewShotClassifier, make_args
+    args = make_args(name, batch_size=tasks_per_gpu)
+    model = MAMLFewShotClassifier(im_shape=(2, args.image_channels, args.image_height, args.image_width), device=dev, args=args)
+    r = measure_device_loop(model, args, dev, rank, world, K, W, flush, n_pool=2)
+    t = torch.tensor([r["sum_ms"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t[0])
+    prof = profile_classes(model, r["device_step"], steps=2)
+    value = tasks_per_gpu * world * K / (total_ms * 1e-3)
+    fpt = flops_per_task(args)
+    roof = roofline_from_profile(prof, 2, peaks, peak_src, value, fpt, world, None)
+    out = {"config": name, "tasks_per_gpu": tasks_per_gpu, "global_meta_batch": tasks_per_gpu * world, "scaling": scaling,
+           "value": value, "unit": "tasks/s", "ms_per_step": total_ms / K, "steps": K, "warmup": W,
+           "gflop_per_task": fpt / 1e9, "alg_tflops": value * fpt / 1e12,
+           "frac_of_3xtf32_peak": value * fpt / 1e12 / (roof["peak"] * world),
+           "conv_class_tflops": roof["achieved"], "conv_class_frac": roof["frac"],
+           "by_class_ms_per_step": roof["by_class_ms_per_step"], "workspace_mib": model._engine.workspace_bytes / 2 ** 20}
+    del model
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -235,7 +420,10 @@ def main():
     ap.add_argument("--config", type=str, default=DEFAULT_CONFIG)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short lines for the other BASELINE configurations")
     ap.add_argument("--batch-size", type=int, default=None, help="tasks per GPU (default: the config's batch_size)")
+    ap.add_argument("--scaling", type=str, default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU holds the config's meta-batch; strong: the config's meta-batch is split over the GPUs")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic: do not flush L2 between timed steps")
     ap.add_argument("--sync-each-step", action="store_true", help="diagnostic: synchronize after every timed step")
     cli = ap.parse_args()
@@ -250,13 +438,18 @@ def main():
     if cli.batch_size:
         over["batch_size"] = cli.batch_size
     args = make_args(cli.config, **over)
+    if cli.scaling == "strong" and world > 1:
+        if int(args.batch_size) % world:
+            raise SystemExit("strong scaling needs the meta-batch (%d) to be a multiple of the GPU count" % int(args.batch_size))
+        args = make_args(cli.config, batch_size=int(args.batch_size) // world)
+    SCALING[cli.config] = cli.scaling
 
     if cli.impl == "reference":
-        run_reference_arm(cli, args, rank, world)
+        run_reference_arm(cli, make_args(cli.config, **over), rank, world)
         return
 
     import torch.distributed as dist
-    from howtotrainyourmamlpytorch_b200 import MAMLFewShotClassifier, synthetic_batch, _native
+    from howtotrainyourmamlpytorch_b200 import MAMLFewShotClassifier
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
     torch.cuda.set_device(local_rank)
@@ -268,46 +461,16 @@ def main():
 
     model = MAMLFewShotClassifier(im_shape=(2, args.image_channels, args.image_height, args.image_width), device=dev, args=args)
     B = int(args.batch_size)
-    n_pool = 8
-    host_batches = [synthetic_batch(args, iteration=1000 * rank + i) for i in range(n_pool)]
-    dev_batches = [(hb[0].to(dev), hb[1].to(dev), hb[2].long().to(dev), hb[3].long().to(dev)) for hb in host_batches]
+    flush = None if cli.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    # ---------------- device-resident throughput (value); clocks sampled on rank 0 only (8 nvidia-smi pollers perturb)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    r = measure_device_loop(model, args, dev, rank, world, K, W, flush, sampler=sampler, sync_each_step=cli.sync_each_step)
+    step_ms, device_step, barrier = r["step_ms"], r["device_step"], r["barrier"]
+    host_batches = r["host_batches"]
+    n_pool = len(host_batches)
     pinned_batches = [tuple(t.pin_memory() for t in hb) for hb in host_batches]
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def device_step(i):
-        # inputs already resident in HBM; no host sync inside
-        model._current_lr = model._cosine_lr(0)
-        return model._run(dev_batches[i % n_pool], 0, training_phase=True, apply_update=True)
-
-    # ---------------- device-resident throughput (value)
-    # warm-up: at least W steps and at least one pass over every distinct episode batch (the engine captures one
-    # CUDA graph per distinct set of buffer addresses; captures belong to warm-up, not to the timed region)
-    for i in range(max(W, n_pool)):
-        device_step(i)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    wall0 = time.perf_counter()
-    for i in range(K):
-        if not cli.no_flush:
-            flush.zero_()
-        ev[i][0].record()
-        device_step(W + i)
-        ev[i][1].record()
-        if cli.sync_each_step:
-            torch.cuda.synchronize()
-    barrier()
-    wall_dev = time.perf_counter() - wall0
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = sum(step_ms)
-    launches_per_step = model._engine.last_launch_count() + 1 + (1 if args.per_step_bn_statistics else 0)
+    launches_per_step = model._engine.last_launch_count() + 1 + (1 if args.per_step_bn_statistics else 0) + model.collective_launches()
 
     # ---------------- end to end through the public API with host buffers (e2e)
     for i in range(max(3, W)):
@@ -318,59 +481,69 @@ def main():
         losses, preds = model.run_train_iter(pinned_batches[(W + i) % n_pool], 0)
     barrier()
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler is not None else None
     h2d = sum(t.numel() * (8 if j >= 2 else 4) for j, t in enumerate(host_batches[0]))   # images fp32, labels int64 on the device
     n_t = args.num_classes_per_set * args.num_target_samples
     d2h = 2 * 4 + B * n_t * args.num_classes_per_set * 4
 
+    # ---------------- the collective alone (N > 1): CUDA events around the in-engine all-reduce of the result vector
+    coll_us = 0.0
+    if world > 1:
+        coll_us = model.time_collective(iters=20)
+
     # ---------------- roofline leg: per-launch CUDA events by kernel class (separate, un-timed pass)
-    eng = model._engine
-    eng.profile(True)
     prof_steps = 3
-    for i in range(prof_steps):
-        device_step(i)
-    prof = eng.profile_read()
-    eng.profile(False)
+    prof = profile_classes(model, device_step, prof_steps)
+    eng = model._engine
 
     # max over ranks
-    t_dev = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t_dev = torch.tensor([r["sum_ms"], e2e_s * 1e3, r["loop_ms"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t_dev[0]), float(t_dev[1])
+    total_ms, e2e_ms, loop_ms = float(t_dev[0]), float(t_dev[1]), float(t_dev[2])
+    per_rank = gather_rank_stats(step_ms, r["loop_ms"], coll_us, dev, world)
+
+    peaks, peak_src = measured_peaks()
+    extras = []
+    if not cli.no_extras and cli.config == DEFAULT_CONFIG and not cli.batch_size:
+        # the other BASELINE configurations, each sharded the way SURVEY.md section 8e prescribes for this GPU count
+        plan = []
+        if world == 1:
+            plan = [("omniglot_maml_5w1s", 8, "single"), ("mini_imagenet_mamlpp_5w1s", 2, "single"),
+                    ("mini_imagenet_mamlpp_5w5s", 2, "per-GPU shard of B=16 over 8 GPUs"),
+                    ("omniglot_mamlpp_20w5s", 8, "per-GPU shard of B=64 over 8 GPUs")]
+        else:
+            if 8 % world == 0:
+                plan.append(("omniglot_mamlpp_5w1s", 8 // world, "strong (B=8 split over %d GPUs)" % world))
+            if world == 2:
+                plan.append(("mini_imagenet_mamlpp_5w1s", 1, "strong (B=2 split over 2 GPUs)"))
+            plan.append(("mini_imagenet_mamlpp_5w5s", 2, "B=%d, 2 tasks per GPU%s" % (2 * world, " (= BASELINE configs[3])" if world == 8 else "")))
+            plan.append(("omniglot_mamlpp_20w5s", 8, "B=%d, 8 tasks per GPU%s" % (8 * world, " (= BASELINE configs[4])" if world == 8 else "")))
+        for name, tpg, how in plan:
+            try:
+                extras.append(extra_config_line(name, tpg, how, dev, rank, world, local_rank, flush, peaks, peak_src))
+            except Exception as exc:                   # an extra must never take the headline down
+                extras.append({"config": name, "tasks_per_gpu": tpg, "error": repr(exc)[:300]})
 
     if rank == 0:
-        peaks, peak_src = measured_peaks()
         tasks_total = B * world * K
         value = tasks_total / (total_ms * 1e-3)
         e2e_value = tasks_total / (e2e_ms * 1e-3)
         fpt = flops_per_task(args)
-        conv_ms, conv_fl, conv_n = prof["conv_igemm"]
-        wg_ms, wg_fl, wg_n = prof["wgrad"]
-        tot_prof_ms = sum(v[0] for v in prof.values())
-        # dominant kernel class = the implicit-GEMM convolutions (forward / tangent / dgrad) + wgrad
-        dom_ms, dom_fl, dom_n = conv_ms + wg_ms, conv_fl + wg_fl, conv_n + wg_n
-        tf32_peak = peaks["bf16_tflops"] / 2.0            # dense TF32 = half of dense bf16 (measured burst)
-        peak_3x = tf32_peak / 3.0                         # fp32-faithful 3xTF32 operand split
-        achieved = dom_fl / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r1.json")))["dominant_kernel_traffic_bytes_per_launch"]
-        except Exception:
-            pass
-        roofline = {
-            "bound": "tensor", "kernel": "3x3 implicit-GEMM conv: conv_tc_kernel (tcgen05, 3xTF32, cluster split-K) + wgrad_row_kernel (FFMA)",
-            "achieved": achieved, "peak": peak_3x, "unit": "TFLOP/s", "frac": achieved / peak_3x,
-            "traffic": traffic,
-            "traffic_note": "dram__bytes_read+write of one block-1 conv_tc_kernel launch, grid (10,8,1) (ncu --set full, cold cache; profiles/ncu_summary_r1.json)",
-            "peak_source": peak_src + ": bf16_tflops %.1f / 2 (tf32) / 3 (3xTF32 split)" % peaks["bf16_tflops"],
-            "launches_profiled": int(dom_n), "mean_launch_us": 1e3 * dom_ms / max(dom_n, 1),
-            "share_of_step": dom_ms / tot_prof_ms if tot_prof_ms > 0 else None,
-            "whole_iteration": {"alg_tflops": value * fpt / 1e12, "frac_of_peak": value * fpt / 1e12 / (peak_3x * world)},
-            "by_class_ms_per_step": {k: v[0] / prof_steps for k, v in prof.items()},
-        }
+        traffic, traffic_note = None, None
+        for cand in ("ncu_summary_r2.json", "ncu_summary_r1.json"):
+            try:
+                d = json.load(open(os.path.join(ROOT, "profiles", cand)))
+                traffic = d["dominant_kernel_traffic_bytes_per_launch"]
+                traffic_note = d.get("traffic_note", "dram__bytes_read+write of one dominant-kernel launch (ncu --set full, cold cache; profiles/%s)" % cand)
+                break
+            except Exception:
+                continue
+        roofline = roofline_from_profile(prof, prof_steps, peaks, peak_src, value, fpt, world, traffic)
+        roofline["traffic_note"] = traffic_note
         line = {
             "metric": METRIC, "value": value, "unit": "tasks/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": cli.scaling, "vs_baseline": None,
             "dtype": "fp32", "data": "synthetic", "config": workload_desc(cli.config, args, world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "tasks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -378,18 +551,32 @@ def main():
             "gpu_launches": int(launches_per_step * K),
             "roofline": roofline,
             "gflop_per_task": fpt / 1e9,
-            "wall_s_device_loop": wall_dev,
-            "step_ms": {"min": min(step_ms), "median": sorted(step_ms)[len(step_ms) // 2], "max": max(step_ms)},
+            "wall_s_device_loop": r["wall_s"],
+            "loop_ms_per_step_incl_flush": loop_ms / K,
+            "step_ms": _stats(step_ms),
+            "per_rank": {"columns": ["step_ms_min", "step_ms_median", "step_ms_max", "loop_ms", "collective_us"], "rows": per_rank},
+            "collective": model.collective_desc(),
             "workspace_mib": eng.workspace_bytes / 2 ** 20,
             "last_loss": float(losses["loss"]),
+            "other_configs": extras,
         }
         if not cli.no_cpu_baseline and world == 1:
-            try:
-                line["torch_gpu_baseline"] = torch_gpu_port_tasks_per_sec(args, dev)
-            except Exception as exc:      # a baseline must never take the measurement down
-                line["torch_gpu_baseline"] = {"unavailable": repr(exc)[:200]}
-            tps, cores, sample, _ = cpu_port_tasks_per_sec(args, iters=8, warmup=2)
-            line["cpu_baseline"] = {"value": tps, "unit": "tasks/s", "cores": cores, "kind": "port", "sample": sample}
+            # the reference's own GPU path (it self-selects CUDA, few_shot_learning_system.py:73-81): the library-kernel
+            # baseline on the same B200; then its CPU path on the host cores (bounded sample)
+            g = run_unmodified_reference(cli.config, B, "cuda", steps=3, warmup=2, local_rank=local_rank)
+            if "unavailable" in g:
+                try:
+                    line["torch_gpu_baseline"] = torch_gpu_port_tasks_per_sec(args, dev)
+                    line["torch_gpu_baseline"]["fallback_reason"] = g["unavailable"]
+                except Exception as exc:      # a baseline must never take the measurement down
+                    line["torch_gpu_baseline"] = {"unavailable": repr(exc)[:200]}
+            else:
+                line["torch_gpu_baseline"] = {
+                    "value": g["tasks_per_sec"], "unit": "tasks/s", "ms_per_step": g["ms_per_iter"],
+                    "kind": "reference (unmodified, baseline/_ref) on its own GPU path: eager PyTorch cuDNN / ATen, fp32, TF32 off",
+                    "sample": "%d timed iterations of %d tasks (median), %d warm-up" % (len(g["times_s"]), g["batch_size"], g["warmup"]),
+                    "gpu": g.get("gpu")}
+            line["cpu_baseline"], _ = reference_cpu_baseline(cli, args, steps=8, warmup=2)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

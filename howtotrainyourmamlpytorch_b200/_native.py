@@ -21,6 +21,8 @@ EXPORTED_SYMBOLS = [
     "maml_b200_running_stats_update", "maml_b200_debug_read", "maml_b200_last_launch_count",
     "maml_b200_profile", "maml_b200_profile_read", "maml_b200_net_forward",
     "maml_b200_trace", "maml_b200_trace_read",
+    "maml_b200_comm_init", "maml_b200_comm_connect", "maml_b200_comm_world", "maml_b200_all_reduce",
+    "maml_b200_comm_status",
 ]
 PROF_CATS = ["conv_igemm", "conv_first_block", "wgrad", "wgrad_first_block", "bn_act_pool", "head", "param"]
 
@@ -92,6 +94,16 @@ def load_library():
     lib.maml_b200_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                            ctypes.POINTER(i64), i32]
     lib.maml_b200_profile_read.restype = ctypes.c_int
+    lib.maml_b200_comm_init.argtypes = [vp, i32, i32, vp]
+    lib.maml_b200_comm_init.restype = ctypes.c_int
+    lib.maml_b200_comm_connect.argtypes = [vp, vp]
+    lib.maml_b200_comm_connect.restype = ctypes.c_int
+    lib.maml_b200_comm_world.argtypes = [vp]
+    lib.maml_b200_comm_world.restype = ctypes.c_int
+    lib.maml_b200_all_reduce.argtypes = [vp, vp, vp]
+    lib.maml_b200_all_reduce.restype = ctypes.c_int
+    lib.maml_b200_comm_status.argtypes = [vp]
+    lib.maml_b200_comm_status.restype = i64
     if lib.maml_b200_abi_version() != ABI_VERSION:
         raise NativeLibraryError("libmaml_b200.so ABI version mismatch: rebuild the library")
     _lib = lib
@@ -179,6 +191,27 @@ class Engine(object):
         rc = self.lib.maml_b200_running_stats_update(self.h, result.data_ptr(), running_mean.data_ptr(),
                                                      running_var.data_ptr(), arr, self._stream())
         _check(self.lib, rc, "maml_b200_running_stats_update")
+
+    # ---- multi-GPU: peer-memory all-reduce of the result vector (CUDA IPC handles are exchanged by the caller)
+    def comm_init(self, rank, world):
+        """Allocate this rank's communication block; returns its 64-byte IPC handle (bytes)."""
+        buf = ctypes.create_string_buffer(64)
+        _check(self.lib, self.lib.maml_b200_comm_init(self.h, int(rank), int(world), buf), "maml_b200_comm_init")
+        return bytes(buf.raw)
+
+    def comm_connect(self, handles):
+        blob = b"".join(handles)
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        _check(self.lib, self.lib.maml_b200_comm_connect(self.h, buf), "maml_b200_comm_connect")
+
+    def comm_world(self):
+        return int(self.lib.maml_b200_comm_world(self.h))
+
+    def all_reduce(self, vec):
+        _check(self.lib, self.lib.maml_b200_all_reduce(self.h, vec.data_ptr(), self._stream()), "maml_b200_all_reduce")
+
+    def comm_status(self):
+        return int(self.lib.maml_b200_comm_status(self.h))
 
     def trace(self, enable):
         _check(self.lib, self.lib.maml_b200_trace(self.h, int(bool(enable))), "maml_b200_trace")

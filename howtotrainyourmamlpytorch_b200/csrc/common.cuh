@@ -217,7 +217,24 @@ void launch_param_reduce(const ParamLayout& pl, const PartialDesc& pd, const flo
 void launch_dots_u(const ParamLayout& pl, float* tbar, const float* tgrad, const float* g, float* u, double* abar,
                    const float* meta, int step, long long task_stride, int tasks, cudaStream_t st);
 
+// Peer-memory all-reduce of the result vector (kernels_param.cu: export_kernel publishes, allreduce_kernel sums).
+// Every rank owns one cudaMalloc'ed communication block that its peers map through CUDA IPC:
+//   [2 slots][slot_stride floats] data | flags[MAML_MAX_RANKS] | seq | counters[2]
+// Round `seq` (device-side counter, so a replayed CUDA graph needs no new parameters) uses slot seq & 1.
+#define MAML_MAX_RANKS 8
+struct CommDev {
+  int rank, world;                        // world <= 1: no collective, export writes the caller's result vector
+  float* local_data; long long slot_stride;
+  unsigned* local_flags;                  // [MAML_MAX_RANKS]: flags[p] = last round rank p has published (written BY p)
+  unsigned* seq;                          // current round (starts at 1)
+  unsigned* counters;                     // [0]: export blocks done, [1]: reduce blocks done
+  const float* peer_data[MAML_MAX_RANKS]; // peer p's data block (peer_data[rank] = local_data)
+  unsigned* peer_flags[MAML_MAX_RANKS];   // peer p's flag array
+  long long* status;                      // [0] != 0: a wait timed out (peer missing); read by the host after a sync
+};
+
 struct ExportArgs {
+  CommDev comm;
   ParamLayout pl;
   const float* tbar; long long task_stride;          // [tasks][P]
   const double* abar;                                // [tasks][nseg_inner][MAML_MAX_STEPS] (fp64 dot products)
@@ -234,6 +251,10 @@ struct ExportArgs {
   int tag;          // launch sequence number inside the iteration (device trace)
 };
 void launch_export(const ExportArgs& a, cudaStream_t st);
+// all ranks' published slots of this round -> `result` (sum in rank order: bit-identical on every rank)
+void launch_allreduce(const CommDev& c, float* result, long long n, cudaStream_t st);
+// stand-alone publish of an existing vector (timing / tests): copy into this round's slot + signal the peers
+void launch_publish(const CommDev& c, const float* src, long long n, cudaStream_t st);
 
 void launch_adam(float* meta, const float* grad, float* m, float* v, long long n, float lr, float bc1, float bc2,
                  const long long* seg_end_host, int nseg, unsigned trainable_mask, unsigned clamp_mask,

@@ -112,6 +112,11 @@ struct maml_b200_handle {
   float *pack_theta = nullptr, *pack_u = nullptr;       // [4 planes][steps][T][(L-1)*9*F*F]
   long long pack_theta_plane = 0, pack_u_plane = 0, pack_task = 0;
   CUtensorMap theta_map[4], u_map[4];                   // planes: W hi, W lo, WT hi, WT lo
+  // multi-GPU: peer-memory all-reduce of the result vector (maml_b200_comm_*)
+  CommDev comm{};                                       // world <= 1 until connected
+  char* comm_block = nullptr; long long comm_bytes = 0;
+  void* comm_opened[MAML_MAX_RANKS] = {};               // peer blocks mapped with cudaIpcOpenMemHandle
+  bool comm_connected = false;
 };
 
 extern "C" int maml_b200_abi_version(void) { return MAML_B200_ABI_VERSION; }
@@ -398,8 +403,15 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   return 0;
 }
 
+static void comm_release(maml_b200_handle* h) {
+  for (int p = 0; p < MAML_MAX_RANKS; ++p) if (h->comm_opened[p]) { cudaIpcCloseMemHandle(h->comm_opened[p]); h->comm_opened[p] = nullptr; }
+  if (h->comm_block) { cudaFree(h->comm_block); h->comm_block = nullptr; }
+  h->comm = CommDev{}; h->comm_connected = false;
+}
+
 extern "C" void maml_b200_destroy(maml_b200_handle* h) {
   if (!h) return;
+  comm_release(h);
   for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (h->s_cap) cudaStreamDestroy(h->s_cap);
   if (h->s_tgt) cudaStreamDestroy(h->s_tgt);
@@ -965,7 +977,12 @@ static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it,
   e.n_s = h->n_s; e.n_t = h->n_t;
   for (int l = 0; l < h->L; ++l) e.hw[l] = h->geo[l].h * h->geo[l].w;
   e.result = result;
+  // sharded call with a connected communicator: export publishes into the peer-visible slot and the all-reduce kernel
+  // (same stream, same captured graph) leaves the SUM over ranks in `result` -- no host round trip, no library call
+  const bool reduce = h->comm_connected && it->tasks_global > it->n_tasks;
+  if (reduce) e.comm = h->comm;
   launch_export(e, st);
+  if (reduce) launch_allreduce(h->comm, result, maml_b200_result_size(h), st);
   return 0;
 }
 
@@ -978,6 +995,7 @@ extern "C" int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200
   if (it->num_steps < 1 || it->num_steps > h->S) return fail("num_steps out of range (must be <= inner_steps)");
   if (it->tasks_global < T) return fail("tasks_global < n_tasks");
   if ((it->target_mask & ((1u << it->num_steps) - 1u)) == 0) return fail("target_mask selects no target pass");
+  if (h->comm_connected && (reinterpret_cast<uintptr_t>(result) & 15u) != 0) return fail("result must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const long long* ys = (const long long*)y_support;
   const long long* yt = (const long long*)y_target;
@@ -1084,6 +1102,86 @@ extern "C" int maml_b200_running_stats_update(maml_b200_handle* h, const float* 
                         h->L, h->S, h->F, st);
   CK(cudaGetLastError());
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// communicator: one cudaMalloc'ed block per rank, mapped by the peers through CUDA IPC
+// ---------------------------------------------------------------------------------------------
+static long long comm_slot_stride(const maml_b200_handle* h) { return rup(maml_b200_result_size(h), 64); }
+
+extern "C" int maml_b200_comm_init(maml_b200_handle* h, int32_t rank, int32_t world, void* ipc_handle_out) {
+  if (!h || !ipc_handle_out) return fail("null argument");
+  if (world < 2 || world > MAML_MAX_RANKS || rank < 0 || rank >= world) return fail("comm_init: need 2 <= world <= 8 and 0 <= rank < world");
+  comm_release(h);
+  const long long stride = comm_slot_stride(h);
+  const long long data_bytes = 2 * stride * (long long)sizeof(float);
+  h->comm_bytes = data_bytes + 256;                      // + flags[8] | seq | counters[2] | status (one 256 B line group)
+  CK(cudaMalloc((void**)&h->comm_block, (size_t)h->comm_bytes));
+  CK(cudaMemset(h->comm_block, 0, (size_t)h->comm_bytes));
+  unsigned* ctl = (unsigned*)(h->comm_block + data_bytes);
+  const unsigned one = 1u;
+  CK(cudaMemcpy(ctl + MAML_MAX_RANKS, &one, sizeof(one), cudaMemcpyHostToDevice));       // seq starts at 1 (flags start at 0)
+  CommDev& c = h->comm;
+  c.rank = rank; c.world = world;
+  c.local_data = (float*)h->comm_block; c.slot_stride = stride;
+  c.local_flags = ctl; c.seq = ctl + MAML_MAX_RANKS; c.counters = ctl + MAML_MAX_RANKS + 1;
+  c.status = (long long*)(ctl + MAML_MAX_RANKS + 4);
+  cudaIpcMemHandle_t hd;
+  CK(cudaIpcGetMemHandle(&hd, h->comm_block));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  memcpy(ipc_handle_out, &hd, sizeof(hd));
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+extern "C" int maml_b200_comm_connect(maml_b200_handle* h, const void* all_handles) {
+  if (!h || !all_handles) return fail("null argument");
+  if (!h->comm_block) return fail("comm_connect before comm_init");
+  CommDev& c = h->comm;
+  const long long data_bytes = 2 * c.slot_stride * (long long)sizeof(float);
+  for (int p = 0; p < c.world; ++p) {
+    char* base = nullptr;
+    if (p == c.rank) base = h->comm_block;
+    else {
+      cudaIpcMemHandle_t hd;
+      memcpy(&hd, (const char*)all_handles + (size_t)p * sizeof(hd), sizeof(hd));
+      void* ptr = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) { cudaGetLastError(); return fail(std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(p) + "): " + cudaGetErrorString(e)); }
+      h->comm_opened[p] = ptr;
+      base = (char*)ptr;
+    }
+    c.peer_data[p] = (const float*)base;
+    c.peer_flags[p] = (unsigned*)(base + data_bytes);
+  }
+  h->comm_connected = true;
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);    // graphs captured without the collective are stale
+  h->graphs.clear();
+  return 0;
+}
+
+extern "C" int maml_b200_comm_world(const maml_b200_handle* h) { return (h && h->comm_connected) ? h->comm.world : 1; }
+
+// Stand-alone all-reduce(SUM) of a result-sized vector, in place (publish + reduce kernels on `stream`).  The iteration
+// call does the same inside its own graph; this entry exists for timing the collective and for tests.
+extern "C" int maml_b200_all_reduce(maml_b200_handle* h, float* vec, void* stream) {
+  if (!h || !vec) return fail("null argument");
+  if (!h->comm_connected) return fail("all_reduce: communicator not connected");
+  if ((reinterpret_cast<uintptr_t>(vec) & 15u) != 0) return fail("all_reduce: vector must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_publish(h->comm, vec, maml_b200_result_size(h), st);
+  launch_allreduce(h->comm, vec, maml_b200_result_size(h), st);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// 0 = healthy; otherwise the round in which a wait for a peer timed out (| 1 << 40 | peer << 32).  Synchronises.
+extern "C" int64_t maml_b200_comm_status(maml_b200_handle* h) {
+  if (!h || !h->comm_block) return 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  long long v = 0;
+  cudaMemcpy(&v, h->comm.status, sizeof(v), cudaMemcpyDeviceToHost);
+  return (int64_t)v;
 }
 
 extern "C" int maml_b200_profile(maml_b200_handle* h, int32_t enable) {

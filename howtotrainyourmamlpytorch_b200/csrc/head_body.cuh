@@ -62,7 +62,9 @@ __device__ __forceinline__ void head_body(const HeadArgs& a, int task, int group
     float se = 0.f;
     for (int k = 0; k < N; ++k) se += expf(logits[i * N + k] - mx);
     const float lse = mx + logf(se);
-    const int yi = (int)y[i];
+    // labels index shared memory below: out-of-range values (rejected on the host for host batches; torch's
+    // cross_entropy raises) are clamped so that a bad device-resident label cannot read outside the row
+    const int yi = min(max((int)y[i], 0), N - 1);
     float pd = 0.f;
     for (int k = 0; k < N; ++k) {
       const float p = expf(logits[i * N + k] - mx) / se;

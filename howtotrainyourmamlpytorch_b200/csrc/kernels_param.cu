@@ -157,8 +157,51 @@ __device__ __forceinline__ const double* stat_ptr(const ExportArgs& a, int task,
          (long long)layer * a.st_layer_stride;
 }
 
+__device__ void export_body(const ExportArgs& a);
+
+// ---- peer-memory signalling (system scope: the flag lives in ANOTHER GPU's memory, reached over NVLink) ----
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_relaxed_sys_v4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// Called by every thread of a publishing kernel after its stores: the LAST block to arrive makes the whole slot visible
+// system-wide and raises this rank's flag in every peer's memory.
+__device__ __forceinline__ void comm_signal_when_last(const CommDev& c, unsigned seq) {
+  __threadfence();                                        // this block's stores are in L2 (the point peers read from)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(&c.counters[0], 1u);
+    if (done == gridDim.x * gridDim.y - 1) {
+      __threadfence_system();
+      c.counters[0] = 0;                                  // re-armed for the next launch
+      for (int p = 0; p < c.world; ++p)
+        if (p != c.rank) st_release_sys(c.peer_flags[p] + c.rank, seq);
+    }
+  }
+}
+
 __global__ void export_kernel(ExportArgs a) {
   pdl_prologue(18, a.tag);
+  unsigned seq = 0;
+  if (a.comm.world > 1) {
+    // multi-GPU: write straight into this round's communication slot (peers read it over NVLink) and signal
+    seq = *(volatile unsigned*)a.comm.seq;
+    a.result = a.comm.local_data + (long long)(seq & 1u) * a.comm.slot_stride;
+  }
+  export_body(a);
+  if (a.comm.world > 1) comm_signal_when_last(a.comm, seq);
+}
+
+__device__ void export_body(const ExportArgs& a) {
   const ParamLayout& pl = a.pl;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long LSF = (long long)pl.L * pl.S * pl.F;
@@ -246,7 +289,8 @@ __global__ void export_kernel(ExportArgs a) {
   const int l = (int)(rel / ((long long)pl.S * pl.F));
   const int s = (int)((rel / pl.F) % pl.S);
   const int f = (int)(rel % pl.F);
-  if (!a.training || s >= a.num_steps) { a.result[i] = 0.f; return; }
+  // evaluation passes leave the EMA side effect behind too (the reference's backup is an alias, see run_validation_iter)
+  if (s >= a.num_steps) { a.result[i] = 0.f; return; }
   const bool has_t = (a.target_mask >> s) & 1u;
   const int c = has_t ? 2 : 1;
   const int U = c * a.tasks_global;
@@ -273,6 +317,83 @@ void launch_export(const ExportArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_PARAM, 0.0, st);
   const long long total = a.pl.meta_size + 2 + (a.pl.per_step_bn ? 2LL * a.pl.L * a.pl.S * a.pl.F : 0);
   launch_pdl(export_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st, tagged(a));
+  CUDA_CHECK_LAUNCH();
+}
+
+// ---------------------------------------------------------------------------------------------
+// The ONE collective of an iteration (replaces the reference's DataParallel gather, few_shot_learning_system.py:74-77):
+// all-reduce(SUM) of the result vector as a kernel over peer memory.  Every block waits until all peers have raised
+// their flag for this round (their slot is complete and visible), then each thread pulls one float4 from every rank's
+// slot -- peer loads over NVLink / NVSwitch, all issued before the first add -- and sums them in rank order, so every
+// rank computes bit-identical sums.  Two slots suffice: a rank rewrites slot k two rounds later, after its own reduce of
+// the round in between, which needed every peer's flag for that round, which a peer raises only after ITS reduce of
+// round k (stream order) -- i.e. after it finished reading the slot.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) allreduce_kernel(CommDev c, float* __restrict__ result, long long n, int tag) {
+  const long long n4 = (n + 3) / 4;
+  pdl_prologue(24, tag);
+  const unsigned seq = *(volatile unsigned*)c.seq;
+  if (threadIdx.x < c.world && threadIdx.x != c.rank) {
+    const unsigned* f = c.local_flags + threadIdx.x;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    unsigned spins = 0;
+    while ((int)(ld_acquire_sys(f) - seq) < 0) {
+      if ((++spins & 0x3ff) == 0) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 30ull * 1000000000ull) {           // a peer never arrived: report instead of hanging the GPU
+          atomicExch((unsigned long long*)c.status, (unsigned long long)seq | (1ull << 40) | ((unsigned long long)threadIdx.x << 32));
+          break;
+        }
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    const long long off = (long long)(seq & 1u) * c.slot_stride + i * 4;
+    float4 v[MAML_MAX_RANKS];
+#pragma unroll
+    for (int p = 0; p < MAML_MAX_RANKS; ++p)
+      if (p < c.world) v[p] = ld_relaxed_sys_v4(c.peer_data[p] + off);
+    float4 acc = v[0];
+#pragma unroll
+    for (int p = 1; p < MAML_MAX_RANKS; ++p)
+      if (p < c.world) { acc.x += v[p].x; acc.y += v[p].y; acc.z += v[p].z; acc.w += v[p].w; }
+    if (i * 4 + 4 <= n) *reinterpret_cast<float4*>(result + i * 4) = acc;
+    else {                                                 // ragged tail (slots are padded to 4 floats, `result` is not)
+      const float t[4] = {acc.x, acc.y, acc.z, acc.w};
+      for (int k = 0; i * 4 + k < n; ++k) result[i * 4 + k] = t[k];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(&c.counters[1], 1u);
+    if (done == gridDim.x - 1) { c.counters[1] = 0; __threadfence(); *(volatile unsigned*)c.seq = seq + 1u; }
+  }
+}
+
+void launch_allreduce(const CommDev& c, float* result, long long n, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_PARAM, 0.0, st);
+  const long long n4 = (n + 3) / 4;
+  launch_pdl(allreduce_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), (size_t)(0), st, c, result, n, launch_tag());
+  CUDA_CHECK_LAUNCH();
+}
+
+__global__ void __launch_bounds__(256) publish_kernel(CommDev c, const float* __restrict__ src, long long n, int tag) {
+  pdl_prologue(25, tag);
+  const unsigned seq = *(volatile unsigned*)c.seq;
+  float* dst = c.local_data + (long long)(seq & 1u) * c.slot_stride;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+  comm_signal_when_last(c, seq);
+}
+
+void launch_publish(const CommDev& c, const float* src, long long n, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_PARAM, 0.0, st);
+  launch_pdl(publish_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), st, c, src, n, launch_tag());
   CUDA_CHECK_LAUNCH();
 }
 

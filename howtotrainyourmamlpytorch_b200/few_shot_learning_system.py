@@ -112,9 +112,7 @@ class MAMLFewShotClassifier(nn.Module):
         self.optimizer = _FlatAdamState(self)
         self._current_lr = float(args.meta_learning_rate)
         self._staging = {}
-        self.rank, self.world_size = 0, 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            self.rank, self.world_size = torch.distributed.get_rank(), torch.distributed.get_world_size()
+        self.rank, self.world_size = 0, 1          # resolved at call time (_dist)
 
     # ------------------------------------------------------------------ parameters / flat storage
     def get_inner_loop_parameter_dict(self, params):
@@ -292,72 +290,101 @@ class MAMLFewShotClassifier(nn.Module):
                 if (off, size) != self._flat_slices[n]:
                     raise RuntimeError("engine segment layout mismatch at %s" % n)
             self._result = torch.zeros(self._engine.result_size, dtype=torch.float32, device=self.device)
+            self._comm_mode = None          # decided (collectively) by the first sharded call on this engine
         if not self._views_intact():
             self._build_flat_storage()
         return self._engine
 
-    def _stage(self, key, tensor, dtype):
-        """Pinned host staging + async H2D copy into a PERSISTENT device buffer (replaces the reference's unpinned
-        synchronous ``torch.Tensor(x).float().to(device)``, :355-358).  Persistent addresses keep the engine's
-        CUDA-graph cache hot.  Labels follow the reference's float -> long conversion (:357-358)."""
-        t = tensor if torch.is_tensor(tensor) else torch.as_tensor(np.asarray(tensor))
-        if t.device.type == "cuda":
-            if t.dtype == dtype and t.is_contiguous() and t.device == self.device:
-                return t
-            if dtype == torch.int64 and t.is_floating_point():
-                return t.to(self.device).long().contiguous()
-            return t.to(self.device, dtype).contiguous()
-        if dtype == torch.int64:
-            t = t.to(torch.float32).long() if t.is_floating_point() else t.long()
-        else:
-            t = t.to(dtype)
-        buf = self._staging.get(key)
-        if buf is None or buf[0].shape != t.shape:
-            buf = (torch.empty(t.shape, dtype=dtype).pin_memory(), torch.empty(t.shape, dtype=dtype, device=self.device))
-            self._staging[key] = buf
-        buf[0].copy_(t)
-        buf[1].copy_(buf[0], non_blocking=True)
-        return buf[1]
+    # number of staging slots: a batch is staged into slot i % 2, so the host may fill the next batch's pinned block
+    # while the device still reads the previous one (replaces the reference's unpinned, synchronous
+    # ``torch.Tensor(x).float().to(device)``, :355-358)
+    _STAGE_SLOTS = 2
+
+    def _expected_shapes(self, B):
+        a = self.args
+        N, K, T = int(a.num_classes_per_set), int(a.num_samples_per_class), int(a.num_target_samples)
+        C, H, W = int(self.im_shape[1]), int(self.im_shape[2]), int(self.im_shape[3])
+        return ((B, N, K, C, H, W), (B, N, T, C, H, W), (B, N, K), (B, N, T))
+
+    def _check_batch(self, ts):
+        """The engine reads raw pointers: reject anything whose shape is not the episode shape ``args`` describes
+        (the reference would fail inside ``.view`` / the conv; here it would be an out-of-bounds read)."""
+        if len(ts) != 4:
+            raise ValueError("data_batch must be (x_support, x_target, y_support, y_target)")
+        if ts[0].dim() != 6:
+            raise ValueError("x_support must be [B, N, K, C, H, W], got %s" % (tuple(ts[0].shape),))
+        B = int(ts[0].shape[0])
+        for name, t, want in zip(("x_support", "x_target", "y_support", "y_target"), ts, self._expected_shapes(B)):
+            if tuple(t.shape) != want:
+                raise ValueError("%s has shape %s, the engine was configured for %s (args: N=%d K=%d T=%d, image %s)"
+                                 % (name, tuple(t.shape), want, want[1], self._expected_shapes(B)[0][2],
+                                    self._expected_shapes(B)[1][2], tuple(self.im_shape[1:])))
+        return B
 
     def _stage_batch(self, data_batch):
-        """Host episode batch -> device: the four tensors are packed into ONE pinned staging block and moved with ONE
-        asynchronous H2D copy into a persistent device block (typed views of it are what the engine sees).  Batches that
-        already live on the device go through ``_stage`` tensor by tensor."""
+        """Episode batch -> persistent device block.  Host batches: the four tensors are packed into ONE pinned staging
+        block and moved with ONE asynchronous H2D copy; device batches: four D2D copies into the same block.  Either
+        way the engine always sees the same (two) sets of addresses, which keeps its CUDA-graph cache hot -- a caller
+        that allocates fresh device tensors every iteration would otherwise force a re-capture per step.  Labels follow
+        the reference's float -> long conversion (:357-358); host labels are range-checked (torch's cross_entropy
+        raises on a bad label, the kernel would index shared memory with it)."""
         want = (torch.float32, torch.float32, torch.int64, torch.int64)
         ts = [t if torch.is_tensor(t) else torch.as_tensor(np.asarray(t)) for t in data_batch]
-        if any(t.device.type == "cuda" for t in ts):
-            return tuple(self._stage(k, t, d) for k, t, d in zip(("xs", "xt", "ys", "yt"), ts, want))
+        B = self._check_batch(ts)
+        on_dev = [t.device.type == "cuda" for t in ts]
         conv = []
-        for t, d in zip(ts, want):
+        for t, d, dev in zip(ts, want, on_dev):
             if d == torch.int64:
                 t = t.to(torch.float32).long() if t.is_floating_point() else t.long()      # reference :357-358
+                if not dev and t.numel() and (int(t.min()) < 0 or int(t.max()) >= int(self.args.num_classes_per_set)):
+                    raise ValueError("labels must lie in [0, num_classes_per_set)")
             else:
                 t = t.to(d)
             conv.append(t)
         key = tuple(tuple(t.shape) for t in conv)
         st = self._staging.get("batch")
-        if st is None or st[0] != key:
+        if st is None or st["key"] != key:
             offs, total = [], 0
             for t in conv:
                 offs.append(total)
                 total += (t.numel() * t.element_size() + 15) // 16 * 16
-            pin = torch.empty(total, dtype=torch.uint8).pin_memory()
-            dev = torch.empty(total, dtype=torch.uint8, device=self.device)
 
             def views(block):
                 return [block[o:o + t.numel() * t.element_size()].view(t.dtype).view(t.shape) for o, t in zip(offs, conv)]
-            st = (key, pin, dev, views(pin), views(dev))
+            st = {"key": key, "slots": [], "next": 0}
+            for _ in range(self._STAGE_SLOTS):
+                pin = torch.empty(total, dtype=torch.uint8).pin_memory()
+                dev = torch.empty(total, dtype=torch.uint8, device=self.device)
+                st["slots"].append({"pin": pin, "dev": dev, "pin_views": views(pin), "dev_views": views(dev),
+                                    "copied": torch.cuda.Event()})
             self._staging["batch"] = st
-        _, pin, dev, pin_views, dev_views = st
-        for v, t in zip(pin_views, conv):
-            v.copy_(t)
-        dev.copy_(pin, non_blocking=True)
-        return tuple(dev_views)
+        slot = st["slots"][st["next"]]
+        st["next"] = (st["next"] + 1) % self._STAGE_SLOTS
+        with torch.cuda.device(self.device):
+            if all(on_dev):
+                for v, t in zip(slot["dev_views"], conv):
+                    v.copy_(t, non_blocking=True)
+            else:
+                slot["copied"].synchronize()          # the H2D copy that last read this pinned block has finished
+                for v, t in zip(slot["pin_views"], conv):
+                    v.copy_(t)                        # (device-resident members come through the host: rare, mixed batches)
+                slot["dev"].copy_(slot["pin"], non_blocking=True)
+                slot["copied"].record()
+        return tuple(slot["dev_views"])
+
+    def _dist(self):
+        """(rank, world_size), resolved at call time: a process group initialised AFTER the model was built must not
+        leave the ranks silently training independent replicas."""
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            return torch.distributed.get_rank(), torch.distributed.get_world_size()
+        return 0, 1
 
     def _run(self, data_batch, epoch, training_phase, apply_update):
         if self.device.type != "cuda":
             raise _native.NativeLibraryError(
                 "MAMLFewShotClassifier needs a CUDA (sm_100a) device: the hot path has no CPU fallback")
+        # _shard_override = (rank, world): test hook -- act as one rank of a sharded job without a process group
+        self.rank, self.world_size = getattr(self, "_shard_override", None) or self._dist()
         xs, xt, ys, yt = self._stage_batch(data_batch)
         B = xs.shape[0]
         n_t = xt.shape[1] * xt.shape[2]
@@ -371,25 +398,120 @@ class MAMLFewShotClassifier(nn.Module):
             out = torch.empty(2 + B * n_t * N, dtype=torch.float32, device=self.device)
             self._staging[("out", B)] = out
         logits = out[2:].view(B, n_t, N)
+        if self.world_size > 1 and getattr(self, "_shard_override", None) is None:
+            self._ensure_comm(eng)
+            eng = self._engine
         with torch.cuda.device(self.device):
             eng.fwd_bwd(n_tasks=B, task_offset=task_offset, tasks_global=B_global, num_steps=num_steps,
                         second_order=second, training=training_phase, target_mask=mask, target_weight=weights,
                         meta=self._flat, xs=xs, ys=ys, xt=xt, yt=yt, result=self._result, last_logits=logits)
-            if self.world_size > 1:
-                torch.distributed.all_reduce(self._result, op=torch.distributed.ReduceOp.SUM)
+            reduced = self._all_reduce_result(eng)
             ms = eng.meta_size
-            out[:2].copy_(self._result[ms:ms + 2])
+            out[:2].copy_(reduced[ms:ms + 2])
             head = out
             if training_phase and apply_update:
                 self.optimizer.step_count += 1
-                eng.adam_step(self._flat, self._result, self._exp_avg, self._exp_avg_sq, lr=self._current_lr,
+                eng.adam_step(self._flat, reduced, self._exp_avg, self._exp_avg_sq, lr=self._current_lr,
                               step=self.optimizer.step_count, trainable_mask=self._trainable_mask,
                               clamp_mask=self._clamp_mask)
-                if self.args.per_step_bn_statistics:
-                    S = int(self.args.number_of_training_steps_per_iter)
-                    decay = sharding.decay_vector(mask, num_steps, S, B_global)
-                    eng.running_stats_update(self._result, self._running[0], self._running[1], decay)
+            if self.args.per_step_bn_statistics and (apply_update or not training_phase):
+                # F.batch_norm's EMA side effect on running_*[step].  Evaluation passes leave it behind as well: the
+                # reference's backup is copy(tensor.data), an alias, so restore_backup_stats restores the mutated values
+                # (meta_neural_network_architectures.py:240-255; pinned by the val/ golden entries).
+                S = int(self.args.number_of_training_steps_per_iter)
+                decay = sharding.decay_vector(mask, num_steps, S, B_global)
+                eng.running_stats_update(reduced, self._running[0], self._running[1], decay)
         return head, logits, w_msl, B_global, n_t
+
+    def _ensure_comm(self, eng):
+        """Connect the engine's peer-memory communicator (once per engine; every rank must get here together, like any
+        collective).  Each rank allocates a communication block inside the engine, the 64-byte CUDA IPC handles travel
+        through ``torch.distributed`` (plumbing), every rank maps its peers' blocks.  If ANY rank cannot (IPC unavailable
+        in this container, > 8 ranks, peers on another node) all ranks fall back to ``torch.distributed.all_reduce``
+        -- reported by ``collective_desc`` -- so the ranks never disagree about who sums."""
+        if self._comm_mode is not None:
+            return self._comm_mode
+        dist = torch.distributed
+        ok, why = 1, ""
+        if os.environ.get("MAML_B200_COLLECTIVE", "").lower() == "nccl":
+            ok, why = 0, "disabled by MAML_B200_COLLECTIVE=nccl"
+        handle = b"\0" * 64
+        if ok:
+            try:
+                with torch.cuda.device(self.device):
+                    handle = eng.comm_init(self.rank, self.world_size)
+            except Exception as exc:
+                ok, why = 0, repr(exc)[:200]
+        gathered = [None] * self.world_size
+        dist.all_gather_object(gathered, (ok, handle, why))
+        if all(g[0] for g in gathered):
+            try:
+                with torch.cuda.device(self.device):
+                    eng.comm_connect([g[1] for g in gathered])
+            except Exception as exc:
+                ok, why = 0, repr(exc)[:200]
+        else:
+            ok, why = 0, next(g[2] for g in gathered if not g[0])
+        flags = [None] * self.world_size
+        dist.all_gather_object(flags, (ok, why))
+        if all(f[0] for f in flags):
+            self._comm_mode = "peer"
+            self._comm_why = ""
+        else:
+            self._comm_mode = "nccl"
+            self._comm_why = next(f[1] for f in flags if not f[0])
+            if eng.comm_world() > 1:           # this rank did connect, another one could not: rebuild without
+                self._engine = None
+                eng = self._ensure_engine(self._engine_tasks)
+                self._comm_mode, self._comm_why = "nccl", self._comm_why
+        return self._comm_mode
+
+    def _all_reduce_result(self, eng):
+        """Sum of the flat result vector over the ranks -- the ONE collective of an iteration.
+        ``peer`` mode: nothing to do here, the engine call already ran its all-reduce kernel over peer memory inside the
+        iteration's CUDA graph and ``_result`` holds the sum.  ``nccl`` mode (fallback): one library all-reduce."""
+        if self.world_size > 1 and getattr(self, "_shard_override", None) is None and self._comm_mode == "nccl":
+            torch.distributed.all_reduce(self._result, op=torch.distributed.ReduceOp.SUM)
+        return self._result
+
+    def collective_desc(self):
+        mode = getattr(self, "_comm_mode", None)
+        if self.world_size <= 1 or mode is None:
+            return {"kind": "none (single GPU)"}
+        if mode == "peer":
+            return {"kind": "in-engine peer-memory all-reduce (export kernel publishes into an IPC-mapped slot, "
+                            "allreduce_kernel pulls every rank's slot over NVLink and sums in rank order; inside the "
+                            "iteration's CUDA graph)", "bytes": 4 * int(self._engine.result_size), "ranks": self.world_size}
+        return {"kind": "torch.distributed.all_reduce (NCCL) -- FALLBACK", "why": getattr(self, "_comm_why", ""),
+                "bytes": 4 * int(self._engine.result_size), "ranks": self.world_size}
+
+    def collective_launches(self):
+        """Kernels of THIS repo launched per iteration for the collective beyond what the engine call already counts
+        (peer mode: the all-reduce kernel is a node of the iteration graph and is in ``last_launch_count``; the NCCL
+        fallback's kernel is not ours)."""
+        return 0
+
+    def time_collective(self, iters=20):
+        """Median duration (us) of the stand-alone all-reduce of a result-sized vector, CUDA events on the launching
+        stream (bench.py's per-rank ``collective_us``).  Every rank must call it."""
+        if self.world_size <= 1 or self._engine is None:
+            return 0.0
+        vec = torch.zeros_like(self._result)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        with torch.cuda.device(self.device):
+            for i in range(iters + 3):
+                torch.distributed.barrier()
+                if i >= 3:
+                    ev[i - 3][0].record()
+                if self._comm_mode == "peer":
+                    self._engine.all_reduce(vec)
+                else:
+                    torch.distributed.all_reduce(vec)
+                if i >= 3:
+                    ev[i - 3][1].record()
+            torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) * 1e3 for a, b in ev)
+        return ts[len(ts) // 2]
 
     def _finish(self, head, logits, w_msl, B_global, n_t):
         """One D2H read of (loss, n_correct, logits) -- the reference syncs per task (:246,:249,:261)."""
@@ -416,8 +538,9 @@ class MAMLFewShotClassifier(nn.Module):
         return losses, preds
 
     def run_validation_iter(self, data_batch):
-        """Evaluation on a batch of tasks: first-order adaptation, final-step target loss only, running
-        statistics untouched (reference :371-397, :311-323, backup/restore :240-255)."""
+        """Evaluation on a batch of tasks: first-order adaptation, final-step target loss only (reference :371-397,
+        :311-323).  Like the reference, the pass leaves its BatchNorm EMA updates in ``running_mean`` / ``running_var``
+        (the reference's backup/restore, meta_neural_network_architectures.py:240-255, aliases the live tensor)."""
         if self.training:
             self.eval()
         head, logits, w_msl, Bg, n_t = self._run(data_batch, self.current_epoch, training_phase=False, apply_update=False)

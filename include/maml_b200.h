@@ -129,6 +129,21 @@ int maml_b200_running_stats_update(maml_b200_handle* h, const float* result,
                                    float* running_mean, float* running_var,
                                    const float* decay_host, void* stream);
 
+/* Multi-GPU (one process per GPU, all on one node): the ONE collective of an iteration -- all-reduce(SUM) of the result
+ * vector over the ranks -- runs as kernels over peer memory (NVLink / NVSwitch) inside the iteration's own CUDA graph.
+ * It replaces the reference's nn.DataParallel scatter / gather (few_shot_learning_system.py:74-77).
+ *   comm_init     allocates this rank's communication block and returns its 64-byte CUDA IPC handle;
+ *   (the caller exchanges the handles between the ranks, e.g. torch.distributed.all_gather_object)
+ *   comm_connect  maps every peer's block: all_handles = world x 64 bytes in rank order.
+ * Afterwards every maml_b200_meta_batch_fwd_bwd call with tasks_global > n_tasks leaves the all-reduced vector in
+ * `result` on every rank (bit-identical: the ranks are summed in rank order).  All ranks must issue the same sequence of
+ * sharded calls.  A rank that waits more than 30 s for a peer gives up and reports it through comm_status. */
+int maml_b200_comm_init(maml_b200_handle* h, int32_t rank, int32_t world, void* ipc_handle_out);
+int maml_b200_comm_connect(maml_b200_handle* h, const void* all_handles);
+int maml_b200_comm_world(const maml_b200_handle* h);
+int maml_b200_all_reduce(maml_b200_handle* h, float* vec, void* stream);   /* stand-alone, in place, result_size floats */
+int64_t maml_b200_comm_status(maml_b200_handle* h);
+
 /* Debug / test hook: copy one named internal buffer of the last call to host memory.
  * Returns the number of floats the buffer holds (or <0 on error); copies at most `capacity`.
  * Names: see DESIGN.md ("debug taps").  Synchronises the device. */

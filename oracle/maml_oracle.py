@@ -273,8 +273,10 @@ def autograd_train_iter(state, args, batch, epoch, training_phase=True, current_
         gr = torch.autograd.grad(loss, [leaves[n] for n in names], allow_unused=True)
         out["grads"] = OrderedDict((n, (g if g is not None else torch.zeros_like(leaves[n])).detach())
                                    for n, g in zip(names, gr))
-    out["running"] = apply_running_stats(state, args, stats) if training_phase else \
-        {k: v.clone() for k, v in state.items() if "running" in k}
+    # The reference's evaluation "backup" of the running statistics is copy(tensor.data): an ALIAS of the same storage
+    # (meta_neural_network_architectures.py:240-242), so restore_backup_stats (:250-255) puts the mutated values back --
+    # F.batch_norm's EMA side effect survives run_validation_iter.  Pinned by the val/ entries of the golden fixtures.
+    out["running"] = apply_running_stats(state, args, stats)
     return out
 
 
@@ -581,9 +583,7 @@ def manual_train_iter(state, args, batch, epoch, training_phase=True, current_ep
     if training_phase:
         names = trainable_names(args)
         out["grads"] = OrderedDict((n, outer[n] / B) for n in names)
-        out["running"] = apply_running_stats(state, args, stats)
-    else:
-        out["running"] = {k: v.clone() for k, v in state.items() if "running" in k}
+    out["running"] = apply_running_stats(state, args, stats)     # evaluation too: see autograd_train_iter
     if keep_intermediates:
         out["intermediates"] = inter
     return out

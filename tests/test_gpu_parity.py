@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import ALL_CASES, BIG_CASES, TINY_CASES, load_golden, grad_tolerance
+from conftest import ALL_CASES, BERNOULLI_CASES, BIG_CASES, TINY_CASES, load_golden, grad_tolerance
 from engine_layout import geometry, grid_to_nchw, flat_to_nchw, theta_to_ref, rel_err
 from oracle import maml_oracle as O
 
@@ -30,9 +30,27 @@ def _report(tag, rows):
         print("   " + r)
 
 
-@pytest.mark.parametrize("case", ["tiny_pp", "tiny_maml", "tiny_odd"])
+def _count_exact_ties(fwd_blocks):
+    """(#pooling windows, #windows whose maximum is attained by >= 2 elements) over the blocks of one oracle pass."""
+    import torch.nn.functional as Fnn
+    nwin, nties = 0, 0
+    for blk in fwd_blocks:
+        y = blk["y"]
+        act = torch.where(y > 0, y, 0.01 * y)
+        n_, c_, hh, ww = act.shape
+        win = Fnn.unfold(act.reshape(n_ * c_, 1, hh, ww), kernel_size=2, stride=2)      # [n*c, 4, windows]
+        mx = win.max(dim=1, keepdim=True).values
+        nwin += win.shape[0] * win.shape[2]
+        nties += int(((win == mx).sum(dim=1) >= 2).sum())
+    return nwin, nties
+
+
+@pytest.mark.parametrize("case", ["tiny_pp", "tiny_maml", "tiny_odd", "tiny_bern"])
 def test_stagewise_against_oracle(case, cuda_device):
-    """Every materialised intermediate of task 0 against the autograd-free oracle (fp32)."""
+    """Every materialised intermediate of task 0 against the autograd-free oracle (fp32).  ``tiny_bern`` runs
+    Bernoulli(0.93) binary images (the distribution bench.py uses): thousands of pooling windows with EXACT ties,
+    which F.max_pool2d resolves first-max-wins -- a tie resolved differently routes the gradient to another pixel and
+    shows up as an O(1) error in dz / dp of that block."""
     g = load_golden(case)
     a = g.args
     m = _model(g, cuda_device)
@@ -95,6 +113,14 @@ def test_stagewise_against_oracle(case, cuda_device):
                 chk("g[%d] %s" % (s, n[-22:]), gg[n], v, tol=2e-4)
             else:
                 chk("g[%d] %s" % (s, n[-22:]), gg[n], v, tol=5e-5)
+    if case in BERNOULLI_CASES:
+        nwin, nties = 0, 0
+        for s in range(S):
+            w_, t_ = _count_exact_ties(inter["sup_f"][s]["blocks"])
+            nwin += w_; nties += t_
+        rows.append("pooling windows with an exact tie (oracle, task 0 support passes): %d of %d -- resolved like "
+                    "F.max_pool2d iff the dz / dp rows above agree" % (nties, nwin))
+        assert nties > 100, "the Bernoulli case is supposed to exercise exact pooling ties"
     _report(case + " stagewise", rows)
     # final outputs
     assert abs(float(losses["loss"]) - float(ref["loss"])) <= 2e-5 * abs(float(ref["loss"]))
@@ -111,11 +137,10 @@ def test_golden_reference_parity(case, cuda_device):
     g = load_golden(case)
     m = _model(g, cuda_device)
     losses, preds, grads = m.meta_gradient(g.batch(0), g.iters[0][0])
-    # Tie-breaking chaos (conftest.grad_tolerance) can hit ANY case whose pre-activations land within an ulp of
-    # a branch point under this implementation's rounding (observed on tiny_odd with the tensor-core convs: one
-    # flip -> 1e-4), so the direct comparison always uses the loose bound; the tight statement is
-    # test_decision_forced_parity, which runs on every case.
-    big = True
+    # Full-size cases: tie-breaking chaos (conftest.grad_tolerance) makes the direct comparison loose by nature; the
+    # tight statement for them is test_decision_forced_parity.  Tiny cases stay on the tight fp32 bounds so that a
+    # regression in the un-pinned path is visible.
+    big = case in BIG_CASES
     ref_loss32, ref_loss64 = g.scalar("loss"), g.scalar("loss64")
     ltol = max(3 * abs(ref_loss32 - ref_loss64), (5e-3 if big else 2e-5) * abs(ref_loss64))
     assert abs(float(losses["loss"]) - ref_loss64) <= ltol, (float(losses["loss"]), ref_loss32, ref_loss64)
@@ -124,6 +149,15 @@ def test_golden_reference_parity(case, cuda_device):
     assert got_logits.shape == ref_logits.shape
     assert float((got_logits - ref_logits).abs().max()) <= (0.25 if big else 1e-3) * float(ref_logits.abs().max())
     g32, g64 = g.grads(0, ""), g.grads(0, "64")
+    if case in BERNOULLI_CASES and not big:
+        # exact pooling ties: fp64 resolves them differently from fp32, so the reference's OWN fp32-vs-fp64 distance is
+        # ~1e-3 here and the fp64-anchored policy below is loose.  With ties resolved like the reference the engine
+        # must sit next to the fp32 reference instead.
+        for n in g32:
+            if "conv.bias" in n or "conv-bias" in n:
+                continue
+            e32 = float((grads[n].cpu().double() - g32[n].double()).abs().max())
+            assert e32 <= 1e-4 * float(g32[n].abs().max()) + 1e-7, ("fp32-anchored (ties)", n, e32)
     rows, bad = [], []
     for n in g64:
         got = grads[n].cpu().double()
@@ -175,22 +209,124 @@ def test_train_iterations_post_state(case, cuda_device):
                     p.copy_(post[k].to(p.device))
 
 
-@pytest.mark.parametrize("case", ["tiny_pp", "tiny_maml", "omniglot_mamlpp_5w1s"])
+@pytest.mark.parametrize("case", ["tiny_pp", "tiny_maml", "tiny_bern", "omniglot_mamlpp_5w1s", "omniglot_mamlpp_5w1s_bernoulli"])
 def test_validation_iter(case, cuda_device):
+    """run_validation_iter against the reference's own run_validation_iter (golden val/ entries): loss, accuracy,
+    last-step logits, AND the state afterwards -- parameters untouched, running statistics mutated exactly like the
+    reference's (its evaluation backup is an alias, meta_neural_network_architectures.py:240-255)."""
     g = load_golden(case)
     m = _model(g, cuda_device)
     m.current_epoch = g.iters[0][0]
     before = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
     losses, preds = m.run_validation_iter(g.batch(0))
-    ref = O.autograd_train_iter(g.state(), g.args, g.batch(0), g.iters[0][0], training_phase=False,
-                                current_epoch=g.iters[0][0])
-    tol = 1e-3 if case in BIG_CASES else 2e-5
-    assert abs(float(losses["loss"]) - float(ref["loss"])) <= tol * abs(float(ref["loss"]))
+    big = case in BIG_CASES
+    tol = 1e-3 if big else 2e-5
+    ref_loss = float(g.val("loss"))
+    assert abs(float(losses["loss"]) - ref_loss) <= tol * abs(ref_loss), (float(losses["loss"]), ref_loss)
+    ref_logits = torch.from_numpy(g.val("logits"))
     got = torch.from_numpy(np.stack(preds))
-    assert float((got - ref["logits"]).abs().max()) <= 10 * tol * float(ref["logits"].abs().max())
+    assert got.shape == ref_logits.shape
+    assert float((got - ref_logits).abs().max()) <= 10 * tol * float(ref_logits.abs().max())
+    assert abs(float(losses["accuracy"]) - float(g.val("accuracy"))) <= (0.051 if big else 1e-6)
     after = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    post = g.val_post()
     for k in before:
-        assert torch.equal(before[k], after[k]), "validation must not change %s" % k
+        if "running" in k:
+            assert torch.allclose(after[k], post[k], rtol=1e-4, atol=1e-5), (k, float((after[k] - post[k]).abs().max()))
+        else:
+            assert torch.equal(before[k], after[k]), "validation must not change %s" % k
+    if g.args.per_step_bn_statistics:
+        assert any(not torch.equal(before[k], post[k]) for k in post), "reference fixture should show the mutation"
+
+
+def _result_vector(m, batch, epoch, shard=None):
+    """Raw result vector of one engine call (meta-gradient | loss | n_correct | running-stat partial sums)."""
+    if shard is not None:
+        m._shard_override = shard
+    try:
+        m.meta_gradient(batch, epoch)
+    finally:
+        m._shard_override = None
+    return m._result.detach().double().cpu().clone()
+
+
+@pytest.mark.parametrize("case,G", [("tiny_pp", 3), ("tiny_odd", 2), ("omniglot_mamlpp_5w1s_bernoulli", 2)])
+def test_engine_as_rank_r_of_G_sums_to_single_call(case, G, cuda_device):
+    """The N>1 data path of the ENGINE (task_offset > 0, tasks_global > n_tasks: 1/B_global scaling and the
+    position-weighted running-statistics partial sums of export_kernel): run the engine as rank r of G, one rank after
+    the other on one GPU, sum the G result vectors (= what the all-reduce does) and require the single-call vector."""
+    g = load_golden(case)
+    batch, epoch = g.batch(0), g.iters[0][0]
+    B = batch[0].shape[0]
+    assert B % G == 0
+    Bl = B // G
+    m = _model(g, cuda_device)
+    full = _result_vector(m, batch, epoch)
+    acc = torch.zeros_like(full)
+    for r in range(G):
+        mr = _model(g, cuda_device)
+        shard = tuple(t[r * Bl:(r + 1) * Bl].contiguous() for t in batch)
+        acc += _result_vector(mr, shard, epoch, shard=(r, G))
+    ms = m._engine.meta_size
+    segs = m._engine.segments
+    for (off, size), name in zip(segs, m._order):
+        a, b = acc[off:off + size], full[off:off + size]
+        if "conv.bias" in name or "conv-bias" in name:
+            assert float((a - b).abs().max()) <= 1e-5, name
+        else:
+            assert float((a - b).abs().max()) <= 2e-6 * float(b.abs().max()) + 1e-9, (name, float((a - b).abs().max()), float(b.abs().max()))
+    assert abs(float(acc[ms] - full[ms])) <= 1e-6 * abs(float(full[ms]))          # loss
+    assert float(acc[ms + 1]) == float(full[ms + 1])                              # number of correct predictions
+    tail_a, tail_b = acc[ms + 2:], full[ms + 2:]
+    if tail_b.numel():
+        assert float((tail_a - tail_b).abs().max()) <= 1e-6 * float(tail_b.abs().max()) + 1e-9   # running-stat partial sums
+
+
+def _two_rank_worker(rank, world, port, case, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    g = load_golden(case)
+    m = _model(g, dev)
+    B = g.batch(0)[0].shape[0]
+    Bl = B // world
+    for it, (epoch, _) in enumerate(g.iters):
+        shard = tuple(t[rank * Bl:(rank + 1) * Bl].contiguous() for t in g.batch(it))
+        losses, preds = m.run_train_iter(shard, epoch)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    torch.save({"sd": sd, "loss": float(losses["loss"]), "acc": float(losses["accuracy"])},
+               os.path.join(out_dir, "rank%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["tiny_odd", "tiny_bern"])
+def test_two_gpus_equal_one_gpu(case, cuda_device, tmp_path):
+    """Two ranks over NCCL (tasks sharded, one all-reduce per iteration) against one GPU holding the whole meta-batch:
+    same losses, same post-Adam state_dict, identical replicas."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    s_ = socket.socket(); s_.bind(("127.0.0.1", 0)); port = s_.getsockname()[1]; s_.close()
+    mp.spawn(_two_rank_worker, args=(2, port, case, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(os.path.join(str(tmp_path), "rank0.pt"))
+    r1 = torch.load(os.path.join(str(tmp_path), "rank1.pt"))
+    g = load_golden(case)
+    m = _model(g, cuda_device)
+    for it, (epoch, _) in enumerate(g.iters):
+        losses, _ = m.run_train_iter(g.batch(it), epoch)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    assert abs(r0["loss"] - float(losses["loss"])) <= 1e-6 * abs(float(losses["loss"]))
+    assert abs(r0["acc"] - float(losses["accuracy"])) <= 1e-9
+    for k in sd:
+        assert torch.equal(r0["sd"][k], r1["sd"][k]), ("replicas diverged", k)
+        if "conv.bias" in k or "conv-bias" in k:
+            continue
+        assert torch.allclose(r0["sd"][k], sd[k], rtol=1e-4, atol=2e-5), (k, float((r0["sd"][k] - sd[k]).abs().max()))
 
 
 def test_properties_full_size(cuda_device):
