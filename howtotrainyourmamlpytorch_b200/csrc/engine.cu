@@ -108,6 +108,7 @@ struct maml_b200_handle {
   unsigned long long graph_clock = 0;
   // tensor-core path (blocks l >= 1 when F % 32 == 0)
   bool use_tc = false;
+  int tc_stack = 1;        // N-stacked 3xTF32 MMAs (env MAML_B200_TC_STACK=0: three MMAs per k-step)
   int tc_bo_mode = 0;      // 0: row-shifted UMMA descriptors keep base_offset = 0 (correct on B200); 1: experiment (env MAML_B200_TC_BO)
   float *pack_theta = nullptr, *pack_u = nullptr;       // [4 planes][steps][T][(L-1)*9*F*F]
   long long pack_theta_plane = 0, pack_u_plane = 0, pack_task = 0;
@@ -357,6 +358,7 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   // tensor-core (tcgen05 / TMA, 3xTF32) convolutions for blocks l >= 1; reserved bit 1 forces the fp32 FFMA kernels (tests)
   h->use_tc = (h->L > 1) && !(cfg->reserved & 2);
   if (const char* bo = getenv("MAML_B200_TC_BO")) h->tc_bo_mode = atoi(bo);
+  if (const char* sk = getenv("MAML_B200_TC_STACK")) h->tc_stack = atoi(sk) != 0;
   if (const char* sp = getenv("MAML_B200_TC_SPLIT")) tc_conv_set_split(atoi(sp));
   g_launch_prio = getenv("MAML_B200_LAUNCH_PRIO") ? 1 : 0;
   if (const char* wr = getenv("MAML_B200_WGRAD_ROW")) wgrad_set_row_variant(atoi(wr));
@@ -545,6 +547,7 @@ static void tc_conv(maml_b200_handle* h, int l, int n, int nsrc, const TcOp* ops
   TcMaps maps;
   TcConvArgs a{};
   a.nsrc = nsrc; a.kc = h->F; a.rows = n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.ncols = h->F; a.mode = mode; a.tasks = T; a.plan_tasks = h->maxT;
+  a.stack = h->tc_stack;
   a.halo = g.gw + 1; a.rpad = tc_conv_rpad(g.gw); a.nb = tc_conv_ring(h->F, g.gw); a.bo_mode = h->tc_bo_mode; { const char* tl = getenv("MAML_B200_TC_TIMELINE"); a.timeline = (tl && (atoi(tl) <= 0 || atoi(tl) == l)) ? 1 : 0; }
   for (int s = 0; s < nsrc; ++s) {
     maps.m[s * 4 + 0] = ops[s].a_maps[0]; maps.m[s * 4 + 1] = ops[s].a_maps[1];

@@ -161,8 +161,9 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
   trace_mark(22, a.tag);
   constexpr int B_BYTES = NCOLS * 128;
   constexpr int BSTAGE = 2 * B_BYTES;            // B_hi + B_lo of one (tap, k-chunk)
-  constexpr int NACC = 5;                        // 4 x hi*hi (round-robin over k-steps) + 1 x (lo*hi + hi*lo)
-  constexpr int TMEM_COLS = NCOLS <= 16 ? 128 : (NCOLS <= 48 ? 256 : 512);   // power of two >= NACC * NCOLS
+  // accumulators: plain mode 4 x hi*hi (round-robin over k-steps) + 1 x (lo*hi + hi*lo) = 5 * NCOLS columns;
+  // stacked mode 4 x [hi*hi | hi*lo + lo*hi] = 8 * NCOLS columns (see the MMA issuer)
+  constexpr int TMEM_COLS = NCOLS <= 16 ? 128 : (NCOLS <= 32 ? 256 : 512);   // power of two >= 8 * NCOLS
   constexpr int PITCH = NCOLS + 1;
   constexpr int MAXB = 8;
   extern __shared__ uint8_t smem_raw[];
@@ -272,7 +273,21 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
         const uint64_t al0 = ald + (uint64_t)(row_off * 8);
         const uint64_t bh0 = desc_base + (uint64_t)(smem_u32(bring + (size_t)stage * BSTAGE) >> 4);
         const uint64_t bl0 = bh0 + (uint64_t)(B_BYTES >> 4);
-        if (kstep == 0) {
+        if (a.stack) {
+          // N-stacked 3xTF32: B_hi and B_lo of a stage are adjacent K-major tiles, so ONE descriptor with N = 2 * NCOLS
+          // reads [B_hi; B_lo] and A_hi x [B_hi; B_lo]^T lands as [hi*hi | hi*lo] in 2 * NCOLS adjacent TMEM columns:
+          // two instructions per k-step instead of three, and A_hi crosses the shared-memory port once instead of twice
+          // (14 KB instead of 18 KB of operand fetch per k-step at N = 64 -- the measured floor of this kernel).
+          // lo*hi is added to the small block.  Round-robin over 4 such column blocks keeps <= 18 sequential
+          // accumulations per accumulator (the tensor core's fp32 accumulation truncates, see the header).
+          constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * NCOLS) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+          const uint32_t first = (kstep == 0) ? 0u : 1u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            tc_mma_tf32(tmem_base + (uint32_t)k * 2 * NCOLS, ah0 + 2 * k, bh0 + 2 * k, idesc2, first);
+            tc_mma_tf32_acc(tmem_base + (uint32_t)k * 2 * NCOLS + NCOLS, al0 + 2 * k, bh0 + 2 * k, idesc);
+          }
+        } else if (kstep == 0) {
           // first four k-steps initialise the five accumulators
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -327,11 +342,27 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
     for (int c0 = 0; c0 < NCOLS; c0 += 16) {
       uint32_t v0[16], v1[16], v2[16], v3[16], v4[16];
       const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      tc_ld16(ta, v0);
-      tc_ld16(ta + NCOLS, v1);
-      tc_ld16(ta + 2 * NCOLS, v2);
-      tc_ld16(ta + 3 * NCOLS, v3);
-      tc_ld16(ta + 4 * NCOLS, v4);
+      if (a.stack) {
+        // blocks k = 0..3 at columns k * 2N: [hi*hi | small]; sum the four small blocks first (into v4), then load the big ones
+        tc_ld16(ta + NCOLS, v0);
+        tc_ld16(ta + 3 * NCOLS, v1);
+        tc_ld16(ta + 5 * NCOLS, v2);
+        tc_ld16(ta + 7 * NCOLS, v3);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          v4[i] = __float_as_uint((__uint_as_float(v0[i]) + __uint_as_float(v1[i])) + (__uint_as_float(v2[i]) + __uint_as_float(v3[i])));
+        tc_ld16(ta, v0);
+        tc_ld16(ta + 2 * NCOLS, v1);
+        tc_ld16(ta + 4 * NCOLS, v2);
+        tc_ld16(ta + 6 * NCOLS, v3);
+      } else {
+        tc_ld16(ta, v0);
+        tc_ld16(ta + NCOLS, v1);
+        tc_ld16(ta + 2 * NCOLS, v2);
+        tc_ld16(ta + 3 * NCOLS, v3);
+        tc_ld16(ta + 4 * NCOLS, v4);
+      }
       tc_wait_ld();
       float o[16];
       if (nsplit == 1) {

@@ -9,6 +9,7 @@ struct TcConvArgs {
   int nsrc, kc, rows, gw, G, h, w, ncols, mode, tasks;
   int plan_tasks;        // split-K is planned for this many tasks (the handle's max_tasks) so that a task's arithmetic
                          // does not depend on how many tasks share the call
+  int stack;             // 1: N-stacked 3xTF32 (A_hi x [B_hi; B_lo] as one N = 2 * ncols MMA), 0: three MMAs per k-step
   int halo, rpad, nb, bo_mode, timeline;   // halo = gw + 1 rows; rpad = halo-tile rows (multiple of 8); nb = B ring depth
   int a_row_base[2];     // row (in the A tensor map) of grid row 0 of task 0 for this pass slot (includes the guard)
   int a_task_rows[2];    // rows per task in the A tensor map
