@@ -281,7 +281,7 @@ def run_reference_arm(cli, args, rank, world):
                 "baseline/_ref with CUDA_VISIBLE_DEVICES='' (BASELINE.md section 4); one step = one meta-batch of %d tasks; "
                 "wall %.1f s" % (int(args.batch_size), time.perf_counter() - t0),
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def _stats(xs):
@@ -427,6 +427,17 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="diagnostic: do not flush L2 between timed steps")
     ap.add_argument("--sync-each-step", action="store_true", help="diagnostic: synchronize after every timed step")
     cli = ap.parse_args()
+
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 when
+    # NCCL_DEBUG is set): from here on fd 1 points at stderr and the line goes to the saved original.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(line):
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
+    globals()["_emit"] = emit
 
     import torch
     from howtotrainyourmamlpytorch_b200 import make_args
@@ -577,7 +588,7 @@ def main():
                     "sample": "%d timed iterations of %d tasks (median), %d warm-up" % (len(g["times_s"]), g["batch_size"], g["warmup"]),
                     "gpu": g.get("gpu")}
             line["cpu_baseline"], _ = reference_cpu_baseline(cli, args, steps=8, warmup=2)
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

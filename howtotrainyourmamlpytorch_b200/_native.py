@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "maml_b200_profile", "maml_b200_profile_read", "maml_b200_net_forward",
     "maml_b200_trace", "maml_b200_trace_read",
     "maml_b200_comm_init", "maml_b200_comm_connect", "maml_b200_comm_world", "maml_b200_all_reduce",
-    "maml_b200_comm_status",
+    "maml_b200_comm_status", "maml_b200_net_backward", "maml_b200_net_running_update",
 ]
 PROF_CATS = ["conv_igemm", "conv_first_block", "wgrad", "wgrad_first_block", "bn_act_pool", "head", "param"]
 
@@ -77,6 +77,10 @@ def load_library():
     lib.maml_b200_meta_batch_fwd_bwd.restype = ctypes.c_int
     lib.maml_b200_net_forward.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     lib.maml_b200_net_forward.restype = ctypes.c_int
+    lib.maml_b200_net_backward.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    lib.maml_b200_net_backward.restype = ctypes.c_int
+    lib.maml_b200_net_running_update.argtypes = [vp, i32, i32, vp, vp, vp]
+    lib.maml_b200_net_running_update.restype = ctypes.c_int
     lib.maml_b200_adam_step.argtypes = [vp, vp, vp, vp, vp, f32, i32, u32, u32, vp]
     lib.maml_b200_adam_step.restype = ctypes.c_int
     lib.maml_b200_running_stats_update.argtypes = [vp, vp, vp, vp, ctypes.POINTER(f32), vp]
@@ -179,6 +183,16 @@ class Engine(object):
         rc = self.lib.maml_b200_net_forward(self.h, int(n_tasks), int(num_step), meta_like.data_ptr(), x.data_ptr(),
                                             logits.data_ptr(), self._stream())
         _check(self.lib, rc, "maml_b200_net_forward")
+
+    def net_backward(self, n_tasks, num_step, meta_like, dlogits, grad_out):
+        rc = self.lib.maml_b200_net_backward(self.h, int(n_tasks), int(num_step), meta_like.data_ptr(), dlogits.data_ptr(),
+                                             grad_out.data_ptr(), self._stream())
+        _check(self.lib, rc, "maml_b200_net_backward")
+
+    def net_running_update(self, n_tasks, num_step, running_mean, running_var):
+        rc = self.lib.maml_b200_net_running_update(self.h, int(n_tasks), int(num_step), running_mean.data_ptr(),
+                                                   running_var.data_ptr(), self._stream())
+        _check(self.lib, rc, "maml_b200_net_running_update")
 
     def adam_step(self, meta, grad, exp_avg, exp_avg_sq, lr, step, trainable_mask, clamp_mask):
         rc = self.lib.maml_b200_adam_step(self.h, meta.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(),

@@ -134,7 +134,8 @@ struct BnBwdTanArgs {             // backward reduce / apply (tangent)
   int tag;          // launch sequence number inside the iteration (device trace)
 };
 
-enum { HEAD_SUPPORT = 0, HEAD_TARGET_FWD = 1, HEAD_TARGET_BWD = 2, HEAD_TANGENT = 3 };
+enum { HEAD_SUPPORT = 0, HEAD_TARGET_FWD = 1, HEAD_TARGET_BWD = 2, HEAD_TANGENT = 3,
+       HEAD_EXTERNAL_BWD = 4 };     // backward of the linear layer for an externally supplied d(loss)/d(logits) (functional operator)
 
 struct HeadArgs {
   int mode;
@@ -144,6 +145,7 @@ struct HeadArgs {
   const float* Wfc; const float* bfc; long long theta_stride;     // [N][D], [N] (internal order), per task
   const float* uW; const float* ub; long long u_stride;           // tangent direction (HEAD_TANGENT)
   const long long* y; long long y_stride;         // labels [n]
+  const float* dl_ext; long long dl_ext_stride;   // HEAD_EXTERNAL_BWD: upstream gradient w.r.t. the logits [n][N], per task
   float scale;                                    // loss weight folded into dlogits (1 for the support loss)
   float* gW; float* gb; long long g_stride;       // gradient (or H*u) output for the head tensors (chunk 0)
   long long g_chunk_stride;                       // stride between the row-group chunks of gW / gb
@@ -261,6 +263,9 @@ void launch_adam(float* meta, const float* grad, float* m, float* v, long long n
                  cudaStream_t st);
 void launch_running_update(const float* part_mean, const float* part_var, float* rm, float* rv,
                            const float* decay_dev, int L, int S, int F, cudaStream_t st);
+// one sequential EMA update per task from the batch sums of a forward pass (functional operator's side effect)
+void launch_running_ema_from_stats(const double* stats, long long stats_task_stride, long long layer_stride, int tasks, float* rm,
+                                   float* rv, int L, int S, int F, int step, const int* hw_host, int n, cudaStream_t st);
 
 // stats arena pass ids
 enum { PASS_SUP_FWD = 0, PASS_SUP_BWD = 1, PASS_TGT_FWD = 2, PASS_TGT_BWD = 3, PASS_TAN_FWD = 4, PASS_TAN_BWD = 5,
@@ -297,6 +302,7 @@ void trace_set_bn(unsigned long long* p);
 void trace_set_head(unsigned long long* p);
 void trace_set_param(unsigned long long* p);
 void trace_set_tc(unsigned long long* p);
+void trace_set_wgtc(unsigned long long* p);
 
 __device__ __forceinline__ void pdl_prologue(int kid = 0, int tag = 0) {
   trace_mark(kid, tag);

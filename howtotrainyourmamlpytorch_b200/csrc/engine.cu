@@ -64,6 +64,9 @@ struct PassSet {            // activation buffers of one kind of pass (support: 
   float* dz_base[MAML_MAX_LAYERS] = {}; long long dz_plane[MAML_MAX_LAYERS] = {};
   CUtensorMap ain_map[MAML_MAX_LAYERS][2];   // [layer][hi/lo]
   CUtensorMap dz_map[MAML_MAX_LAYERS][2];
+  // the same planes seen by the tcgen05 weight-gradient kernel (MN-major operands: swizzle 128B_ATOM_32B, other boxes)
+  CUtensorMap ain_wg_map[MAML_MAX_LAYERS][2];
+  CUtensorMap dz_wg_map[MAML_MAX_LAYERS][2];
 };
 
 struct ChunkPlan { int rows_per_chunk[MAML_MAX_LAYERS]; int nchunks[MAML_MAX_LAYERS]; PartialDesc pd; long long size; int head_groups; };
@@ -108,6 +111,7 @@ struct maml_b200_handle {
   unsigned long long graph_clock = 0;
   // tensor-core path (blocks l >= 1 when F % 32 == 0)
   bool use_tc = false;
+  bool wgrad_tc = true;    // tcgen05 weight gradient for blocks l >= 1 (env MAML_B200_WGRAD_TC=0: the FFMA filter-row kernel)
   int tc_stack = 1;        // N-stacked 3xTF32 MMAs (env MAML_B200_TC_STACK=0: three MMAs per k-step)
   int tc_bo_mode = 0;      // 0: row-shifted UMMA descriptors keep base_offset = 0 (correct on B200); 1: experiment (env MAML_B200_TC_BO)
   float *pack_theta = nullptr, *pack_u = nullptr;       // [4 planes][steps][T][(L-1)*9*F*F]
@@ -191,8 +195,16 @@ static void plan_chunks(maml_b200_handle* h, int n, ChunkPlan* cp) {
       static const int wg_per_chunk = (getenv("MAML_B200_WGRAD_ROW") && atoi(getenv("MAML_B200_WGRAD_ROW")) == 0) ? 9 : 3;
       long long want = std::max<long long>(1, wg_slots / ((long long)wg_per_chunk * h->maxT));
       nch = (int)std::min<long long>(std::min<long long>(64, want), std::max<long long>(1, (rows + 15) / 16));
+      if (h->use_tc && h->wgrad_tc) {
+        // tcgen05 weight gradient: 3 CTAs (filter rows) per chunk, stages of 32 rows, accumulators drained every 64 rows
+        // (so chunk length is a scheduling choice only): one wave of CTAs, chunks of at least 64 rows to amortise a
+        // CTA's fixed cost, at most 64 chunks per task.
+        long long r = rup((rows + want - 1) / want, 32);
+        r = std::max<long long>(64, r);
+        nch = (int)std::min<long long>(64, (rows + r - 1) / r);
+      }
     }
-    rpc = (int)rup((rows + nch - 1) / nch, 16);
+    rpc = (int)rup((rows + nch - 1) / nch, (l > 0 && h->use_tc && h->wgrad_tc) ? 32 : 16);
     nch = (int)((rows + rpc - 1) / rpc);
     cp->rows_per_chunk[l] = rpc; cp->nchunks[l] = nch;
     const long long cs = 9LL * h->geo[l].cin * h->F + h->F;
@@ -232,7 +244,8 @@ static EncodeTiledFn get_encode_fn() {
   }
   return fn;
 }
-static int make_map(CUtensorMap* m, const float* base, long long rows, int cols, int box_rows) {
+static int make_map(CUtensorMap* m, const float* base, long long rows, int cols, int box_rows,
+                    CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -240,7 +253,7 @@ static int make_map(CUtensorMap* m, const float* base, long long rows, int cols,
   cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   return 0;
 }
@@ -250,6 +263,10 @@ static int make_pass_maps(maml_b200_handle* h, PassSet& ps, bool has_dz) {
       const int rp = tc_conv_rpad(h->geo[l].gw);       // one TMA box = the 128-row tile plus its halo
       if (make_map(&ps.ain_map[l][pl], ps.ain_base[l] + (pl + 1) * ps.ain_plane[l], ps.ain_plane[l] / h->F, h->F, rp)) return 1;
       if (has_dz && make_map(&ps.dz_map[l][pl], ps.dz_base[l] + (pl + 1) * ps.dz_plane[l], ps.dz_plane[l] / h->F, h->F, rp)) return 1;
+      if (make_map(&ps.ain_wg_map[l][pl], ps.ain_base[l] + (pl + 1) * ps.ain_plane[l], ps.ain_plane[l] / h->F, h->F, 40,
+                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+      if (has_dz && make_map(&ps.dz_wg_map[l][pl], ps.dz_base[l] + (pl + 1) * ps.dz_plane[l], ps.dz_plane[l] / h->F, h->F, 32,
+                             CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
     }
   }
   return 0;
@@ -262,6 +279,7 @@ static int make_all_maps(maml_b200_handle* h) {
     if (make_map(&h->u_map[pl], h->pack_u + pl * h->pack_u_plane, h->pack_u_plane / h->F, h->F, h->F)) return 1;
   }
   if (tc_conv_prepare()) return fail("cudaFuncSetAttribute(max dynamic shared memory) failed for the tcgen05 conv kernel");
+  if (wgrad_tc_prepare()) return fail("cudaFuncSetAttribute(max dynamic shared memory) failed for the tcgen05 wgrad kernel");
   return 0;
 }
 
@@ -359,6 +377,7 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   h->use_tc = (h->L > 1) && !(cfg->reserved & 2);
   if (const char* bo = getenv("MAML_B200_TC_BO")) h->tc_bo_mode = atoi(bo);
   if (const char* sk = getenv("MAML_B200_TC_STACK")) h->tc_stack = atoi(sk) != 0;
+  if (const char* wt = getenv("MAML_B200_WGRAD_TC")) h->wgrad_tc = atoi(wt) != 0;
   if (const char* sp = getenv("MAML_B200_TC_SPLIT")) tc_conv_set_split(atoi(sp));
   g_launch_prio = getenv("MAML_B200_LAUNCH_PRIO") ? 1 : 0;
   if (const char* wr = getenv("MAML_B200_WGRAD_ROW")) wgrad_set_row_variant(atoi(wr));
@@ -562,6 +581,29 @@ static void tc_conv(maml_b200_handle* h, int l, int n, int nsrc, const TcOp* ops
   launch_conv_tc(maps, a, st);
 }
 
+// tcgen05 weight gradient of block l >= 1: sum over sources of A(ain of a_ps/a_slot)^T-shifted x D(dz of d_ps/d_slot)
+struct WgSrc { const PassSet* a_ps; int a_slot; const PassSet* d_ps; int d_slot; };
+static void tc_wgrad(maml_b200_handle* h, int l, int n, int nsrc, const WgSrc* src, float* partial, const ChunkPlan& cp, int T,
+                     cudaStream_t st) {
+  const LayerGeom& g = h->geo[l];
+  TcMaps maps;
+  WgTcArgs a{};
+  a.nsrc = nsrc; a.kc = h->F; a.ncols = h->F; a.rows = n * g.G; a.gw = g.gw;
+  a.rows_per_chunk = cp.rows_per_chunk[l]; a.nchunks = cp.nchunks[l];
+  for (int s = 0; s < nsrc; ++s) {
+    const PassSet& ap = *src[s].a_ps; const PassSet& dp = *src[s].d_ps;
+    maps.m[s * 4 + 0] = ap.ain_wg_map[l][0]; maps.m[s * 4 + 1] = ap.ain_wg_map[l][1];
+    maps.m[s * 4 + 2] = dp.dz_wg_map[l][0]; maps.m[s * 4 + 3] = dp.dz_wg_map[l][1];
+    a.a_row_base[s] = a_row_base_of(h, ap.ain_sz[l], l, src[s].a_slot); a.a_task_rows[s] = (int)(ap.ain_sz[l] * ap.slots / h->F);
+    a.b_row_base[s] = a_row_base_of(h, dp.dz_sz[l], l, src[s].d_slot); a.b_task_rows[s] = (int)(dp.dz_sz[l] * dp.slots / h->F);
+  }
+  if (nsrc == 1) for (int k = 4; k < 8; ++k) maps.m[k] = maps.m[k - 4];
+  a.partial = partial + cp.pd.off[2 * l]; a.partial_task_stride = cp.pd.task_stride; a.chunk_stride = cp.pd.cstride[2 * l];
+  a.tasks = T;
+  a.alg_flops = conv_flops(h, l, n, T, nsrc);
+  launch_wgrad_tc(maps, a, st);
+}
+
 // primal forward of one pass: conv -> stats -> BN/leaky/pool for every block
 static void forward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const float* theta, int th_step, const float* meta,
                          int bn_step, int stat_kind, int T, cudaStream_t st, BnActArgs* defer_last = nullptr) {
@@ -660,7 +702,12 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
         a.alg_flops = conv_flops(h, l, ps.n, T, 1);
         launch_conv_rows(a, st);
       }
-      launch_wgrad(w, wst);
+      if (h->use_tc && h->wgrad_tc) {
+        WgSrc ws{&ps, slot, &ps, slot};
+        tc_wgrad(h, l, ps.n, 1, &ws, partial, cp, T, wst);
+      } else {
+        launch_wgrad(w, wst);
+      }
       if (split && l == 1) reduce_upper_on_side(h, *rs, cp.pd, partial, meta, T);
     }
   }
@@ -822,7 +869,12 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
         a.alg_flops = conv_flops(h, l, sp.n, T, 2);
         launch_conv_rows(a, st);
       }
-      launch_wgrad(w, h->s_wg);
+      if (h->use_tc && h->wgrad_tc) {
+        WgSrc ws[2] = {{&sp, s, &tn, 0}, {&tn, 0, &sp, s}};        // (a_in, dz_dot) + (a_in_dot, dz)
+        tc_wgrad(h, l, sp.n, 2, ws, h->sup_partial, cp, T, h->s_wg);
+      } else {
+        launch_wgrad(w, h->s_wg);
+      }
       if (l == 1) reduce_upper_on_side(h, rs, cp.pd, h->sup_partial, meta, T);
     }
   }
@@ -1078,6 +1130,75 @@ extern "C" int maml_b200_net_forward(maml_b200_handle* h, int32_t n_tasks, int32
   return 0;
 }
 
+// Backward of the functional forward above (level B1: lets torch.autograd differentiate through the operator, the way the
+// reference's apply_inner_loop_update does with torch.autograd.grad, few_shot_learning_system.py:138-139, first order).
+// Must follow maml_b200_net_forward on the same handle with the same (n_tasks, num_step, meta_like): the activations of
+// that call are what this one differentiates.  dlogits [n_tasks, N*T, N] = d(loss)/d(logits).  grad_out: result_size
+// floats; the first meta_size hold d(loss)/d(meta_like) in the meta layout (conv / linear weights and biases, BatchNorm
+// beta / gamma of `num_step`; LSLR entries 0), summed over the n_tasks batches.  No gradient w.r.t. the images.
+extern "C" int maml_b200_net_backward(maml_b200_handle* h, int32_t n_tasks, int32_t num_step, const float* meta_like,
+                                     const float* dlogits, float* grad_out, void* stream) {
+  if (!h || !meta_like || !dlogits || !grad_out) return fail("null argument");
+  if (n_tasks < 1 || n_tasks > h->maxT) return fail("n_tasks out of range");
+  if (num_step < 0 || num_step >= h->S) return fail("num_step out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int T = n_tasks;
+  // backward statistics (and the tangent ones export subtracts) start from zero; forward statistics are kept
+  for (int kind : {PASS_TGT_BWD, PASS_TAN_BWD})
+    CK(cudaMemset2DAsync(h->stats + (long long)kind * MAML_MAX_STEPS * h->st_pass_stride, (size_t)h->stats_task_stride * sizeof(double), 0,
+                         (size_t)MAML_MAX_STEPS * h->st_pass_stride * sizeof(double), (size_t)T, st));
+  CK(cudaMemsetAsync(h->abar, 0, (size_t)h->maxT * h->pl.nseg_inner * MAML_MAX_STEPS * sizeof(double), st));
+  CK(cudaMemsetAsync(h->losses, 0, (size_t)h->maxT * MAML_MAX_STEPS * sizeof(float), st));
+  CK(cudaMemsetAsync(h->correct, 0, (size_t)h->maxT * sizeof(float), st));
+  float* tpart = h->tgt_partial;
+  HeadArgs a{};
+  a.mode = HEAD_EXTERNAL_BWD; a.n = h->n_t; a.N = h->N; a.D = h->D; a.scale = 1.f;
+  a.f = AIN(h->tgt, h->L, 0); a.f_stride = STRIDE(h->tgt, ain, h->L);
+  a.Wfc = h->theta + h->pl.fcw_off; a.bfc = h->theta + h->pl.fcb_off; a.theta_stride = h->Ppad;
+  a.y = h->zero_labels; a.y_stride = 0;
+  a.dl_ext = dlogits; a.dl_ext_stride = (long long)h->n_t * h->N;
+  a.gW = tpart + h->plan_tgt.pd.off[2 * h->L]; a.gb = tpart + h->plan_tgt.pd.off[2 * h->L + 1];
+  a.g_stride = h->plan_tgt.pd.task_stride; a.g_chunk_stride = h->plan_tgt.pd.cstride[2 * h->L];
+  a.rows_per_cta = HEAD_ROWS_PER_CTA;
+  a.df = DP(h->tgt, h->L - 1, 0); a.df_stride = STRIDE(h->tgt, dp, h->L - 1);
+  a.tasks = T;
+  launch_head(a, st);
+  backward_pass(h, h->tgt, 0, h->theta, 0, meta_like, num_step, PASS_TGT_FWD, PASS_TGT_BWD, tpart, h->plan_tgt, T, st, false);
+  launch_param_reduce(h->pl, h->plan_tgt.pd, tpart, PR_STORE, nullptr, nullptr, h->tbar, nullptr, meta_like, num_step, h->Ppad, T, st);
+  ExportArgs e{};
+  e.pl = h->pl;
+  e.tbar = h->tbar; e.task_stride = h->Ppad;
+  e.abar = h->abar;
+  e.stats = h->stats; e.stats_task_stride = h->stats_task_stride; e.st_pass_stride = h->st_pass_stride; e.st_layer_stride = h->st_layer_stride;
+  e.losses = h->losses; e.correct = h->correct;
+  e.target_mask = 0; e.num_steps = h->S; e.training = 1;
+  e.tasks = T; e.task_offset = 0; e.tasks_global = 1;            // plain sum over the batches, no 1/B
+  e.n_s = h->n_s; e.n_t = h->n_t;
+  for (int l = 0; l < h->L; ++l) e.hw[l] = h->geo[l].h * h->geo[l].w;
+  e.result = grad_out;
+  launch_export(e, st);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// Side effect of the functional forward in the reference: F.batch_norm's EMA update of running_mean / running_var at
+// `num_step` (meta_neural_network_architectures.py:226-247), from the batch statistics of the last maml_b200_net_forward
+// call (one update per batch, in order).  running_mean / running_var: [stages][S][F] device.  No-op for shared BatchNorm
+// (the reference passes running stats = None there).
+extern "C" int maml_b200_net_running_update(maml_b200_handle* h, int32_t n_tasks, int32_t num_step, float* running_mean,
+                                           float* running_var, void* stream) {
+  if (!h || !running_mean || !running_var) return fail("null argument");
+  if (n_tasks < 1 || n_tasks > h->maxT) return fail("n_tasks out of range");
+  if (num_step < 0 || num_step >= h->S) return fail("num_step out of range");
+  if (!h->cfg.per_step_bn) return 0;
+  int hw[MAML_MAX_LAYERS];
+  for (int l = 0; l < h->L; ++l) hw[l] = h->geo[l].h * h->geo[l].w;
+  launch_running_ema_from_stats(stat_at(h, PASS_TGT_FWD, num_step, 0), h->stats_task_stride, h->st_layer_stride, n_tasks, running_mean,
+                                running_var, h->L, h->S, h->F, num_step, hw, h->n_t, (cudaStream_t)stream);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int maml_b200_adam_step(maml_b200_handle* h, float* meta, const float* grad, float* exp_avg, float* exp_avg_sq,
                                    float lr, int32_t step, uint32_t trainable_mask, uint32_t clamp_mask, void* stream) {
   if (!h || !meta || !grad || !exp_avg || !exp_avg_sq) return fail("null argument");
@@ -1211,7 +1332,7 @@ extern "C" int maml_b200_profile_read(maml_b200_handle* h, double* ms_by_cat, do
 // device-side launch trace (common.cuh: trace_mark): start timestamps of every kernel of the following calls
 static unsigned long long* g_trace_dev = nullptr;
 static void trace_set_all(unsigned long long* p) {
-  trace_set_conv(p); trace_set_bn(p); trace_set_head(p); trace_set_param(p); trace_set_tc(p);
+  trace_set_conv(p); trace_set_bn(p); trace_set_head(p); trace_set_param(p); trace_set_tc(p); trace_set_wgtc(p);
 }
 extern "C" int maml_b200_trace(maml_b200_handle* h, int32_t enable) {
   if (!h) return fail("null argument");

@@ -69,7 +69,9 @@ __device__ __forceinline__ void head_body(const HeadArgs& a, int task, int group
     for (int k = 0; k < N; ++k) {
       const float p = expf(logits[i * N + k] - mx) / se;
       prob[i * N + k] = p;
-      dl[i * N + k] = (p - (k == yi ? 1.f : 0.f)) * (wscale * inv_n);
+      dl[i * N + k] = (a.mode == HEAD_EXTERNAL_BWD)
+                          ? a.dl_ext[(long long)task * a.dl_ext_stride + (long long)(row0 + i) * N + k]
+                          : (p - (k == yi ? 1.f : 0.f)) * (wscale * inv_n);
       if (tan) pd += p * ldot[i * N + k];
     }
     if (tan)

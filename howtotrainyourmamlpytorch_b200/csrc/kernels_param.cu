@@ -453,4 +453,41 @@ void launch_running_update(const float* part_mean, const float* part_var, float*
   CUDA_CHECK_LAUNCH();
 }
 
+// Functional operator (VGGReLUNormNetwork.forward as a stand-alone call): the reference's F.batch_norm leaves
+// running[step] <- 0.9 running[step] + 0.1 batch statistic behind for every block (meta_neural_network_architectures.py:
+// 226-247), one update per forward call (= per task here, in task order).
+struct HwArr { int v[MAML_MAX_LAYERS]; };
+__global__ void running_ema_from_stats_kernel(const double* __restrict__ stats, long long task_stride, long long layer_stride, int tasks,
+                                              float* __restrict__ rm, float* __restrict__ rv, int L, int S, int F, int step, HwArr hw, int n,
+                                              int tag) {
+  pdl_prologue(26, tag);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L * F) return;
+  const int l = i / F, f = i - l * F;
+  const double m = (double)n * (double)hw.v[l];
+  float* pm = rm + ((long long)l * S + step) * F + f;
+  float* pv = rv + ((long long)l * S + step) * F + f;
+  float a = *pm, b = *pv;
+  for (int t = 0; t < tasks; ++t) {
+    const double* sp = stats + (long long)t * task_stride + (long long)l * layer_stride;
+    const double mean = sp[f * 2] / m;
+    double var = sp[f * 2 + 1] / m - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double unbiased = var * (m / (m > 1.0 ? m - 1.0 : 1.0));
+    a = 0.9f * a + 0.1f * (float)mean;          // fp32 like the reference's running buffers
+    b = 0.9f * b + 0.1f * (float)unbiased;
+  }
+  *pm = a; *pv = b;
+}
+
+void launch_running_ema_from_stats(const double* stats, long long stats_task_stride, long long layer_stride, int tasks, float* rm,
+                                   float* rv, int L, int S, int F, int step, const int* hw_host, int n, cudaStream_t st) {
+  ProfScope prof_scope__(PROF_PARAM, 0.0, st);
+  HwArr hw{};
+  for (int l = 0; l < L; ++l) hw.v[l] = hw_host[l];
+  launch_pdl(running_ema_from_stats_kernel, dim3((L * F + 127) / 128), dim3(128), (size_t)(0), st, stats, stats_task_stride, layer_stride,
+             tasks, rm, rv, L, S, F, step, hw, n, launch_tag());
+  CUDA_CHECK_LAUNCH();
+}
+
 MAML_TRACE_SETTER(trace_set_param)

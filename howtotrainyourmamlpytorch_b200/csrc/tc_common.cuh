@@ -33,3 +33,19 @@ int tc_read_timeline(long long* out16);
 void launch_conv_tc(const TcMaps& maps, const TcConvArgs& a, cudaStream_t st);
 void launch_pack_weights(const ParamLayout& pl, const float* theta, long long theta_task_stride, float* pack,
                          long long pack_task_stride, long long plane_stride, int tasks, cudaStream_t st);
+
+// tcgen05 weight gradient (kernels_wgrad_tc.cu).  maps.m[s * 4 + {0,1,2,3}] = A_hi, A_lo, D_hi, D_lo of source s, all with
+// swizzle 128B_ATOM_32B and boxes [40 rows][32] (A) / [32 rows][32] (D) over the same planes the conv kernel reads.
+struct WgTcArgs {
+  int nsrc, kc, ncols, rows, gw;
+  int rows_per_chunk, nchunks;          // rows_per_chunk is a multiple of 32
+  int a_row_base[2], a_task_rows[2];    // row (in the A map) of grid row 0 of task 0 for this pass slot; rows per task
+  int b_row_base[2], b_task_rows[2];
+  float* partial; long long partial_task_stride; long long chunk_stride;    // [task][chunk][9 * kc * ncols + ncols]
+  int tasks;
+  double alg_flops;
+  int tag;
+};
+size_t wgrad_tc_smem_bytes();
+int wgrad_tc_prepare();
+void launch_wgrad_tc(const TcMaps& maps, const WgTcArgs& a, cudaStream_t st);

@@ -6,7 +6,8 @@ followed by a linear layer, all taking externally supplied ("fast") weights.  He
 the reference's module tree and parameter names -- so ``state_dict`` keys, shapes, registration
 order (= Adam parameter order) and initialisation RNG consumption are identical -- but they are
 parameter containers: the arithmetic of the path runs in the CUDA engine (``csrc/``), which sees
-these parameters as one flat buffer.
+these parameters as one flat buffer.  ``VGGReLUNormNetwork.forward`` is the functional-network operator of the
+boundary (level B1): forward and (first-order) backward both run on the engine through ``torch.autograd.Function``.
 
 Initialisation restates reference ``:62-66`` (xavier_uniform_ conv weight, zero bias),
 ``:114-118`` (xavier_uniform_ linear weights), ``:177-192`` (running_mean zeros; running_var ones
@@ -120,22 +121,10 @@ class VGGReLUNormNetwork(nn.Module):
             out.append(fast.get(n, own[n]))
         return out
 
-    def forward(self, x, num_step, params=None, training=False, backup_running_statistics=False):
-        """Logits of a batch under externally supplied ("fast") weights -- reference
-        ``VGGReLUNormNetwork.forward`` (:620-660): ``params`` maps ``layer_dict.conv{i}.conv.{weight,bias}`` /
-        ``layer_dict.linear.{weights,bias}`` to tensors carrying a leading replica dim (as the reference passes them)
-        or not; missing entries fall back to the module's own parameters.  BatchNorm always uses batch statistics
-        (the reference hard-codes ``training=True``, :246-247) with the gamma / beta of ``num_step``.
-        Runs on the CUDA engine (C ABI ``maml_b200_net_forward``); the running-statistics EMA side effect of the
-        reference is not applied by this stand-alone operator (they are write-only bookkeeping there).
-        The batch size must be a multiple of the number of classes (episode shaped)."""
+    def _operator_engine(self, x):
+        """(engine, meta-layout scratch, logits out, gradient out, running-stat scratch) for this batch shape."""
         from . import _native
-        if x.device.type != "cuda":
-            raise _native.NativeLibraryError("VGGReLUNormNetwork.forward needs a CUDA (sm_100a) device: no CPU fallback")
-        n = int(x.shape[0])
-        N = self.num_output_classes
-        if n % N != 0:
-            raise ValueError("batch size %d is not a multiple of num_output_classes %d" % (n, N))
+        n, N = int(x.shape[0]), self.num_output_classes
         key = (n, x.device.index)
         cache = self.__dict__.setdefault("_engines", {})
         if key not in cache:
@@ -145,21 +134,108 @@ class VGGReLUNormNetwork(nn.Module):
                                      width=int(x.shape[3]), filters=self.cnn_filters, num_stages=self.num_stages,
                                      inner_steps=int(a.number_of_training_steps_per_iter),
                                      per_step_bn=bool(a.per_step_bn_statistics), max_tasks=1)
-            cache[key] = (eng, torch.zeros(eng.meta_size, dtype=torch.float32, device=x.device),
-                          torch.empty(1, n, N, dtype=torch.float32, device=x.device))
-        eng, meta_like, logits = cache[key]
+            S = int(a.number_of_training_steps_per_iter) if a.per_step_bn_statistics else 1
+            cache[key] = {"eng": eng, "gen": 0,
+                          "meta": torch.zeros(eng.meta_size, dtype=torch.float32, device=x.device),
+                          "logits": torch.empty(1, n, N, dtype=torch.float32, device=x.device),
+                          "grad": torch.zeros(eng.result_size, dtype=torch.float32, device=x.device),
+                          "run": torch.zeros(2, self.num_stages, S, self.cnn_filters, dtype=torch.float32, device=x.device)}
+        return cache[key]
+
+    def forward(self, x, num_step, params=None, training=False, backup_running_statistics=False):
+        """Logits of a batch under externally supplied ("fast") weights -- reference
+        ``VGGReLUNormNetwork.forward`` (:620-660): ``params`` maps ``layer_dict.conv{i}.conv.{weight,bias}`` /
+        ``layer_dict.linear.{weights,bias}`` to tensors carrying a leading replica dim (as the reference passes them)
+        or not; missing entries fall back to the module's own parameters.  BatchNorm always uses batch statistics
+        (the reference hard-codes ``training=True``, :246-247) with the gamma / beta of ``num_step``, and -- like
+        ``F.batch_norm`` there -- leaves its EMA update in ``running_mean / running_var[num_step]`` (per-step BN only).
+
+        Runs on the CUDA engine (C ABI ``maml_b200_net_forward`` / ``maml_b200_net_backward``) and is differentiable
+        through ``torch.autograd`` with respect to every weight it uses (conv / linear fast weights, BatchNorm gamma /
+        beta), which is what the reference's ``apply_inner_loop_update`` needs (``torch.autograd.grad`` of the support
+        loss, few_shot_learning_system.py:138-139).  First order only: the second-order terms live in the fused
+        iteration (``MAMLFewShotClassifier``).  No gradient flows to ``x``.  The batch size must be a multiple of the
+        number of classes (episode shaped)."""
+        from . import _native
+        if x.device.type != "cuda":
+            raise _native.NativeLibraryError("VGGReLUNormNetwork.forward needs a CUDA (sm_100a) device: no CPU fallback")
+        n = int(x.shape[0])
+        if n % self.num_output_classes != 0:
+            raise ValueError("batch size %d is not a multiple of num_output_classes %d" % (n, self.num_output_classes))
         tensors = self._segment_tensors(params)
-        for (off, size), t in zip(eng.segments, tensors):
-            meta_like[off:off + size].copy_(t.detach().reshape(-1).to(torch.float32))
-        with torch.cuda.device(x.device):
-            eng.net_forward(1, int(num_step), meta_like, x.detach().to(torch.float32).contiguous(), logits)
-        return logits[0].clone()
+        return _FunctionalForward.apply(self, x, int(num_step), *tensors)
+
+    def _apply_running_ema(self, st, num_step):
+        if not self.args.per_step_bn_statistics:
+            return
+        run = st["run"]
+        with torch.no_grad():
+            for l in range(self.num_stages):
+                bn = self.layer_dict["conv%d" % l].norm_layer
+                run[0, l].copy_(bn.running_mean.data)
+                run[1, l].copy_(bn.running_var.data)
+            st["eng"].net_running_update(1, num_step, run[0], run[1])
+            for l in range(self.num_stages):
+                bn = self.layer_dict["conv%d" % l].norm_layer
+                bn.running_mean.data.copy_(run[0, l])
+                bn.running_var.data.copy_(run[1, l])
 
     def zero_grad(self, params=None):
+        """Reference :662-677: clears the gradients of ``params`` (or of the module's own parameters)."""
         if params is None:
             for p in self.parameters():
                 p.grad = None
+        else:
+            for p in params.values():
+                if getattr(p, "grad", None) is not None:
+                    p.grad = None
 
     def restore_backup_stats(self):
-        """Evaluation never commits running statistics in the engine, so there is nothing to restore."""
+        """The reference's evaluation backup of the running statistics is ``copy(tensor.data)`` -- an alias of the live
+        storage (:240-242) -- so its restore (:250-255) puts the already-mutated values back: a no-op on the values,
+        which is what this is."""
         return None
+
+
+class _FunctionalForward(torch.autograd.Function):
+    """``VGGReLUNormNetwork.forward`` as an autograd node: forward = ``maml_b200_net_forward``, backward =
+    ``maml_b200_net_backward`` (head backward for an external d(logits), BatchNorm / pool / leaky-ReLU backward, dgrad and
+    wgrad kernels of the engine).  The engine keeps the activations of its LAST forward only, so a backward that arrives
+    after another forward of the same shape first replays its own forward (cheap) -- correctness does not depend on the
+    call order."""
+
+    @staticmethod
+    def forward(ctx, net, x, num_step, *tensors):
+        st = net._operator_engine(x)
+        eng, meta_like, logits = st["eng"], st["meta"], st["logits"]
+        xin = x.detach().to(torch.float32).contiguous()
+        with torch.no_grad():
+            for (off, size), t in zip(eng.segments, tensors):
+                meta_like[off:off + size].copy_(t.detach().reshape(-1).to(torch.float32))
+        with torch.cuda.device(x.device):
+            eng.net_forward(1, num_step, meta_like, xin, logits)
+            net._apply_running_ema(st, num_step)
+        st["gen"] += 1
+        ctx.net, ctx.num_step, ctx.gen = net, num_step, st["gen"]
+        ctx.save_for_backward(xin, *[t.detach() for t in tensors])
+        return logits[0].clone()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dlogits):
+        net, num_step = ctx.net, ctx.num_step
+        xin, tensors = ctx.saved_tensors[0], ctx.saved_tensors[1:]
+        st = net._operator_engine(xin)
+        eng, meta_like, logits, grad = st["eng"], st["meta"], st["logits"], st["grad"]
+        with torch.cuda.device(xin.device):
+            if st["gen"] != ctx.gen:                 # another forward ran since: replay ours (no EMA side effect again)
+                for (off, size), t in zip(eng.segments, tensors):
+                    meta_like[off:off + size].copy_(t.reshape(-1).to(torch.float32))
+                eng.net_forward(1, num_step, meta_like, xin, logits)
+                st["gen"] += 1
+                ctx.gen = st["gen"]
+            eng.net_backward(1, num_step, meta_like, dlogits.detach().to(torch.float32).contiguous().view(1, *dlogits.shape), grad)
+        grads = []
+        for (off, size), t, need in zip(eng.segments, tensors, ctx.needs_input_grad[3:]):
+            grads.append(grad[off:off + size].view(t.shape).clone() if need else None)
+        return (None, None, None) + tuple(grads)

@@ -112,6 +112,22 @@ int maml_b200_meta_batch_fwd_bwd(maml_b200_handle* h, const maml_b200_iter_args*
 int maml_b200_net_forward(maml_b200_handle* h, int32_t n_tasks, int32_t num_step, const float* meta_like,
                           const float* x, float* logits, void* stream);
 
+/* Backward of maml_b200_net_forward (so that torch.autograd can differentiate through the functional operator, as the
+ * reference's apply_inner_loop_update does with torch.autograd.grad, few_shot_learning_system.py:138-139; first order).
+ * Must directly follow maml_b200_net_forward on the same handle with the same (n_tasks, num_step, meta_like).
+ *   dlogits  [n_tasks, N*T, N]   d(loss) / d(logits)
+ *   grad_out [result_size]       (out) first meta_size floats = d(loss) / d(meta_like) in the meta layout (conv / linear
+ *                                weights and biases, BatchNorm beta / gamma rows of num_step; LSLR entries 0), summed over
+ *                                the n_tasks batches.  No gradient with respect to the images is produced. */
+int maml_b200_net_backward(maml_b200_handle* h, int32_t n_tasks, int32_t num_step, const float* meta_like,
+                           const float* dlogits, float* grad_out, void* stream);
+
+/* EMA side effect of the functional forward (F.batch_norm updating running_mean / running_var at num_step, reference
+ * meta_neural_network_architectures.py:226-247) from the batch statistics of the last maml_b200_net_forward call.
+ * running_mean / running_var: [stages][S][F] device.  No-op without per-step BatchNorm. */
+int maml_b200_net_running_update(maml_b200_handle* h, int32_t n_tasks, int32_t num_step, float* running_mean,
+                                 float* running_var, void* stream);
+
 /* Outer step on the flat vectors: optional clamp to [-10,10] (reference :332-335), Adam
  * (betas 0.9/0.999, eps 1e-8, no weight decay; reference :69,:336).  `grad` is the first
  * meta_size floats of (the all-reduced) result.  Bit i of trainable_mask / clamp_mask refers to
