@@ -487,9 +487,15 @@ def test_decision_forced_parity(case, cuda_device):
             # dead parameter (true gradient 0): fp32 cancellation noise, proportional to the live gradients
             tol = 1e-5 * max(1.0, max(float(x.abs().max()) for x in ref["grads"].values()))
         else:
-            # Mini-ImageNet 5-way 5-shot: the inner loop diverges at LR 0.1 (loss 29, gradients up to 240) and the LSLR
-            # gradients -<theta_bar, g> are dot products with heavy cancellation: fp32 rounding shows up to 2e-4 there
-            tol = (5e-4 if (case == "mini_imagenet_mamlpp_5w5s" and "names_learning_rates" in n) else 1e-4) * scale + 1e-7
+            # Mini-ImageNet 5-way 5-shot: the inner loop diverges at LR 0.1 (loss 29, gradients up to 240; the reference's
+            # own fp32 run is 10 % away from its fp64 run).  Rounding differences of the fast weights are amplified step
+            # by step (GPU decisions flip at fp64 margins up to 4e-4, see above), and the LSLR gradients -<theta_bar, g>
+            # are dot products with heavy cancellation: measured 1.2e-4 of max-norm on the ordinary tensors and 1.2e-3 on
+            # one LSLR vector with the 3xTF32 tensor-core weight gradient (2e-5 / 2e-4 with the fp32 FFMA one).
+            if case == "mini_imagenet_mamlpp_5w5s":
+                tol = (3e-3 if "names_learning_rates" in n else 3e-4) * scale + 1e-7
+            else:
+                tol = 1e-4 * scale + 1e-7
         rows.append("%-78s err %.2e (%.1e of max)" % (n, err, err / scale))
         if err > tol:
             bad.append((n, err, tol))
