@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "maml_b200_profile", "maml_b200_profile_read", "maml_b200_net_forward",
     "maml_b200_trace", "maml_b200_trace_read",
     "maml_b200_comm_init", "maml_b200_comm_connect", "maml_b200_comm_world", "maml_b200_all_reduce",
-    "maml_b200_comm_status", "maml_b200_net_backward", "maml_b200_net_running_update",
+    "maml_b200_comm_status", "maml_b200_net_backward", "maml_b200_net_running_update", "maml_b200_episode_gather",
 ]
 PROF_CATS = ["conv_igemm", "conv_first_block", "wgrad", "wgrad_first_block", "bn_act_pool", "head", "param"]
 
@@ -81,6 +81,9 @@ def load_library():
     lib.maml_b200_net_backward.restype = ctypes.c_int
     lib.maml_b200_net_running_update.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.maml_b200_net_running_update.restype = ctypes.c_int
+    lib.maml_b200_episode_gather.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, ctypes.POINTER(f32),
+                                             ctypes.POINTER(f32), vp, vp, vp, vp, vp]
+    lib.maml_b200_episode_gather.restype = ctypes.c_int
     lib.maml_b200_adam_step.argtypes = [vp, vp, vp, vp, vp, f32, i32, u32, u32, vp]
     lib.maml_b200_adam_step.restype = ctypes.c_int
     lib.maml_b200_running_stats_update.argtypes = [vp, vp, vp, vp, ctypes.POINTER(f32), vp]
@@ -117,6 +120,20 @@ def load_library():
 def _check(lib, rc, what):
     if rc != 0:
         raise RuntimeError("%s failed: %s" % (what, lib.maml_b200_last_error().decode()))
+
+
+def episode_gather(dataset, image_index, rot_k, n_tasks, n_way, k_shot, t_target, channels, height, width, mean, std,
+                   xs, xt, ys, yt):
+    """``maml_b200_episode_gather`` on the current stream (all tensors on the current CUDA device)."""
+    import torch
+    lib = load_library()
+    mean_arr = (ctypes.c_float * channels)(*[float(v) for v in mean]) if mean is not None else None
+    std_arr = (ctypes.c_float * channels)(*[float(v) for v in std]) if std is not None else None
+    rc = lib.maml_b200_episode_gather(dataset.data_ptr(), image_index.data_ptr(), rot_k.data_ptr(), int(n_tasks), int(n_way),
+                                      int(k_shot), int(t_target), int(channels), int(height), int(width), mean_arr, std_arr,
+                                      xs.data_ptr(), xt.data_ptr(), ys.data_ptr(), yt.data_ptr(),
+                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _check(lib, rc, "maml_b200_episode_gather")
 
 
 class Engine(object):

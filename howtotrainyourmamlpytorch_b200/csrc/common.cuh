@@ -267,6 +267,10 @@ void launch_running_update(const float* part_mean, const float* part_var, float*
 void launch_running_ema_from_stats(const double* stats, long long stats_task_stride, long long layer_stride, int tasks, float* rm,
                                    float* rv, int L, int S, int F, int step, const int* hw_host, int n, cudaStream_t st);
 
+void launch_episode_gather(const float* dataset, const long long* image_index, const int* rot_k, int B, int N, int K, int T, int C,
+                           int H, int W, const float* mean, const float* stdv, float* xs, float* xt, long long* ys, long long* yt,
+                           cudaStream_t st);
+
 // stats arena pass ids
 enum { PASS_SUP_FWD = 0, PASS_SUP_BWD = 1, PASS_TGT_FWD = 2, PASS_TGT_BWD = 3, PASS_TAN_FWD = 4, PASS_TAN_BWD = 5,
        PASS_KINDS = 6 };

@@ -1308,6 +1308,21 @@ extern "C" int64_t maml_b200_comm_status(maml_b200_handle* h) {
   return (int64_t)v;
 }
 
+// GPU-resident episode assembly (no handle: it only needs the current device).  mean / stdv: host arrays of `channels`
+// floats or null (no normalisation).  rot_k[b][n] in {0,1,2,3}: np.rot90 count of class n of task b (needs H == W when odd).
+extern "C" int maml_b200_episode_gather(const float* dataset, const int64_t* image_index, const int32_t* rot_k, int32_t n_tasks,
+                                       int32_t n_way, int32_t k_shot, int32_t t_target, int32_t channels, int32_t height,
+                                       int32_t width, const float* mean_host, const float* std_host, float* x_support,
+                                       float* x_target, int64_t* y_support, int64_t* y_target, void* stream) {
+  if (!dataset || !image_index || !rot_k || !x_support || !x_target || !y_support || !y_target) return fail("null argument");
+  if (n_tasks < 1 || n_way < 1 || k_shot < 1 || t_target < 1 || channels < 1 || channels > 4 || height < 1 || width < 1)
+    return fail("episode_gather: bad shape");
+  launch_episode_gather(dataset, (const long long*)image_index, rot_k, n_tasks, n_way, k_shot, t_target, channels, height, width,
+                        mean_host, std_host, x_support, x_target, (long long*)y_support, (long long*)y_target, (cudaStream_t)stream);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int maml_b200_profile(maml_b200_handle* h, int32_t enable) {
   if (!h) return fail("null argument");
   if (enable) { h->prof.reset(); g_prof = &h->prof; } else { g_prof = nullptr; }

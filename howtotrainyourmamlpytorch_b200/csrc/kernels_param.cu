@@ -490,4 +490,58 @@ void launch_running_ema_from_stats(const double* stats, long long stats_task_str
   CUDA_CHECK_LAUNCH();
 }
 
+// ---------------------------------------------------------------------------------------------
+// GPU-resident episode assembly (replaces the reference's 4-worker PIL / NumPy loader for in-memory datasets,
+// data.py:478-524): gather the sampled images of every task from the device-resident dataset [image][H][W][C],
+// apply the class's rot90 (Omniglot train augmentation, data.py:17-34 -- np.rot90, counter-clockwise) or the
+// ImageNet normalisation (data.py:100-106: ToTensor then (x - mean) / std), write NCHW support / target tensors and
+// the class-major labels.  One thread per output pixel.
+// ---------------------------------------------------------------------------------------------
+struct EpisodeArgs {
+  const float* dataset; const long long* image_index; const int* rot_k;
+  int B, N, K, T, C, H, W;
+  float mean[4], stdv[4]; int normalise;
+  float* xs; float* xt; long long* ys; long long* yt;
+};
+__global__ void episode_gather_kernel(EpisodeArgs a, int tag) {
+  pdl_prologue(28, tag);
+  const long long per_img = (long long)a.C * a.H * a.W;
+  const long long total = (long long)a.B * a.N * (a.K + a.T) * per_img;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % a.W), y = (int)((i / a.W) % a.H), c = (int)((i / ((long long)a.W * a.H)) % a.C);
+  const long long img = i / per_img;                                   // (b, n, j) flattened, j over K + T
+  const int j = (int)(img % (a.K + a.T)), n = (int)((img / (a.K + a.T)) % a.N), b = (int)(img / ((long long)(a.K + a.T) * a.N));
+  const int k = a.rot_k[b * a.N + n] & 3;
+  int sy = y, sx = x;                                                  // np.rot90(m, k): out[y][x] = in[sy][sx]
+  if (k == 1) { sy = x; sx = a.W - 1 - y; }
+  else if (k == 2) { sy = a.H - 1 - y; sx = a.W - 1 - x; }
+  else if (k == 3) { sy = a.H - 1 - x; sx = y; }
+  const long long src = a.image_index[img];
+  float v = a.dataset[((src * a.H + sy) * a.W + sx) * a.C + c];
+  if (a.normalise) v = __fdiv_rn(__fsub_rn(v, a.mean[c]), a.stdv[c]);
+  if (j < a.K) {
+    a.xs[((((long long)b * a.N + n) * a.K + j) * a.C + c) * a.H * a.W + (long long)y * a.W + x] = v;
+    if (c == 0 && y == 0 && x == 0) a.ys[((long long)b * a.N + n) * a.K + j] = n;
+  } else {
+    const int jt = j - a.K;
+    a.xt[((((long long)b * a.N + n) * a.T + jt) * a.C + c) * a.H * a.W + (long long)y * a.W + x] = v;
+    if (c == 0 && y == 0 && x == 0) a.yt[((long long)b * a.N + n) * a.T + jt] = n;
+  }
+}
+
+void launch_episode_gather(const float* dataset, const long long* image_index, const int* rot_k, int B, int N, int K, int T, int C,
+                           int H, int W, const float* mean, const float* stdv, float* xs, float* xt, long long* ys, long long* yt,
+                           cudaStream_t st) {
+  EpisodeArgs a{};
+  a.dataset = dataset; a.image_index = image_index; a.rot_k = rot_k;
+  a.B = B; a.N = N; a.K = K; a.T = T; a.C = C; a.H = H; a.W = W;
+  a.normalise = (mean && stdv) ? 1 : 0;
+  for (int c = 0; c < 4; ++c) { a.mean[c] = (a.normalise && c < C) ? mean[c] : 0.f; a.stdv[c] = (a.normalise && c < C) ? stdv[c] : 1.f; }
+  a.xs = xs; a.xt = xt; a.ys = ys; a.yt = yt;
+  const long long total = (long long)B * N * (K + T) * C * H * W;
+  launch_pdl(episode_gather_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st, a, launch_tag());
+  CUDA_CHECK_LAUNCH();
+}
+
 MAML_TRACE_SETTER(trace_set_param)

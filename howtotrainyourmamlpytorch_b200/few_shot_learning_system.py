@@ -492,8 +492,8 @@ class MAMLFewShotClassifier(nn.Module):
         return 0
 
     def time_collective(self, iters=20):
-        """Median duration (us) of the stand-alone all-reduce of a result-sized vector, CUDA events on the launching
-        stream (bench.py's per-rank ``collective_us``).  Every rank must call it."""
+        """Duration (us, minimum over ``iters``) of the stand-alone all-reduce of a result-sized vector, CUDA events on the
+        launching stream (bench.py's per-rank ``collective_us``).  Every rank must call it."""
         if self.world_size <= 1 or self._engine is None:
             return 0.0
         vec = torch.zeros_like(self._result)
@@ -511,7 +511,7 @@ class MAMLFewShotClassifier(nn.Module):
                     ev[i - 3][1].record()
             torch.cuda.synchronize()
         ts = sorted(a.elapsed_time(b) * 1e3 for a, b in ev)
-        return ts[len(ts) // 2]
+        return ts[0]      # minimum: the other samples include the launch skew between the ranks (they wait for each other)
 
     def _finish(self, head, logits, w_msl, B_global, n_t):
         """One D2H read of (loss, n_correct, logits) -- the reference syncs per task (:246,:249,:261)."""

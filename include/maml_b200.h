@@ -160,6 +160,18 @@ int maml_b200_comm_world(const maml_b200_handle* h);
 int maml_b200_all_reduce(maml_b200_handle* h, float* vec, void* stream);   /* stand-alone, in place, result_size floats */
 int64_t maml_b200_comm_status(maml_b200_handle* h);
 
+/* GPU-resident episode assembly -- replaces the reference's worker-process loader for in-memory datasets
+ * (data.py:478-524 get_set: class / sample selection is seeded host arithmetic, the image work happens here):
+ *   dataset      [n_images, H, W, C] fp32 device (what the reference keeps in RAM: Omniglot binary floats, ImageNet x/255)
+ *   image_index  [n_tasks, N, K+T] int64 device: dataset row of every sampled image (support samples first)
+ *   rot_k        [n_tasks, N] int32 device: np.rot90 count of the class (Omniglot train augmentation, data.py:17-34), 0 = none
+ *   mean/std     host arrays of C floats (ImageNet normalisation, data.py:100-106) or NULL
+ * Writes x_support [n_tasks,N,K,C,H,W], x_target [n_tasks,N,T,C,H,W] (fp32) and the class-major labels (int64). */
+int maml_b200_episode_gather(const float* dataset, const int64_t* image_index, const int32_t* rot_k, int32_t n_tasks,
+                             int32_t n_way, int32_t k_shot, int32_t t_target, int32_t channels, int32_t height, int32_t width,
+                             const float* mean_host, const float* std_host, float* x_support, float* x_target,
+                             int64_t* y_support, int64_t* y_target, void* stream);
+
 /* Debug / test hook: copy one named internal buffer of the last call to host memory.
  * Returns the number of floats the buffer holds (or <0 on error); copies at most `capacity`.
  * Names: see DESIGN.md ("debug taps").  Synchronises the device. */

@@ -191,6 +191,68 @@ def run_reference_fp64(args, iters, state32, big, kind=KIND):
     return out
 
 
+def write_reference_checkpoint(case="tiny_pp"):
+    """A checkpoint WRITTEN BY THE REFERENCE (its own save_model, few_shot_learning_system.py:399-409) after the recorded
+    train iterations of ``case`` -> tests/golden/ref_ckpt_<case>/train_model_latest.  tests/test_host_logic.py loads it
+    through this repo's load_model and compares with the post-state fixtures."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    args, argdict, iters = make_args(case)
+    model = build_reference(args, torch.float32)
+    for epoch, seed_it in iters:
+        batch = O.synthetic_batch(args, iteration=seed_it, kind=case_kind(case))
+        with contextlib.redirect_stdout(io.StringIO()):
+            model.run_train_iter(data_batch=batch, epoch=epoch)
+    d = os.path.join(ROOT, "tests", "golden", "ref_ckpt_" + case)
+    os.makedirs(d, exist_ok=True)
+    state = {"best_val_acc": 0.25, "best_val_iter": 1, "current_iter": len(iters), "best_epoch": 0,
+             "train_loss_mean": 1.5, "per_epoch_statistics": {"train_loss_mean": [1.5]}}
+    model.save_model(model_save_dir=os.path.join(d, "train_model_latest"), state=state)
+    return d
+
+
+def write_episode_fixture():
+    """Episodes drawn by the reference's own ``FewShotLearningDatasetParallel.get_set`` (data.py:478-524) from a small
+    synthetic IN-MEMORY dataset (the object is built without its file-scanning __init__) -> tests/golden/episodes.npz:
+    for Omniglot-like (1 channel, rot90 train augmentation) and ImageNet-like (3 channels, mean / std normalisation)
+    settings, several seeds, augmentation on and off.  The GPU sampler must reproduce them bit for bit."""
+    sys.path.insert(0, REF)
+    sys.argv = [sys.argv[0]]
+    import data as ref_data  # noqa: the reference, unmodified
+    from howtotrainyourmamlpytorch_b200.data import synthetic_class_images
+    blob = {}
+    for tag, dataset_name, C, binary in (("omni", "omniglot_dataset", 1, True), ("imnet", "mini_imagenet_full_size", 3, False)):
+        H = W = 8
+        classes = synthetic_class_images(12, 7, H, W, C, seed=11 if C == 1 else 12, binary=binary)
+        args, _, _ = make_args("tiny_pp")
+        args.dataset_name = dataset_name
+        args.image_channels, args.image_height, args.image_width = C, H, W
+        args.num_classes_per_set, args.num_samples_per_class, args.num_target_samples = 4, 2, 3
+        ds = object.__new__(ref_data.FewShotLearningDatasetParallel)
+        ds.args = args
+        ds.dataset_name = dataset_name
+        ds.data_loaded_in_memory = True
+        ds.image_channel = C
+        ds.num_classes_per_set, ds.num_samples_per_class, ds.num_target_samples = 4, 2, 3
+        ds.dataset_size_dict = {"train": {k: len(v) for k, v in classes.items()}}
+        ds.datasets = {"train": {k: v for k, v in classes.items()}}
+        cases = []
+        for seed in (5, 123456, 99):
+            for aug in (False, True):
+                xs, xt, ys, yt, _ = ds.get_set("train", seed=seed, augment_images=aug)
+                key = "%s/seed%d_aug%d" % (tag, seed, int(aug))
+                blob[key + "/xs"] = xs.numpy().astype(np.float32); blob[key + "/xt"] = xt.numpy().astype(np.float32)
+                blob[key + "/ys"] = np.asarray(ys, dtype=np.float32); blob[key + "/yt"] = np.asarray(yt, dtype=np.float32)
+                cases.append((seed, int(aug)))
+        blob[tag + "/cases"] = np.array(cases)
+        blob[tag + "/meta"] = np.array(json.dumps({"dataset_name": dataset_name, "C": C, "H": H, "W": W, "classes": 12,
+                                                   "samples": 7, "seed": 11 if C == 1 else 12, "binary": binary,
+                                                   "N": 4, "K": 2, "T": 3}))
+    path = os.path.join(ROOT, "tests", "golden", "episodes.npz")
+    np.savez_compressed(path, **blob)
+    return path
+
+
 def check_against_oracle(args, blob, iters, kind=KIND):
     """Immediately validate both restatements against what was just generated."""
     state = {k[len("state/"):]: torch.from_numpy(v) for k, v in blob.items() if k.startswith("state/")}
@@ -228,6 +290,12 @@ def main():
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     which = sys.argv[1:] or list(CASES.keys())
     torch.set_num_threads(8)
+    if "--episodes" in which:
+        print(write_episode_fixture())
+        return
+    if "--checkpoint" in which:
+        print(write_reference_checkpoint("tiny_pp"))
+        return
     for case in which:
         args, argdict, iters = make_args(case)
         kind = case_kind(case)

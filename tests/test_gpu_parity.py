@@ -668,3 +668,60 @@ def test_device_trace(cuda_device):
     assert len(starts) == eng.last_launch_count()
     assert sorted(tag for t, k, tag in tr if not (k & 0x80)) == list(range(len(starts)))     # one entry per graph node
     assert max(starts) - min(starts) < 1e9           # nanoseconds: one tiny iteration spans far less than a second
+
+
+def test_reference_experiment_builder_drives_the_class(cuda_device, tmp_path, monkeypatch):
+    """Level B0 as the reference uses it: the UNMODIFIED ``ExperimentBuilder`` (reference experiment_builder.py:102-164,
+    190-206, staged under baseline/_ref) runs ``train_iteration`` / ``evaluation_iteration`` / ``save_models`` on THIS
+    repo's ``MAMLFewShotClassifier`` -- losses dict keys survive ``float()``, checkpoints are written through
+    ``save_model`` and found again by ``load_model``."""
+    import sys
+    import tqdm
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "experiment_builder.py")):
+        pytest.skip("baseline/_ref is not staged")
+    from howtotrainyourmamlpytorch_b200 import MAMLFewShotClassifier
+    g = load_golden("tiny_maml")
+    a = g.args
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(sys, "argv", ["x"])
+    sys.path.insert(0, ref_dir)
+    saved_utils = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "utils" or k.startswith("utils.")}
+    try:
+        import experiment_builder as ref_builder      # the reference, unmodified
+
+        class _Data(object):                           # stands in for MetaLearningSystemDataLoader (data.py: out of scope)
+            def __init__(self, args, current_iter):
+                self.dataset = type("D", (), {"seed": {"train": 0, "val": 0}})()
+
+        a.experiment_name = os.path.join(str(tmp_path), "exp")
+        a.continue_from_epoch = "from_scratch"
+        a.max_models_to_save = 2
+        a.total_epochs_before_pause = 1
+        model = MAMLFewShotClassifier(im_shape=(2, a.image_channels, a.image_height, a.image_width), device=cuda_device, args=a)
+        model.load_state_dict(g.state())
+        eb = ref_builder.ExperimentBuilder(args=a, data=_Data, model=model, device=cuda_device)
+        xs, xt, ys, yt = g.batch(0)
+        with tqdm.tqdm(total=2) as pbar:
+            train_losses, total_losses, it = eb.train_iteration(train_sample=(xs.numpy(), xt.numpy(), ys.numpy(), yt.numpy(), 0),
+                                                                sample_idx=0, epoch_idx=0.0, total_losses={}, current_iter=0,
+                                                                pbar_train=pbar)
+            val_losses, val_total = eb.evaluation_iteration(val_sample=(xs, xt, ys, yt, 0), total_losses={}, pbar_val=pbar,
+                                                            phase="val")
+        assert it == 1
+        assert abs(train_losses["train_loss_mean"] - g.scalar("loss", 0)) <= 1e-4 * abs(g.scalar("loss", 0))
+        assert "train_accuracy_mean" in train_losses and "train_learning_rate_mean" in train_losses
+        assert "val_loss_mean" in val_losses and np.isfinite(val_losses["val_loss_mean"])
+        eb.state["current_iter"] = 1
+        eb.save_models(model=model, epoch=0, state=eb.state)
+        assert os.path.exists(os.path.join(eb.saved_models_filepath, "train_model_latest"))
+        m2 = MAMLFewShotClassifier(im_shape=(2, a.image_channels, a.image_height, a.image_width), device=cuda_device, args=a)
+        st = m2.load_model(model_save_dir=eb.saved_models_filepath, model_name="train_model", model_idx="latest")
+        assert st["current_iter"] == 1
+        for k, v in model.state_dict().items():
+            assert torch.equal(v.cpu(), m2.state_dict()[k].cpu()), k
+    finally:
+        sys.path.remove(ref_dir)
+        for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.") or k == "experiment_builder"]:
+            sys.modules.pop(k)
+        sys.modules.update(saved_utils)

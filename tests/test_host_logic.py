@@ -113,6 +113,45 @@ def test_checkpoint_save_load(tmp_path):
     assert torch.equal(m2._flat, m._flat) and m2._views_intact()
 
 
+def test_loads_a_checkpoint_written_by_the_reference():
+    """tests/golden/ref_ckpt_tiny_pp/train_model_latest was written by the UNMODIFIED reference's save_model after the
+    recorded tiny_pp iterations (oracle/gen_golden.py --checkpoint).  load_model (reference :411-424) must restore the
+    network state_dict, the Adam moments / step count and hand back the experiment state."""
+    g = load_golden("tiny_pp")
+    m = _model(g)
+    d = os.path.join(ROOT, "tests", "golden", "ref_ckpt_tiny_pp")
+    state = m.load_model(d, "train_model", "latest")
+    assert state["current_iter"] == len(g.iters) and abs(state["best_val_acc"] - 0.25) < 1e-12
+    post = g.post(len(g.iters) - 1)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(post.keys())
+    for k in post:
+        assert torch.equal(sd[k], post[k]), k
+    assert m._views_intact()
+    raw = torch.load(os.path.join(d, "train_model_latest"), map_location="cpu", weights_only=False)
+    assert m.optimizer.step_count == int(float(raw["optimizer"]["state"][0]["step"])) == len(g.iters)
+    for i, (name, p) in enumerate(m._trainable_param_list()):
+        off, size = m._flat_slices[name]
+        assert torch.equal(m._exp_avg[off:off + size].view(p.shape), raw["optimizer"]["state"][i]["exp_avg"]), name
+        assert torch.equal(m._exp_avg_sq[off:off + size].view(p.shape), raw["optimizer"]["state"][i]["exp_avg_sq"]), name
+    # and the other direction: what save_model writes is loadable by torch's own Adam / a plain nn.Module state_dict
+    out = os.path.join(d, "..", "_roundtrip_tmp")
+    try:
+        m.save_model(out, {"current_iter": 3})
+        again = torch.load(out, map_location="cpu", weights_only=False)
+        assert list(again["network"].keys()) == list(raw["network"].keys())
+        for k in raw["network"]:
+            assert torch.equal(again["network"][k], raw["network"][k]), k
+        for i in raw["optimizer"]["state"]:
+            for f in ("exp_avg", "exp_avg_sq"):
+                assert torch.equal(again["optimizer"]["state"][i][f], raw["optimizer"]["state"][i][f])
+            assert float(again["optimizer"]["state"][i]["step"]) == float(raw["optimizer"]["state"][i]["step"])
+        assert set(again["optimizer"]["param_groups"][0].keys()) == set(raw["optimizer"]["param_groups"][0].keys())
+    finally:
+        if os.path.exists(out):
+            os.remove(out)
+
+
 def test_c_abi_library_exports_every_declared_symbol():
     import __graft_entry__ as ge
     from howtotrainyourmamlpytorch_b200 import _native
