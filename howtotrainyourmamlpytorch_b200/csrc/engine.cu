@@ -590,6 +590,7 @@ static void tc_wgrad(maml_b200_handle* h, int l, int n, int nsrc, const WgSrc* s
   WgTcArgs a{};
   a.nsrc = nsrc; a.kc = h->F; a.ncols = h->F; a.rows = n * g.G; a.gw = g.gw;
   a.rows_per_chunk = cp.rows_per_chunk[l]; a.nchunks = cp.nchunks[l];
+  { static const int lite = getenv("MAML_B200_WGRAD_LITE") ? atoi(getenv("MAML_B200_WGRAD_LITE")) : 1; a.force_flush = lite ? 0 : 1; }
   for (int s = 0; s < nsrc; ++s) {
     const PassSet& ap = *src[s].a_ps; const PassSet& dp = *src[s].d_ps;
     maps.m[s * 4 + 0] = ap.ain_wg_map[l][0]; maps.m[s * 4 + 1] = ap.ain_wg_map[l][1];

@@ -93,6 +93,10 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // grid (nchunks, 3, tasks); 192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+// LITE (chunks of at most 48 K-steps over all sources -- the small Omniglot layers): no draining; the K-steps alternate
+// between the two accumulator sets (<= 48 accumulations each) and the epilogue adds them once at the end.  It needs ~90
+// registers per thread instead of 254, which matters because these CTAs share SMs with the latency-critical main chain.
+template <bool LITE>
 __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ TcMaps maps, const WgTcArgs a) {
   pdl_trigger();
   trace_mark(27, a.tag);
@@ -175,12 +179,17 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
         const uint64_t bh = make_desc_mn(base + 4 * WG_A_TILE, WG_B_TILE);                    // D_hi atoms 0, 1: N = 64
         const uint64_t bl = make_desc_mn(base + 4 * WG_A_TILE + 2 * WG_B_TILE, WG_B_TILE);    // D_lo
         for (int t = 0; t < ksteps; ++t) {
-          const int p = seg & 1;
-          if (kcount == 0) {                       // first K-step of a segment: the epilogue must have drained this set
-            mbar_wait(&acc_empty[p], (((uint32_t)seg >> 1) & 1u) ^ 1u);
-            tc_fence_after();
+          int p; uint32_t acc;
+          if constexpr (LITE) {
+            p = kcount & 1; acc = kcount >= 2 ? 1u : 0u;      // K-steps alternate between the two sets; the first two initialise them
+          } else {
+            p = seg & 1;
+            if (kcount == 0) {                     // first K-step of a segment: the epilogue must have drained this set
+              mbar_wait(&acc_empty[p], (((uint32_t)seg >> 1) & 1u) ^ 1u);
+              tc_fence_after();
+            }
+            acc = kcount > 0 ? 1u : 0u;
           }
-          const uint32_t acc = kcount > 0 ? 1u : 0u;
           const uint64_t bo = (uint64_t)(t * 64);                                             // 8 rows x 128 B in 16-byte units
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
@@ -194,12 +203,16 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
             tc_mma_tf32(tmem_base + 384u, ones_desc, bl + bo, idesc, 1u);
             bias_started = 1u;
           }
-          if (++kcount == WG_SEG_KSTEPS) { tc_commit(&acc_full[p]); ++seg; kcount = 0; }
+          ++kcount;
+          if constexpr (!LITE) {
+            if (kcount == WG_SEG_KSTEPS) { tc_commit(&acc_full[p]); ++seg; kcount = 0; }
+          }
         }
         tc_commit(&empty[stage]);
         if (++stage == WG_NSTAGE) { stage = 0; phase ^= 1u; }
       }
-      if (kcount > 0) tc_commit(&acc_full[seg & 1]);
+      if constexpr (LITE) tc_commit(&acc_full[0]);
+      else if (kcount > 0) tc_commit(&acc_full[seg & 1]);
     }
   } else {
     // ===== epilogue warps: drain every finished accumulator segment into fp32 register accumulators (IEEE adds).
@@ -207,57 +220,94 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
     // of channel c = m, rows 64..127 = (lo*hi + lo*lo) of channel c = m - 64.
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    float acc[3][64];
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-      for (int i = 0; i < 64; ++i) acc[kx][i] = 0.f;
-    for (int g = 0; g < nseg; ++g) {
-      const int p = g & 1;
-      mbar_wait(&acc_full[p], ((uint32_t)g >> 1) & 1u);
-      tc_fence_after();
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-#pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 16) {
-          uint32_t v[16];
-          tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * 192 + kx * 64 + c0), v);
-          tc_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) acc[kx][c0 + i] += __uint_as_float(v[i]);
-        }
-      }
-      // every read of this set has completed (wait::ld): hand it back to the issuer
-      tc_fence_before();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[p])) : "memory");
-    }
-    // dW[c] = rows c + rows c + 64: the upper half goes through shared memory (the stage ring is free: every MMA has
-    // completed), the lower half adds it and writes its row of each tap (F contiguous floats) to the partial buffer
     float* xch = reinterpret_cast<float*>(smem);
     const int c = m & 63;
-    if (m >= 64) {
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-        for (int i = 0; i < 64; ++i) xch[(kx * 64 + i) * WG_ACC_PITCH + c] = acc[kx][i];
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
     float* P = a.partial + (long long)task * a.partial_task_stride + (long long)chunk * a.chunk_stride;
     const int CF = a.kc * a.ncols;
-    if (m < 64 && c < a.kc) {
+    if constexpr (LITE) {
+      const bool two = (ks_src * a.nsrc) >= 2;                 // the second set exists only if a second K-step ran
+      mbar_wait(&acc_full[0], 0);
+      tc_fence_after();
+      // pass 1: rows 64..127 (lo*hi + lo*lo) -> shared memory; pass 2: rows 0..63 add them and write dW
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        const bool mine = (pass == 0) ? (m >= 64) : (m < 64);
+#pragma unroll 1
+        for (int kx = 0; kx < 3; ++kx) {
+          float* prow = P + (long long)(ky * 3 + kx) * CF + (long long)c * a.ncols;
+          for (int c0 = 0; c0 < a.ncols; c0 += 16) {
+            uint32_t v0[16], v1[16];
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kx * 64 + c0);
+            tc_ld16(ta, v0);
+            if (two) tc_ld16(ta + 192u, v1);
+            tc_wait_ld();
+            if (!mine) continue;
+            float o[16];
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        float* prow = P + (long long)(ky * 3 + kx) * CF + (long long)c * a.ncols;
+            for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(v0[i]) + (two ? __uint_as_float(v1[i]) : 0.f);
+            if (pass == 0) {
 #pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-          if (i < a.ncols) {
-            float4 o;
-            o.x = acc[kx][i] + xch[(kx * 64 + i) * WG_ACC_PITCH + c];
-            o.y = acc[kx][i + 1] + xch[(kx * 64 + i + 1) * WG_ACC_PITCH + c];
-            o.z = acc[kx][i + 2] + xch[(kx * 64 + i + 2) * WG_ACC_PITCH + c];
-            o.w = acc[kx][i + 3] + xch[(kx * 64 + i + 3) * WG_ACC_PITCH + c];
-            *reinterpret_cast<float4*>(prow + i) = o;
+              for (int i = 0; i < 16; ++i) xch[(kx * 64 + c0 + i) * WG_ACC_PITCH + c] = o[i];
+            } else if (c < a.kc) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4*>(prow + c0 + i) =
+                    make_float4(o[i] + xch[(kx * 64 + c0 + i) * WG_ACC_PITCH + c], o[i + 1] + xch[(kx * 64 + c0 + i + 1) * WG_ACC_PITCH + c],
+                                o[i + 2] + xch[(kx * 64 + c0 + i + 2) * WG_ACC_PITCH + c], o[i + 3] + xch[(kx * 64 + c0 + i + 3) * WG_ACC_PITCH + c]);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    } else {
+      float acc[3][64];
+  #pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
+  #pragma unroll
+        for (int i = 0; i < 64; ++i) acc[kx][i] = 0.f;
+      for (int g = 0; g < nseg; ++g) {
+        const int p = g & 1;
+        mbar_wait(&acc_full[p], ((uint32_t)g >> 1) & 1u);
+        tc_fence_after();
+  #pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+  #pragma unroll
+          for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t v[16];
+            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * 192 + kx * 64 + c0), v);
+            tc_wait_ld();
+  #pragma unroll
+            for (int i = 0; i < 16; ++i) acc[kx][c0 + i] += __uint_as_float(v[i]);
+          }
+        }
+        // every read of this set has completed (wait::ld): hand it back to the issuer
+        tc_fence_before();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[p])) : "memory");
+      }
+      // dW[c] = rows c + rows c + 64: the upper half goes through shared memory (the stage ring is free: every MMA has
+      // completed), the lower half adds it and writes its row of each tap (F contiguous floats) to the partial buffer
+      if (m >= 64) {
+  #pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+  #pragma unroll
+          for (int i = 0; i < 64; ++i) xch[(kx * 64 + i) * WG_ACC_PITCH + c] = acc[kx][i];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (m < 64 && c < a.kc) {
+  #pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          float* prow = P + (long long)(ky * 3 + kx) * CF + (long long)c * a.ncols;
+  #pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            if (i < a.ncols) {
+              float4 o;
+              o.x = acc[kx][i] + xch[(kx * 64 + i) * WG_ACC_PITCH + c];
+              o.y = acc[kx][i + 1] + xch[(kx * 64 + i + 1) * WG_ACC_PITCH + c];
+              o.z = acc[kx][i + 2] + xch[(kx * 64 + i + 2) * WG_ACC_PITCH + c];
+              o.w = acc[kx][i + 3] + xch[(kx * 64 + i + 3) * WG_ACC_PITCH + c];
+              *reinterpret_cast<float4*>(prow + i) = o;
+            }
           }
         }
       }
@@ -289,13 +339,16 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
 size_t wgrad_tc_smem_bytes() { return (size_t)WG_NSTAGE * WG_STAGE_BYTES + WG_ONES_BYTES + 1024; }
 
 int wgrad_tc_prepare() {
-  return cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_tc_smem_bytes()) == cudaSuccess ? 0 : 1;
+  return (cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_tc_smem_bytes()) == cudaSuccess &&
+          cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_tc_smem_bytes()) == cudaSuccess) ? 0 : 1;
 }
 
 void launch_wgrad_tc(const TcMaps& maps, const WgTcArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_WGRAD, a.alg_flops, st);
   dim3 grid(a.nchunks, 3, a.tasks);
-  launch_pdl(wgrad_tc_kernel, grid, dim3(192), wgrad_tc_smem_bytes(), st, maps, tagged(a));
+  const int ksteps = a.nsrc * ((a.rows_per_chunk + 7) / 8);
+  if (ksteps <= 48 && !a.force_flush) launch_pdl(wgrad_tc_kernel<true>, grid, dim3(192), wgrad_tc_smem_bytes(), st, maps, tagged(a));
+  else launch_pdl(wgrad_tc_kernel<false>, grid, dim3(192), wgrad_tc_smem_bytes(), st, maps, tagged(a));
   CUDA_CHECK_LAUNCH();
 }
 

@@ -39,6 +39,7 @@ void launch_pack_weights(const ParamLayout& pl, const float* theta, long long th
 struct WgTcArgs {
   int nsrc, kc, ncols, rows, gw;
   int rows_per_chunk, nchunks;          // rows_per_chunk is a multiple of 32
+  int force_flush;                      // 1: always the draining variant (env MAML_B200_WGRAD_LITE=0)
   int a_row_base[2], a_task_rows[2];    // row (in the A map) of grid row 0 of task 0 for this pass slot; rows per task
   int b_row_base[2], b_task_rows[2];
   float* partial; long long partial_task_stride; long long chunk_stride;    // [task][chunk][9 * kc * ncols + ncols]
