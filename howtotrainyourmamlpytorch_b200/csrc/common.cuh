@@ -192,6 +192,8 @@ void launch_prep_x(const float* x, float* xg, long long xg_task_stride, int task
                    cudaStream_t st);
 void launch_conv_rows(const ConvArgs& a, cudaStream_t st);
 void launch_conv0(const Conv0Args& a, cudaStream_t st);
+void conv0_set_rb(int on);
+void wgrad0_set_rb(int on);
 void launch_wgrad(const WgradArgs& a, cudaStream_t st);
 void wgrad_set_row_variant(int on);
 void launch_wgrad0(const WgradArgs& a, cudaStream_t st);

@@ -382,6 +382,8 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   g_launch_prio = getenv("MAML_B200_LAUNCH_PRIO") ? 1 : 0;
   if (const char* wr = getenv("MAML_B200_WGRAD_ROW")) wgrad_set_row_variant(atoi(wr));
   if (const char* bf = getenv("MAML_B200_BN_FUSE")) bn_set_fuse(atoi(bf));
+  if (const char* rb = getenv("MAML_B200_CONV0_RB")) conv0_set_rb(atoi(rb));
+  if (const char* rb = getenv("MAML_B200_WGRAD0_RB")) wgrad0_set_rb(atoi(rb));
   for (int l = 1; l < h->L && h->use_tc; ++l)
     if (tc_conv_rpad(h->geo[l].gw) > 256 || tc_conv_ring(h->F, h->geo[l].gw) < 2) h->use_tc = false;   // image too wide for one halo box      // F in {16, 32, 48, 64}: ragged K chunks are zero-filled by TMA
   plan_chunks(h, h->n_s, &h->plan_sup);

@@ -29,8 +29,8 @@ __device__ __forceinline__ bool row_valid(int row, int rows, int G, int gw, int 
 //   CONV_TAN_STATS: (sum zdot, sum zh * zdot)   -> tangent of the BatchNorm statistics
 // thread (ty, tx) owns rows j0 + ty*4 .. +3 and columns tx*FN .. +FN-1
 // ---------------------------------------------------------------------------------------------
-template <int FN>
-__device__ __forceinline__ void conv_epilogue(float (&acc)[4][FN], int j0, int rows, int gw, int G, int h, int w,
+template <int FN, int R = 4>
+__device__ __forceinline__ void conv_epilogue(float (&acc)[R][FN], int j0, int rows, int gw, int G, int h, int w,
                                               int mode, const float* __restrict__ bias, float* __restrict__ out,
                                               const float* __restrict__ zh, double* __restrict__ stats,
                                               double* sred) {
@@ -43,8 +43,8 @@ __device__ __forceinline__ void conv_epilogue(float (&acc)[4][FN], int j0, int r
 #pragma unroll
   for (int jn = 0; jn < FN; ++jn) { s1[jn] = 0.0; s2[jn] = 0.0; }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = j0 + ty * 4 + i;
+  for (int i = 0; i < R; ++i) {
+    const int row = j0 + ty * R + i;
     if (row < rows) {
       const long long base = (long long)row * NC + tx * FN;
       const bool valid = (mode != CONV_PLAIN) && row_valid(row, rows, G, gw, h, w);
@@ -255,8 +255,96 @@ __global__ void __launch_bounds__(256) conv0_kernel(Conv0Args a) {
                     a.stats ? a.stats + (long long)task * a.stats_stride : nullptr, sred);
 }
 
+// Register-blocked first-block conv (C0 = 1 or 3): a thread owns 8 CONSECUTIVE grid rows x FN columns.  For a filter row
+// ky the inputs of those 8 rows and the three kx taps are 10 consecutive grid positions: they are read once into
+// registers (10 * C0 broadcast loads) and feed 8 x 3 x C0 x FN FMAs, the weights of the row come as 3 * C0 vector loads
+// -- ~4 FMAs per shared-memory load instead of 12 per 7 in conv0_kernel, 128 rows per CTA instead of 64.
+// Measured on Mini-ImageNet target passes (75 images of 84x84x3 -> 48 channels per task): see DESIGN.md.
+template <int FN, int C0>
+__global__ void __launch_bounds__(256) conv0_rb_kernel(Conv0Args a) {
+  pdl_prologue(2, a.tag);
+  constexpr int NC = 16 * FN, R = 8, ROWS = 16 * R;
+  extern __shared__ float sm0[];
+  __shared__ double sred[8 * NC * 2];
+  const int task = blockIdx.y;
+  const int j0 = blockIdx.x * ROWS;
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  float* Ws = sm0;                       // [9*C0][NC]
+  float* xs = sm0 + 9 * C0 * NC;         // [(ROWS + 2*(gw+1))][C0]
+  const int halo = a.gw + 1;
+  const int wrows = ROWS + 2 * halo;
+  const float* W = a.W + (long long)task * a.w_stride;
+  for (int i = tid; i < 9 * C0 * NC; i += 256) Ws[i] = W[i];
+  const float* X = a.X + (long long)task * a.x_stride;
+  const int guard = a.gw + 2;
+  for (int i = tid; i < wrows * C0; i += 256) {
+    const int r = j0 - halo + i / C0;
+    float v = 0.f;
+    if (r >= -guard && r < a.rows + guard) v = X[(long long)(j0 - halo) * C0 + i];
+    xs[i] = v;
+  }
+  __syncthreads();
+
+  float acc[R][FN];
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int jn = 0; jn < FN; ++jn) acc[i][jn] = 0.f;
+
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    // positions ty*R + (ky-1)*gw - 1 + halo .. + R + 1 of the window (always inside it)
+    const float* xp = xs + (ty * R + (ky - 1) * a.gw - 1 + halo) * C0;
+    float xw[(R + 2) * C0];
+#pragma unroll
+    for (int i = 0; i < (R + 2) * C0; ++i) xw[i] = xp[i];
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+      for (int c = 0; c < C0; ++c) {
+        float b[FN];
+        const float* wp = Ws + ((ky * 3 + kx) * C0 + c) * NC + tx * FN;
+#pragma unroll
+        for (int jn = 0; jn < FN; ++jn) b[jn] = wp[jn];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          const float av = xw[(i + kx) * C0 + c];
+#pragma unroll
+          for (int jn = 0; jn < FN; ++jn) acc[i][jn] = fmaf(av, b[jn], acc[i][jn]);
+        }
+      }
+    }
+  }
+  conv_epilogue<FN, R>(acc, j0, a.rows, a.gw, a.G, a.h, a.w, a.mode,
+                       a.bias ? a.bias + (long long)task * a.bias_stride : nullptr,
+                       a.out + (long long)task * a.out_stride,
+                       a.zh ? a.zh + (long long)task * a.zh_stride : nullptr,
+                       a.stats ? a.stats + (long long)task * a.stats_stride : nullptr, sred);
+}
+
+static int g_conv0_rb = 1;               // env MAML_B200_CONV0_RB=0 -> the 64-row kernel
+void conv0_set_rb(int on) { g_conv0_rb = on; }
+
+template <int C0>
+static bool launch_conv0_rb(const Conv0Args& a, cudaStream_t st) {
+  dim3 grid((a.rows + 127) / 128, a.tasks);
+  const size_t smem = (size_t)(9 * C0 * a.ncols + (128 + 2 * (a.gw + 1)) * C0) * sizeof(float);
+  switch (a.ncols / 16) {
+    case 1: launch_pdl(conv0_rb_kernel<1, C0>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a)); break;
+    case 2: launch_pdl(conv0_rb_kernel<2, C0>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a)); break;
+    case 3: launch_pdl(conv0_rb_kernel<3, C0>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a)); break;
+    default: launch_pdl(conv0_rb_kernel<4, C0>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a)); break;
+  }
+  return true;
+}
+
 void launch_conv0(const Conv0Args& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_CONV0, a.alg_flops, st);
+  if (g_conv0_rb && (a.c0 == 1 || a.c0 == 3)) {
+    if (a.c0 == 1) launch_conv0_rb<1>(a, st); else launch_conv0_rb<3>(a, st);
+    CUDA_CHECK_LAUNCH();
+    return;
+  }
   dim3 grid((a.rows + 63) / 64, a.tasks);
   const size_t smem = (size_t)(9 * a.c0 * a.ncols + (64 + 2 * (a.gw + 1)) * a.c0) * sizeof(float);
   switch (a.ncols / 16) {
@@ -562,9 +650,123 @@ __global__ void __launch_bounds__(256) wgrad0_kernel(WgradArgs a) {
   }
 }
 
+// Register-blocked first-block weight gradient (C0 = 1 or 3).  Per grid row the update is the outer product
+// x[27 = tap x c] (x) dz[F]; a thread owns one filter row ky (3 kx x C0 taps) and 4 output channels: 12 * C0 accumulators.
+// The CTA's threads form NS "row streams" of 3 * F/4 threads; a stream walks CONSECUTIVE rows of the staged tile, so the
+// three x positions of a row slide by one per row: per row C0 broadcast loads + one LDS.128 of dz feed 12 * C0 FMAs
+// (wgrad0_kernel: 7 loads per 6 FMAs).  Streams are summed through shared memory in stream order (deterministic).
+template <int C0>
+__global__ void __launch_bounds__(256) wgrad0_rb_kernel(WgradArgs a) {
+  pdl_prologue(4, a.tag);
+  extern __shared__ float smw[];
+  const int task = blockIdx.y, chunk = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int Fc = a.ncols, F4 = Fc >> 2;
+  const int TPS = 3 * F4;                 // threads per row stream
+  const int NS = 256 / TPS;               // row streams
+  constexpr int L = 16;                   // consecutive rows per stream and tile
+  const int RT = NS * L;                  // rows per staged tile
+  const int stream = tid / TPS, rem = tid - stream * TPS;
+  const int ky = rem / F4, f4 = rem - ky * F4;
+  const bool active = stream < NS;
+  const int halo = a.gw + 1;
+  float* Ds = smw;                        // [RT][Fc]
+  float* Xs = smw + RT * Fc;              // [(RT + 2*halo)][C0]
+  float acc[3][C0][4];
+#pragma unroll
+  for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+    for (int c = 0; c < C0; ++c)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[kx][c][j] = 0.f;
+  float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int r_begin = chunk * a.rows_per_chunk;
+  const int r_end = min(a.rows, r_begin + a.rows_per_chunk);
+  const float* A = a.A[0] + (long long)task * a.a_stride[0];
+  const float* D = a.D[0] + (long long)task * a.d_stride[0];
+  const int guard = a.gw + 2;
+  for (int r0 = r_begin; r0 < r_end; r0 += RT) {
+    const int nr = min(RT, r_end - r0);
+    for (int i = tid; i < RT * Fc / 4; i += 256) {
+      const int r = (i * 4) / Fc;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nr) v = *reinterpret_cast<const float4*>(D + (long long)r0 * Fc + (long long)i * 4);
+      *reinterpret_cast<float4*>(Ds + i * 4) = v;                     // rows beyond nr are zero: they add nothing below
+    }
+    for (int i = tid; i < (RT + 2 * halo) * C0; i += 256) {
+      const int r = r0 - halo + i / C0;
+      float v = 0.f;
+      if (r >= -guard && r < a.rows + guard) v = A[(long long)(r0 - halo) * C0 + i];
+      Xs[i] = v;
+    }
+    __syncthreads();
+    if (active) {
+      const int rs = stream * L;                                        // first row of this stream in the tile
+      // window row index of tap (ky, kx) for tile row r: r + halo + (ky-1)*gw + (kx-1)
+      const float* xp = Xs + (rs + halo + (ky - 1) * a.gw - 1) * C0;
+      float xw[3][C0];
+#pragma unroll
+      for (int c = 0; c < C0; ++c) { xw[1][c] = xp[c]; xw[2][c] = xp[C0 + c]; }
+#pragma unroll 4
+      for (int r = 0; r < L; ++r) {
+#pragma unroll
+        for (int c = 0; c < C0; ++c) { xw[0][c] = xw[1][c]; xw[1][c] = xw[2][c]; xw[2][c] = xp[(r + 2) * C0 + c]; }
+        const float4 d = *reinterpret_cast<const float4*>(Ds + (rs + r) * Fc + f4 * 4);
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int c = 0; c < C0; ++c) {
+            acc[kx][c][0] = fmaf(xw[kx][c], d.x, acc[kx][c][0]);
+            acc[kx][c][1] = fmaf(xw[kx][c], d.y, acc[kx][c][1]);
+            acc[kx][c][2] = fmaf(xw[kx][c], d.z, acc[kx][c][2]);
+            acc[kx][c][3] = fmaf(xw[kx][c], d.w, acc[kx][c][3]);
+          }
+        bacc[0] += d.x; bacc[1] += d.y; bacc[2] += d.z; bacc[3] += d.w;
+      }
+    }
+    __syncthreads();
+  }
+  // sum the row streams in order: red[stream][(tap * C0 + c)][f] (+ bias row)
+  const int ncombo = 9 * C0;
+  float* red = smw;                        // NS * (ncombo + 1) * Fc floats (fits: the launcher sizes shared memory for both uses)
+  if (active) {
+    float* mine = red + (long long)stream * (ncombo + 1) * Fc;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int c = 0; c < C0; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mine[((ky * 3 + kx) * C0 + c) * Fc + f4 * 4 + j] = acc[kx][c][j];
+    if (ky == 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mine[ncombo * Fc + f4 * 4 + j] = bacc[j];
+    }
+  }
+  __syncthreads();
+  float* P = a.partial + (long long)task * a.partial_task_stride + (long long)chunk * a.chunk_stride;
+  for (int i = tid; i < (ncombo + 1) * Fc; i += 256) {
+    float t = 0.f;
+    for (int st = 0; st < NS; ++st) t += red[(long long)st * (ncombo + 1) * Fc + i];
+    P[i] = t;
+  }
+}
+
+static int g_wgrad0_rb = 1;              // env MAML_B200_WGRAD0_RB=0 -> wgrad0_kernel
+void wgrad0_set_rb(int on) { g_wgrad0_rb = on; }
+
 void launch_wgrad0(const WgradArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_WGRAD0, a.alg_flops, st);
   dim3 grid(a.nchunks, a.tasks);
+  if (g_wgrad0_rb && (a.kc == 1 || a.kc == 3) && a.nsrc == 1 && (a.ncols % 4) == 0) {
+    const int tps = 3 * (a.ncols / 4), ns = 256 / tps, rt = ns * 16;
+    const size_t stage = (size_t)(rt * a.ncols + (rt + 2 * (a.gw + 1)) * a.kc) * sizeof(float);
+    const size_t red = (size_t)ns * (9 * a.kc + 1) * a.ncols * sizeof(float);
+    const size_t smem = stage > red ? stage : red;
+    if (a.kc == 1) launch_pdl(wgrad0_rb_kernel<1>, dim3(grid), dim3(256), smem, st, tagged(a));
+    else launch_pdl(wgrad0_rb_kernel<3>, dim3(grid), dim3(256), smem, st, tagged(a));
+    CUDA_CHECK_LAUNCH();
+    return;
+  }
   const size_t smem = (size_t)(64 * a.ncols + (64 + 2 * (a.gw + 1)) * a.kc) * sizeof(float);
   const int need = (9 * a.kc + (256 / a.ncols) - 1) / (256 / a.ncols);      // (tap, c) combinations per thread
   if (need <= 3) launch_pdl(wgrad0_kernel<3>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a));
