@@ -67,7 +67,20 @@ struct Conv0Args {                             // first block: K = 9 * C0 is tin
   int tag;          // launch sequence number inside the iteration (device trace)
 };
 
+// Optional tail of the first-block weight-gradient kernel: the LAST CTA of a task to finish sums that task's chunks (fixed
+// order) and applies what param_reduce would have (segments 0, 1 = first-block weight and bias) -- one launch less on
+// the critical path of every backward pass.
+struct FusedReduce {
+  int mode;                                    // -1: off; PR_UPDATE / PR_SUB
+  const float* theta_in; float* theta_out; float* g_out; float* tbar;
+  const float* alpha;                          // meta + m_lslr + step: alpha of segment k at alpha[k * (S + 1)]
+  int alpha_stride;                            // S + 1
+  long long task_stride;                       // Ppad
+  unsigned* counters;                          // [tasks], zero between launches (self-resetting)
+};
+
 struct WgradArgs {
+  FusedReduce fr;
   const float* A[2]; long long a_stride[2];    // conv inputs (guarded matrices) [rows][kc]
   const float* D[2]; long long d_stride[2];    // output gradients (zero-border matrices) [rows][ncols]
   int nsrc;
@@ -197,6 +210,7 @@ void wgrad0_set_rb(int on);
 void launch_wgrad(const WgradArgs& a, cudaStream_t st);
 void wgrad_set_row_variant(int on);
 void launch_wgrad0(const WgradArgs& a, cudaStream_t st);
+bool wgrad0_can_fuse_reduce(int kc, int ncols, int nsrc);
 void launch_bnact(const BnActArgs& a, cudaStream_t st);
 void launch_bnact_tan(const BnActTanArgs& a, cudaStream_t st);
 void launch_bnbwd_reduce(const BnBwdArgs& a, cudaStream_t st);

@@ -90,6 +90,9 @@ struct maml_b200_handle {
   float *losses = nullptr, *correct = nullptr, *decay_dev = nullptr;
   double* abar = nullptr;
   long long* zero_labels = nullptr;   // [max(n_s, n_t)] zeros (label-free forward)
+  unsigned* wg0_counters = nullptr;   // [maxT] arrival counters of the fused first-block reduction (self-resetting)
+  bool fuse_wg0_reduce = false;       // env MAML_B200_WG0_FUSE=1: first-block parameter reduction fused into wgrad0 (last CTA of a
+                                      // task); measured slower than the separate launch (2.817 vs 2.788 ms), so off by default
   float* pinned = nullptr;            // host staging ring for small per-call scalars (16 slots x 32 floats)
   int pin_slot = 0;
   long long last_launches = 0;
@@ -351,6 +354,7 @@ static void carve(maml_b200_handle* h, Bump& b) {
   h->abar = b.d(T * h->pl.nseg_inner * MAML_MAX_STEPS);
   h->decay_dev = b.f(MAML_MAX_STEPS);
   h->zero_labels = (long long*)b.d(std::max(h->n_s, h->n_t));
+  h->wg0_counters = (unsigned*)b.f(h->maxT);
 }
 
 extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** out) {
@@ -384,6 +388,7 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   if (const char* bf = getenv("MAML_B200_BN_FUSE")) bn_set_fuse(atoi(bf));
   if (const char* rb = getenv("MAML_B200_CONV0_RB")) conv0_set_rb(atoi(rb));
   if (const char* rb = getenv("MAML_B200_WGRAD0_RB")) wgrad0_set_rb(atoi(rb));
+  if (const char* fz = getenv("MAML_B200_WG0_FUSE")) h->fuse_wg0_reduce = atoi(fz) != 0;
   for (int l = 1; l < h->L && h->use_tc; ++l)
     if (tc_conv_rpad(h->geo[l].gw) > 256 || tc_conv_ring(h->F, h->geo[l].gw) < 2) h->use_tc = false;   // image too wide for one halo box      // F in {16, 32, 48, 64}: ragged K chunks are zero-filled by TMA
   plan_chunks(h, h->n_s, &h->plan_sup);
@@ -550,6 +555,17 @@ static void reduce_upper_on_side(maml_b200_handle* h, const ReduceSpec& rs, cons
   cudaEventRecord(h->ev_wg, h->s_wg);
   h->wg_pending = true;
 }
+// first-block reduction fused into the weight-gradient kernel (see FusedReduce); false -> the caller launches reduce_lower
+static bool fuse_lower_into_wgrad0(maml_b200_handle* h, const ReduceSpec& rs, const float* meta, WgradArgs& w) {
+  w.fr.mode = -1;
+  if (!h->fuse_wg0_reduce || !wgrad0_can_fuse_reduce(w.kc, w.ncols, w.nsrc)) return false;
+  w.fr.mode = rs.mode;
+  w.fr.theta_in = rs.theta_in; w.fr.theta_out = rs.theta_out; w.fr.g_out = rs.g_out; w.fr.tbar = rs.tbar;
+  w.fr.alpha = meta + h->pl.m_lslr + rs.step; w.fr.alpha_stride = h->S + 1;
+  w.fr.task_stride = h->Ppad; w.fr.counters = h->wg0_counters;
+  return true;
+}
+
 static void reduce_lower(maml_b200_handle* h, const ReduceSpec& rs, const PartialDesc& pd, const float* partial,
                          const float* meta, int T, cudaStream_t st) {
   launch_param_reduce(h->pl, pd, partial, rs.mode, rs.theta_in, rs.theta_out, rs.g_out, rs.tbar, meta, rs.step, h->Ppad, T,
@@ -661,6 +677,7 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
   // reduce_upper_on_side); without one the caller reduces after this function returns.
   cudaStream_t wst = fork_wgrad ? h->s_wg : st;
   const bool split = fork_wgrad && rs != nullptr;
+  bool lower_fused = false;
   for (int l = h->L - 1; l >= 0; --l) {
     const LayerGeom& g = h->geo[l];
     BnBwdArgs b{};
@@ -687,6 +704,8 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
       w.A[0] = ps.xg; w.a_stride[0] = ps.xg_stride; w.kc = h->C;
       w.alg_flops = conv_flops(h, 0, ps.n, T, 1);
       if (split && h->L == 1) reduce_upper_on_side(h, *rs, cp.pd, partial, meta, T);
+      w.fr.mode = -1;
+      if (split) lower_fused = fuse_lower_into_wgrad0(h, *rs, meta, w);
       launch_wgrad0(w, split ? st : wst);
     } else {
       w.A[0] = AIN(ps, l, slot); w.a_stride[0] = STRIDE(ps, ain, l); w.kc = h->F;
@@ -714,8 +733,8 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
       if (split && l == 1) reduce_upper_on_side(h, *rs, cp.pd, partial, meta, T);
     }
   }
-  if (split) reduce_lower(h, *rs, cp.pd, partial, meta, T, st);
-  else if (fork_wgrad) { cudaEventRecord(h->ev_wg, h->s_wg); cudaStreamWaitEvent(st, h->ev_wg, 0); }
+  if (split && !lower_fused) reduce_lower(h, *rs, cp.pd, partial, meta, T, st);
+  else if (fork_wgrad && !split) { cudaEventRecord(h->ev_wg, h->s_wg); cudaStreamWaitEvent(st, h->ev_wg, 0); }
 }
 
 // forward-mode tangent of (support forward + support backward) at step s in direction u  =>  H u into `partial`
@@ -798,6 +817,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
     else launch_bnact_tan(b, st);
   }
   const ChunkPlan& cp = h->plan_sup;
+  bool lower_fused = false;
   join_pending(h, st);
   {
     HeadArgs& a = hd;
@@ -845,6 +865,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
       w.A[0] = sp.xg; w.a_stride[0] = sp.xg_stride; w.kc = h->C;
       w.alg_flops = conv_flops(h, 0, sp.n, T, 1);
       if (h->L == 1) reduce_upper_on_side(h, rs, cp.pd, h->sup_partial, meta, T);
+      lower_fused = fuse_lower_into_wgrad0(h, rs, meta, w);
       launch_wgrad0(w, st);
     } else {
       w.nsrc = 2;
@@ -881,7 +902,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
       if (l == 1) reduce_upper_on_side(h, rs, cp.pd, h->sup_partial, meta, T);
     }
   }
-  reduce_lower(h, rs, cp.pd, h->sup_partial, meta, T, st);
+  if (!lower_fused) reduce_lower(h, rs, cp.pd, h->sup_partial, meta, T, st);
 }
 
 static void pack_theta_step(maml_b200_handle* h, int step, int T, cudaStream_t st) {

@@ -749,10 +749,39 @@ __global__ void __launch_bounds__(256) wgrad0_rb_kernel(WgradArgs a) {
     for (int st = 0; st < NS; ++st) t += red[(long long)st * (ncombo + 1) * Fc + i];
     P[i] = t;
   }
+  if (a.fr.mode < 0) return;
+  // fused parameter-space reduction: the last CTA of this task sums the chunks in order and applies the update
+  __shared__ unsigned s_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned done = atomicAdd(&a.fr.counters[task], 1u);
+    s_last = (done == gridDim.x - 1) ? 1u : 0u;
+    if (s_last) a.fr.counters[task] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* P0 = a.partial + (long long)task * a.partial_task_stride;
+  const int nw = ncombo * Fc;                       // internal fast-weight index: [W_0 (tap, c, f) | b_0 (f)] starts at 0
+  for (int i = tid; i < nw + Fc; i += 256) {
+    float sum = 0.f;
+    for (int ch = 0; ch < a.nchunks; ++ch) sum += __ldcg(P0 + (long long)ch * a.chunk_stride + i);
+    const long long o = (long long)task * a.fr.task_stride + i;
+    if (a.fr.mode == PR_UPDATE) {
+      const float alpha = a.fr.alpha[(i < nw ? 0 : 1) * a.fr.alpha_stride];
+      a.fr.g_out[o] = sum;
+      a.fr.theta_out[o] = a.fr.theta_in[o] - alpha * sum;
+    } else {
+      a.fr.tbar[o] -= sum;
+    }
+  }
 }
 
 static int g_wgrad0_rb = 1;              // env MAML_B200_WGRAD0_RB=0 -> wgrad0_kernel
 void wgrad0_set_rb(int on) { g_wgrad0_rb = on; }
+
+bool wgrad0_can_fuse_reduce(int kc, int ncols, int nsrc) { return g_wgrad0_rb && (kc == 1 || kc == 3) && nsrc == 1 && (ncols % 4) == 0; }
 
 void launch_wgrad0(const WgradArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_WGRAD0, a.alg_flops, st);

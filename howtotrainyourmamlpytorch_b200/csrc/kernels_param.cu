@@ -203,32 +203,33 @@ __global__ void export_kernel(ExportArgs a) {
 
 __device__ void export_body(const ExportArgs& a) {
   const ParamLayout& pl = a.pl;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long LSF = (long long)pl.L * pl.S * pl.F;
   const long long total = pl.meta_size + 2 + (pl.per_step_bn ? 2 * LSF : 0);
-  if (i >= total) return;
   const double invB = 1.0 / (double)a.tasks_global;
+  // ---- range 1: the inner (fast-weight) tensors, walked in the INTERNAL order so that the per-task reads are coalesced
+  // (the reference layout is a transposition of it: [F][C][3][3] vs [tap][c][f]); one scattered 4-byte store per element
+  if (gid < pl.P) {
+    int seg;
+    const long long mi = internal_to_meta(pl, gid, &seg);
+    double val = 0.0;
+    if (a.training)
+      for (int t = 0; t < a.tasks; ++t) val += (double)a.tbar[(long long)t * a.task_stride + gid];
+    a.result[mi] = (float)(val * invB);
+    return;
+  }
+  // ---- range 2: everything else of the result vector (BatchNorm gamma / beta, LSLR, loss, accuracy count, running stats)
+  const long long i = gid - pl.P;
+  if (i >= total) return;
   double val = 0.0;
   if (i < pl.meta_size) {
-    if (!a.training) { a.result[i] = 0.f; return; }
-    // which meta segment?
     bool done = false;
     for (int l = 0; l < pl.L && !done; ++l) {
       const long long wsz = 9LL * pl.cin[l] * pl.F;
       const long long bnsz = (long long)(pl.per_step_bn ? pl.S : 1) * pl.F;
-      if (i >= pl.m_w[l] && i < pl.m_w[l] + wsz) {
-        const long long rel = i - pl.m_w[l];
-        const int tap = (int)(rel % 9);
-        const int c = (int)((rel / 9) % pl.cin[l]);
-        const int f = (int)(rel / (9LL * pl.cin[l]));
-        const long long ii = pl.w_off[l] + ((long long)tap * pl.cin[l] + c) * pl.F + f;
-        for (int t = 0; t < a.tasks; ++t) val += (double)a.tbar[(long long)t * a.task_stride + ii];
-        done = true;
-      } else if (i >= pl.m_b[l] && i < pl.m_b[l] + pl.F) {
-        const long long ii = pl.b_off[l] + (i - pl.m_b[l]);
-        for (int t = 0; t < a.tasks; ++t) val += (double)a.tbar[(long long)t * a.task_stride + ii];
-        done = true;
-      } else if ((i >= pl.m_beta[l] && i < pl.m_beta[l] + bnsz) || (i >= pl.m_gamma[l] && i < pl.m_gamma[l] + bnsz)) {
+      if ((i >= pl.m_w[l] && i < pl.m_w[l] + wsz) || (i >= pl.m_b[l] && i < pl.m_b[l] + pl.F)) return;      // range 1
+      if ((i >= pl.m_beta[l] && i < pl.m_beta[l] + bnsz) || (i >= pl.m_gamma[l] && i < pl.m_gamma[l] + bnsz)) {
+        if (!a.training) { a.result[i] = 0.f; return; }
         const bool is_gamma = (i >= pl.m_gamma[l] && i < pl.m_gamma[l] + bnsz);
         const long long rel = i - (is_gamma ? pl.m_gamma[l] : pl.m_beta[l]);
         const int f = (int)(rel % pl.F);
@@ -246,24 +247,14 @@ __device__ void export_body(const ExportArgs& a) {
     }
     if (!done) {
       const long long D = (long long)pl.pix * pl.F;
-      if (i >= pl.m_fcw && i < pl.m_fcw + (long long)pl.N * D) {
-        const long long rel = i - pl.m_fcw;
-        const int k = (int)(rel / D);
-        const int r2 = (int)(rel % D);
-        const int c = r2 / pl.pix, pix = r2 % pl.pix;
-        const long long ii = pl.fcw_off + (long long)k * D + (long long)pix * pl.F + c;
-        for (int t = 0; t < a.tasks; ++t) val += (double)a.tbar[(long long)t * a.task_stride + ii];
-      } else if (i >= pl.m_fcb && i < pl.m_fcb + pl.N) {
-        const long long ii = pl.fcb_off + (i - pl.m_fcb);
-        for (int t = 0; t < a.tasks; ++t) val += (double)a.tbar[(long long)t * a.task_stride + ii];
-      } else {
-        const long long rel = i - pl.m_lslr;
-        const int seg = (int)(rel / (pl.S + 1));
-        const int s = (int)(rel % (pl.S + 1));
-        if (s < a.num_steps)
-          for (int t = 0; t < a.tasks; ++t)
-            val += a.abar[((long long)t * pl.nseg_inner + seg) * MAML_MAX_STEPS + s];
-      }
+      if ((i >= pl.m_fcw && i < pl.m_fcw + (long long)pl.N * D) || (i >= pl.m_fcb && i < pl.m_fcb + pl.N)) return;   // range 1
+      if (!a.training) { a.result[i] = 0.f; return; }
+      const long long rel = i - pl.m_lslr;
+      const int seg = (int)(rel / (pl.S + 1));
+      const int s = (int)(rel % (pl.S + 1));
+      if (s < a.num_steps)
+        for (int t = 0; t < a.tasks; ++t)
+          val += a.abar[((long long)t * pl.nseg_inner + seg) * MAML_MAX_STEPS + s];
     }
     a.result[i] = (float)(val * invB);
     return;
@@ -315,7 +306,7 @@ __device__ void export_body(const ExportArgs& a) {
 
 void launch_export(const ExportArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_PARAM, 0.0, st);
-  const long long total = a.pl.meta_size + 2 + (a.pl.per_step_bn ? 2LL * a.pl.L * a.pl.S * a.pl.F : 0);
+  const long long total = a.pl.P + a.pl.meta_size + 2 + (a.pl.per_step_bn ? 2LL * a.pl.L * a.pl.S * a.pl.F : 0);
   launch_pdl(export_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st, tagged(a));
   CUDA_CHECK_LAUNCH();
 }
@@ -331,7 +322,7 @@ void launch_export(const ExportArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) allreduce_kernel(CommDev c, float* __restrict__ result, long long n, int tag) {
   const long long n4 = (n + 3) / 4;
-  pdl_prologue(24, tag);
+  pdl_prologue(29, tag);
   const unsigned seq = *(volatile unsigned*)c.seq;
   if (threadIdx.x < c.world && threadIdx.x != c.rank) {
     const unsigned* f = c.local_flags + threadIdx.x;
@@ -383,7 +374,7 @@ void launch_allreduce(const CommDev& c, float* result, long long n, cudaStream_t
 }
 
 __global__ void __launch_bounds__(256) publish_kernel(CommDev c, const float* __restrict__ src, long long n, int tag) {
-  pdl_prologue(25, tag);
+  pdl_prologue(30, tag);
   const unsigned seq = *(volatile unsigned*)c.seq;
   float* dst = c.local_data + (long long)(seq & 1u) * c.slot_stride;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
