@@ -45,7 +45,7 @@ def workload_desc(name, args, n_gpus):
         "config": name, "tasks_per_gpu": int(args.batch_size), "global_meta_batch": int(args.batch_size) * n_gpus,
         "second_order": bool(args.second_order), "multi_step_loss": bool(args.use_multi_step_loss_optimization),
         "per_step_bn": bool(args.per_step_bn_statistics), "parallelism": "task-sharded dp%d" % n_gpus,
-        "l2": "flushed between steps (256 MiB memset outside the per-step event pair); 8 distinct episode batches cycled",
+        "l2": "flushed between steps (256 MiB memset outside the per-step event pair); 8 distinct episode batches cycled through the two staging slots",
         "inputs": "bernoulli(0.93) 28x28x1" if args.image_channels == 1 else "normal(0,1) 84x84x3",
     }
 
@@ -360,7 +360,7 @@ def roofline_from_profile(prof, prof_steps, peaks, peak_src, value, fpt, world, 
     achieved = dom_fl / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
     all_ms, all_fl = dom_ms + c0_ms + w0_ms, dom_fl + c0_fl + w0_fl
     return {
-        "bound": "tensor", "kernel": "3x3 conv contractions of blocks >= 1: conv_tc_kernel (tcgen05, 3xTF32, cluster split-K) + wgrad kernels",
+        "bound": "tensor", "kernel": "3x3 conv contractions of blocks >= 1: conv_tc_kernel (forward / dgrad / tangent) + wgrad_tc_kernel (weight gradient), both tcgen05 3xTF32 fed by TMA",
         "achieved": achieved, "peak": peak_3x, "unit": "TFLOP/s", "frac": achieved / peak_3x,
         "traffic": traffic,
         "peak_source": peak_src + ": bf16_tflops %.1f / 2 (tf32) / 3 (3xTF32 split)" % peaks["bf16_tflops"],
