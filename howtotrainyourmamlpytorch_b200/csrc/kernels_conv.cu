@@ -6,6 +6,7 @@
 //
 // These kernels are the exact-fp32 path: used for the first block (K = 9*C_in is 9 or 27) and
 // for shapes the tcgen05 3xTF32 kernels (kernels_tc.cu) do not cover.
+#include <algorithm>
 #include "common.cuh"
 
 long long g_launch_counter = 0;
@@ -261,65 +262,125 @@ __global__ void __launch_bounds__(256) conv0_kernel(Conv0Args a) {
 // -- ~4 FMAs per shared-memory load instead of 12 per 7 in conv0_kernel, 128 rows per CTA instead of 64.
 // Measured on Mini-ImageNet target passes (75 images of 84x84x3 -> 48 channels per task): see DESIGN.md.
 template <int FN, int C0>
-__global__ void __launch_bounds__(256) conv0_rb_kernel(Conv0Args a) {
+__global__ void __launch_bounds__(256) conv0_rb_kernel(Conv0Args a, int tiles) {
   pdl_prologue(2, a.tag);
   constexpr int NC = 16 * FN, R = 8, ROWS = 16 * R;
   extern __shared__ float sm0[];
   __shared__ double sred[8 * NC * 2];
   const int task = blockIdx.y;
-  const int j0 = blockIdx.x * ROWS;
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int j00 = blockIdx.x * ROWS * tiles;         // this CTA covers `tiles` consecutive 128-row tiles: weights, the input
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;   // window and the statistics reduction are paid once
   float* Ws = sm0;                       // [9*C0][NC]
-  float* xs = sm0 + 9 * C0 * NC;         // [(ROWS + 2*(gw+1))][C0]
+  float* xs = sm0 + 9 * C0 * NC;         // [(ROWS*tiles + 2*(gw+1))][C0]
   const int halo = a.gw + 1;
-  const int wrows = ROWS + 2 * halo;
+  const int wrows = ROWS * tiles + 2 * halo;
   const float* W = a.W + (long long)task * a.w_stride;
   for (int i = tid; i < 9 * C0 * NC; i += 256) Ws[i] = W[i];
   const float* X = a.X + (long long)task * a.x_stride;
   const int guard = a.gw + 2;
   for (int i = tid; i < wrows * C0; i += 256) {
-    const int r = j0 - halo + i / C0;
+    const int r = j00 - halo + i / C0;
     float v = 0.f;
-    if (r >= -guard && r < a.rows + guard) v = X[(long long)(j0 - halo) * C0 + i];
+    if (r >= -guard && r < a.rows + guard) v = X[(long long)(j00 - halo) * C0 + i];
     xs[i] = v;
   }
+  float bv[FN];
+  {
+    const float* bias = a.bias ? a.bias + (long long)task * a.bias_stride : nullptr;
+#pragma unroll
+    for (int jn = 0; jn < FN; ++jn) bv[jn] = bias ? bias[tx * FN + jn] : 0.f;
+  }
+  double s1[FN], s2[FN];
+#pragma unroll
+  for (int jn = 0; jn < FN; ++jn) { s1[jn] = 0.0; s2[jn] = 0.0; }
+  float* out = a.out + (long long)task * a.out_stride;
+  const float* zh = a.zh ? a.zh + (long long)task * a.zh_stride : nullptr;
   __syncthreads();
 
-  float acc[R][FN];
+  for (int t = 0; t < tiles; ++t) {
+    const int j0 = j00 + t * ROWS;
+    if (j0 >= a.rows) break;
+    float acc[R][FN];
 #pragma unroll
-  for (int i = 0; i < R; ++i)
+    for (int i = 0; i < R; ++i)
 #pragma unroll
-    for (int jn = 0; jn < FN; ++jn) acc[i][jn] = 0.f;
-
+      for (int jn = 0; jn < FN; ++jn) acc[i][jn] = 0.f;
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-    // positions ty*R + (ky-1)*gw - 1 + halo .. + R + 1 of the window (always inside it)
-    const float* xp = xs + (ty * R + (ky - 1) * a.gw - 1 + halo) * C0;
-    float xw[(R + 2) * C0];
+    for (int ky = 0; ky < 3; ++ky) {
+      // positions t*ROWS + ty*R + (ky-1)*gw - 1 + halo .. + R + 1 of the window (always inside it)
+      const float* xp = xs + (t * ROWS + ty * R + (ky - 1) * a.gw - 1 + halo) * C0;
+      float xw[(R + 2) * C0];
 #pragma unroll
-    for (int i = 0; i < (R + 2) * C0; ++i) xw[i] = xp[i];
+      for (int i = 0; i < (R + 2) * C0; ++i) xw[i] = xp[i];
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
+      for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
-      for (int c = 0; c < C0; ++c) {
-        float b[FN];
-        const float* wp = Ws + ((ky * 3 + kx) * C0 + c) * NC + tx * FN;
+        for (int c = 0; c < C0; ++c) {
+          float b[FN];
+          const float* wp = Ws + ((ky * 3 + kx) * C0 + c) * NC + tx * FN;
 #pragma unroll
-        for (int jn = 0; jn < FN; ++jn) b[jn] = wp[jn];
+          for (int jn = 0; jn < FN; ++jn) b[jn] = wp[jn];
 #pragma unroll
-        for (int i = 0; i < R; ++i) {
-          const float av = xw[(i + kx) * C0 + c];
+          for (int i = 0; i < R; ++i) {
+            const float av = xw[(i + kx) * C0 + c];
 #pragma unroll
-          for (int jn = 0; jn < FN; ++jn) acc[i][jn] = fmaf(av, b[jn], acc[i][jn]);
+            for (int jn = 0; jn < FN; ++jn) acc[i][jn] = fmaf(av, b[jn], acc[i][jn]);
+          }
         }
       }
     }
+    // store + thread-local fp64 statistics; validity of the 8 consecutive rows is tracked incrementally (one division)
+    int row = j0 + ty * R;
+    int rr = row % a.G;
+    int yy = rr / a.gw, xx = rr - yy * a.gw;
+#pragma unroll
+    for (int i = 0; i < R; ++i, ++row) {
+      if (row < a.rows) {
+        const long long base = (long long)row * NC + tx * FN;
+        const bool valid = (a.mode != CONV_PLAIN) && yy >= 1 && yy <= a.h && xx >= 1 && xx <= a.w;
+        float v[FN];
+#pragma unroll
+        for (int jn = 0; jn < FN; ++jn) v[jn] = acc[i][jn] + bv[jn];
+        if constexpr (FN == 4) *reinterpret_cast<float4*>(out + base) = make_float4(v[0], v[1], v[2], v[3]);
+        else if constexpr (FN == 2) *reinterpret_cast<float2*>(out + base) = make_float2(v[0], v[1]);
+        else {
+#pragma unroll
+          for (int jn = 0; jn < FN; ++jn) out[base + jn] = v[jn];
+        }
+        if (valid) {
+#pragma unroll
+          for (int jn = 0; jn < FN; ++jn) {
+            s1[jn] += (double)v[jn];
+            s2[jn] += (a.mode == CONV_FWD_STATS) ? (double)v[jn] * (double)v[jn] : (double)zh[base + jn] * (double)v[jn];
+          }
+        }
+      }
+      if (++xx == a.gw) { xx = 0; if (++yy == a.G / a.gw) yy = 0; }
+    }
   }
-  conv_epilogue<FN, R>(acc, j0, a.rows, a.gw, a.G, a.h, a.w, a.mode,
-                       a.bias ? a.bias + (long long)task * a.bias_stride : nullptr,
-                       a.out + (long long)task * a.out_stride,
-                       a.zh ? a.zh + (long long)task * a.zh_stride : nullptr,
-                       a.stats ? a.stats + (long long)task * a.stats_stride : nullptr, sred);
+  if (a.mode != CONV_PLAIN) {
+    const int warp = tid >> 5;
+#pragma unroll
+    for (int jn = 0; jn < FN; ++jn) {
+      s1[jn] += __shfl_xor_sync(0xffffffffu, s1[jn], 16);
+      s2[jn] += __shfl_xor_sync(0xffffffffu, s2[jn], 16);
+    }
+    if ((tid & 16) == 0) {
+#pragma unroll
+      for (int jn = 0; jn < FN; ++jn) {
+        sred[(warp * NC + tx * FN + jn) * 2 + 0] = s1[jn];
+        sred[(warp * NC + tx * FN + jn) * 2 + 1] = s2[jn];
+      }
+    }
+    __syncthreads();
+    double* stats = a.stats + (long long)task * a.stats_stride;
+    for (int c = tid; c < NC * 2; c += 256) {
+      double tt = 0.0;
+#pragma unroll
+      for (int wq = 0; wq < 8; ++wq) tt += sred[wq * NC * 2 + c];
+      atomicAdd(&stats[c], tt);
+    }
+  }
 }
 
 static int g_conv0_rb = 1;               // env MAML_B200_CONV0_RB=0 -> the 64-row kernel
@@ -327,13 +388,17 @@ void conv0_set_rb(int on) { g_conv0_rb = on; }
 
 template <int C0>
 static bool launch_conv0_rb(const Conv0Args& a, cudaStream_t st) {
-  dim3 grid((a.rows + 127) / 128, a.tasks);
-  const size_t smem = (size_t)(9 * C0 * a.ncols + (128 + 2 * (a.gw + 1)) * C0) * sizeof(float);
+  // tiles per CTA: as many as keep >= ~3 CTAs per SM in flight (fixed per-CTA cost -- weights, window, fp64 statistics
+  // reduction -- is then paid once per `tiles` x 128 rows); 1 for the small launches that sit on the latency-critical chain
+  const long long t128 = (a.rows + 127) / 128;
+  int tiles = (int)std::min<long long>(8, std::max<long long>(1, t128 * a.tasks / (3 * 148)));
+  dim3 grid((unsigned)((t128 + tiles - 1) / tiles), a.tasks);
+  const size_t smem = (size_t)(9 * C0 * a.ncols + (128 * tiles + 2 * (a.gw + 1)) * C0) * sizeof(float);
   switch (a.ncols / 16) {
-    case 1: launch_pdl(conv0_rb_kernel<1, C0>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a)); break;
-    case 2: launch_pdl(conv0_rb_kernel<2, C0>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a)); break;
-    case 3: launch_pdl(conv0_rb_kernel<3, C0>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a)); break;
-    default: launch_pdl(conv0_rb_kernel<4, C0>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a)); break;
+    case 1: launch_pdl(conv0_rb_kernel<1, C0>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a), tiles); break;
+    case 2: launch_pdl(conv0_rb_kernel<2, C0>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a), tiles); break;
+    case 3: launch_pdl(conv0_rb_kernel<3, C0>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a), tiles); break;
+    default: launch_pdl(conv0_rb_kernel<4, C0>, dim3(grid), dim3(256), (size_t)(smem), st, tagged(a), tiles); break;
   }
   return true;
 }
