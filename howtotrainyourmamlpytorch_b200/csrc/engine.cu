@@ -383,7 +383,7 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   if (const char* sk = getenv("MAML_B200_TC_STACK")) h->tc_stack = atoi(sk) != 0;
   if (const char* wt = getenv("MAML_B200_WGRAD_TC")) h->wgrad_tc = atoi(wt) != 0;
   if (const char* sp = getenv("MAML_B200_TC_SPLIT")) tc_conv_set_split(atoi(sp));
-  g_launch_prio = getenv("MAML_B200_LAUNCH_PRIO") ? 1 : 0;
+  g_launch_prio = (getenv("MAML_B200_LAUNCH_PRIO") && atoi(getenv("MAML_B200_LAUNCH_PRIO")) != 0) ? 1 : 0;
   if (const char* wr = getenv("MAML_B200_WGRAD_ROW")) wgrad_set_row_variant(atoi(wr));
   if (const char* bf = getenv("MAML_B200_BN_FUSE")) bn_set_fuse(atoi(bf));
   if (const char* rb = getenv("MAML_B200_CONV0_RB")) conv0_set_rb(atoi(rb));
@@ -406,7 +406,7 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   e = cudaMallocHost((void**)&h->pinned, 16 * 32 * sizeof(float));
   if (e != cudaSuccess) { cudaFree(h->ws); delete h; return fail(std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
   h->use_graphs = !(cfg->reserved & 4) && !getenv("MAML_B200_NO_GRAPH");
-  g_use_pdl = getenv("MAML_B200_PDL") ? 1 : 0;   // measured: no gain inside the captured graph (4.16 vs 4.02 ms), so off by default
+  g_use_pdl = (getenv("MAML_B200_PDL") && atoi(getenv("MAML_B200_PDL")) != 0) ? 1 : 0;   // measured twice: slower inside the captured graph (round 1: 4.16 vs 4.02 ms; round 2: 2.95 vs 2.77 ms), so off by default
   // Priorities: the support chain (capture stream) is the critical path; the weight-gradient and target streams only
   // have to finish by the end of a step.  Their many small CTAs would otherwise occupy every SM and keep the
   // whole-SM tcgen05 conv CTAs of the critical path waiting (measured: ~20 us per step).
