@@ -220,6 +220,7 @@ void launch_bnbwd_tan_apply(const BnBwdTanArgs& a, cudaStream_t st);
 void launch_bnbwd(const BnBwdArgs& a, cudaStream_t st);          // reduce + apply (one cluster kernel for small blocks)
 void launch_bnbwd_tan(const BnBwdTanArgs& a, cudaStream_t st);
 void bn_set_fuse(int on);
+void bn_set_fuse_max(int v);
 bool tail_fusable(const BnGeom& g, int n_rows, int rows_per_cta);
 void tail_set_onchip(int on);
 void launch_tail_fused(const BnActArgs& fa, const HeadArgs& ha, const BnBwdArgs& ba, cudaStream_t st);

@@ -386,6 +386,7 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   g_launch_prio = (getenv("MAML_B200_LAUNCH_PRIO") && atoi(getenv("MAML_B200_LAUNCH_PRIO")) != 0) ? 1 : 0;
   if (const char* wr = getenv("MAML_B200_WGRAD_ROW")) wgrad_set_row_variant(atoi(wr));
   if (const char* bf = getenv("MAML_B200_BN_FUSE")) bn_set_fuse(atoi(bf));
+  if (const char* bf = getenv("MAML_B200_BN_FUSE_MAX")) bn_set_fuse_max(atoi(bf));
   if (const char* rb = getenv("MAML_B200_CONV0_RB")) conv0_set_rb(atoi(rb));
   if (const char* rb = getenv("MAML_B200_WGRAD0_RB")) wgrad0_set_rb(atoi(rb));
   if (const char* fz = getenv("MAML_B200_WG0_FUSE")) h->fuse_wg0_reduce = atoi(fz) != 0;

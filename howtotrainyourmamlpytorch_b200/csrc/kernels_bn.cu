@@ -361,11 +361,13 @@ __global__ void __launch_bounds__(256) bnbwd_fused_kernel(BnBwdArgs a) {
 }
 
 // cluster size for the fused kernels: enough CTAs for <= 4 windows per thread, else 0 (two-kernel path)
+static int g_bn_fuse_max = 32;       // env MAML_B200_BN_FUSE_MAX: largest "CTAs needed at one window per thread" still fused
+void bn_set_fuse_max(int v) { g_bn_fuse_max = v; }
 static inline int bn_fused_cluster(const BnGeom& g) {
   const int F4 = g.F / 4, wpb = 256 / F4;
   const int NW = g.n * ((g.h + 1) / 2) * ((g.w + 1) / 2);
   const int need = (NW + wpb - 1) / wpb;
-  if (need > 32) return 0;
+  if (need > g_bn_fuse_max) return 0;
   int cl = 1;
   while (cl < need && cl < 8) cl <<= 1;
   return cl;
