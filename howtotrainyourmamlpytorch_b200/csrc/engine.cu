@@ -70,7 +70,14 @@ struct PassSet {            // activation buffers of one kind of pass (support: 
 };
 
 struct ChunkPlan { int rows_per_chunk[MAML_MAX_LAYERS]; int nchunks[MAML_MAX_LAYERS]; PartialDesc pd; long long size; int head_groups; };
-static const int HEAD_ROWS_PER_CTA = 16;
+// rows of a batch one head CTA handles: small batches (<= 16 rows: the Omniglot 5-way passes) stay in ONE CTA so that the
+// last block / head / BatchNorm-backward fusion applies; larger ones are cut into groups of 4 rows -- the head of a 75-row
+// Mini-ImageNet target pass ran as 5 CTAs per task (latency-bound, 1.0 -> 0.55 ms per iteration with 19)
+static inline int head_rows(int n) {
+  static const int forced = getenv("MAML_B200_HEAD_ROWS") ? atoi(getenv("MAML_B200_HEAD_ROWS")) : 0;
+  if (forced > 0) return forced;
+  return n <= 16 ? 16 : 4;
+}
 
 struct maml_b200_handle {
   maml_b200_config cfg;
@@ -216,7 +223,7 @@ static void plan_chunks(maml_b200_handle* h, int n, ChunkPlan* cp) {
     off += cs * nch;
   }
   // head: one gradient chunk per row group of the batch (gW [N][D] followed by gb [N] inside each chunk)
-  const int hg = (n + HEAD_ROWS_PER_CTA - 1) / HEAD_ROWS_PER_CTA;
+  const int hg = (n + head_rows(n) - 1) / head_rows(n);
   const long long hcs = (long long)h->N * h->D + h->N;
   cp->head_groups = hg;
   cp->pd.off[2 * h->L] = off; cp->pd.cstride[2 * h->L] = hcs; cp->pd.nchunks[2 * h->L] = hg;
@@ -748,7 +755,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
   // consumers (bnact_tan / bnbwd_tan) add the two addends.  The main chain keeps the single-pair half: 18 instead of
   // 36 stages per tile on the critical path.
   const bool split = h->use_tc && h->tan_split;
-  const bool fuse_tail = h->tail_fuse && tail_fusable(bn_geom(h, h->L - 1, sp.n), sp.n, HEAD_ROWS_PER_CTA);
+  const bool fuse_tail = h->tail_fuse && tail_fusable(bn_geom(h, h->L - 1, sp.n), sp.n, head_rows(sp.n));
   BnActTanArgs last_act{};
   HeadArgs hd{};
   if (split) {
@@ -829,7 +836,7 @@ static void tangent_pass(maml_b200_handle* h, int s, const float* theta, const f
     a.uW = u + h->pl.fcw_off; a.ub = u + h->pl.fcb_off; a.u_stride = h->Ppad;
     a.y = y_support; a.y_stride = h->n_s;
     a.gW = h->sup_partial + cp.pd.off[2 * h->L]; a.gb = h->sup_partial + cp.pd.off[2 * h->L + 1]; a.g_stride = cp.pd.task_stride;
-    a.g_chunk_stride = cp.pd.cstride[2 * h->L]; a.rows_per_cta = HEAD_ROWS_PER_CTA;
+    a.g_chunk_stride = cp.pd.cstride[2 * h->L]; a.rows_per_cta = head_rows(a.n);
     a.df = DP(tn, h->L - 1, 0); a.df_stride = STRIDE(tn, dp, h->L - 1);
     a.tasks = T;
     if (!fuse_tail) launch_head(a, st);
@@ -952,7 +959,7 @@ static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it,
   for (int s = 0; s < it->num_steps; ++s) {
     const float* th = h->theta + (long long)s * TP;
     float* th_next = h->theta + (long long)(s + 1) * TP;
-    const bool fuse_tail = h->tail_fuse && tail_fusable(bn_geom(h, h->L - 1, h->n_s), h->n_s, HEAD_ROWS_PER_CTA);
+    const bool fuse_tail = h->tail_fuse && tail_fusable(bn_geom(h, h->L - 1, h->n_s), h->n_s, head_rows(h->n_s));
     BnActArgs last_act{};
     forward_pass(h, h->sup, s, th, s, meta, s, PASS_SUP_FWD, T, st, fuse_tail ? &last_act : nullptr);
     join_pending(h, st);
@@ -965,7 +972,7 @@ static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it,
       a.y = ys; a.y_stride = h->n_s;
       a.gW = h->sup_partial + h->plan_sup.pd.off[2 * h->L]; a.gb = h->sup_partial + h->plan_sup.pd.off[2 * h->L + 1];
       a.g_stride = h->plan_sup.pd.task_stride;
-      a.g_chunk_stride = h->plan_sup.pd.cstride[2 * h->L]; a.rows_per_cta = HEAD_ROWS_PER_CTA;
+      a.g_chunk_stride = h->plan_sup.pd.cstride[2 * h->L]; a.rows_per_cta = head_rows(a.n);
       a.df = DP(h->sup, h->L - 1, s); a.df_stride = STRIDE(h->sup, dp, h->L - 1);
       a.tasks = T;
       if (!fuse_tail) launch_head(a, st);
@@ -991,7 +998,7 @@ static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it,
       a.f = AIN(h->tgt, h->L, ts); a.f_stride = STRIDE(h->tgt, ain, h->L);
       a.Wfc = th_next + h->pl.fcw_off; a.bfc = th_next + h->pl.fcb_off; a.theta_stride = h->Ppad;
       a.y = yt; a.y_stride = h->n_t;
-      a.loss_out = h->losses + s; a.loss_stride = MAML_MAX_STEPS; a.rows_per_cta = HEAD_ROWS_PER_CTA;
+      a.loss_out = h->losses + s; a.loss_stride = MAML_MAX_STEPS; a.rows_per_cta = head_rows(a.n);
       if (s == last_t) {
         a.logits_out = last_logits; a.logits_stride = (long long)h->n_t * h->N;
         a.correct_out = h->correct; a.correct_stride = 1;
@@ -1147,7 +1154,7 @@ extern "C" int maml_b200_net_forward(maml_b200_handle* h, int32_t n_tasks, int32
   a.f = AIN(h->tgt, h->L, 0); a.f_stride = STRIDE(h->tgt, ain, h->L);
   a.Wfc = h->theta + h->pl.fcw_off; a.bfc = h->theta + h->pl.fcb_off; a.theta_stride = h->Ppad;
   a.y = h->zero_labels; a.y_stride = 0;
-  a.loss_out = h->losses; a.loss_stride = MAML_MAX_STEPS; a.rows_per_cta = HEAD_ROWS_PER_CTA;
+  a.loss_out = h->losses; a.loss_stride = MAML_MAX_STEPS; a.rows_per_cta = head_rows(a.n);
   a.logits_out = logits; a.logits_stride = (long long)h->n_t * h->N;
   a.tasks = T;
   launch_head(a, st);
@@ -1184,7 +1191,7 @@ extern "C" int maml_b200_net_backward(maml_b200_handle* h, int32_t n_tasks, int3
   a.dl_ext = dlogits; a.dl_ext_stride = (long long)h->n_t * h->N;
   a.gW = tpart + h->plan_tgt.pd.off[2 * h->L]; a.gb = tpart + h->plan_tgt.pd.off[2 * h->L + 1];
   a.g_stride = h->plan_tgt.pd.task_stride; a.g_chunk_stride = h->plan_tgt.pd.cstride[2 * h->L];
-  a.rows_per_cta = HEAD_ROWS_PER_CTA;
+  a.rows_per_cta = head_rows(a.n);
   a.df = DP(h->tgt, h->L - 1, 0); a.df_stride = STRIDE(h->tgt, dp, h->L - 1);
   a.tasks = T;
   launch_head(a, st);

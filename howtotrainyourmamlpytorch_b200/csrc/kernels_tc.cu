@@ -30,7 +30,6 @@
 
 namespace {
 
-constexpr int TC_A_BYTES = 128 * 128;          // 128 rows x 32 fp32 (one 128B swizzle span per row)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -138,18 +137,13 @@ __device__ __forceinline__ void splitk_reduce(uint32_t tile_local, int zrank, in
   }
 }
 
-__device__ __forceinline__ int tap_shift_tc(int tap, int gw) { return (tap / 3 - 1) * gw + (tap % 3 - 1); }
 
 // K-major SWIZZLE_128B descriptor whose start is `row_off` rows into a 1024B-aligned tile.  Measured on B200: the
 // 128B swizzle XOR is a function of the ABSOLUTE shared-memory address bits [7,10) (as for TMA writes), so a start
 // address moved by row_off * 128 B addresses rows row_off .. row_off+127 of the tile correctly with the
 // matrix-base-offset field left at 0; setting base_offset = row_off mod 8 (bo_mode = 1) gives wrong results.
 // This is what lets ONE halo tile serve all nine filter taps.
-__device__ __forceinline__ uint64_t make_desc_sw128_rows(uint32_t tile_base, int row_off, int kbyte, int bo_mode) {
-  uint64_t d = make_desc_sw128(tile_base + (uint32_t)row_off * 128u + (uint32_t)kbyte);
-  if (bo_mode) d |= (uint64_t)(row_off & 7) << 49;
-  return d;
-}
+// (the issuer below adds row_off * 128 B >> 4 to the descriptor's address field)
 
 // debug timeline (clock64 at pipeline milestones of CTA (0,0)); written only when TcConvArgs::timeline != 0
 __device__ long long g_tc_timeline[16];

@@ -406,6 +406,11 @@ class MAMLFewShotClassifier(nn.Module):
                         second_order=second, training=training_phase, target_mask=mask, target_weight=weights,
                         meta=self._flat, xs=xs, ys=ys, xt=xt, yt=yt, result=self._result, last_logits=logits)
             reduced = self._all_reduce_result(eng)
+            if self.world_size > 1 and self._comm_mode == "peer":
+                # a rank that waited 30 s for a peer gives up and flags it; surface that instead of training on garbage
+                self._comm_checks = getattr(self, "_comm_checks", 0) + 1
+                if self._comm_checks % 512 == 0 and eng.comm_status() != 0:
+                    raise RuntimeError("peer-memory all-reduce timed out waiting for another rank (status %#x)" % eng.comm_status())
             ms = eng.meta_size
             out[:2].copy_(reduced[ms:ms + 2])
             head = out
