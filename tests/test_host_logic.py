@@ -164,3 +164,32 @@ def test_c_abi_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert sorted(_native.EXPORTED_SYMBOLS) == declared
     assert lib.maml_b200_abi_version() == _native.ABI_VERSION
+
+
+def test_bench_flop_model_matches_baseline_table():
+    """bench.py's algorithmic FLOPs per task (the numerator of `roofline.achieved`) against BASELINE.md section 3."""
+    import importlib.util
+    from howtotrainyourmamlpytorch_b200 import make_args
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    table = {"omniglot_maml_5w1s": 4.594, "omniglot_mamlpp_5w1s": 5.754, "mini_imagenet_mamlpp_5w1s": 144.60,
+             "mini_imagenet_mamlpp_5w5s": 237.95, "omniglot_mamlpp_20w5s": 91.88}
+    for name, gflop in table.items():
+        got = bench.flops_per_task(make_args(name)) / 1e9
+        assert abs(got - gflop) <= 0.005 * gflop, (name, got, gflop)
+
+
+def test_batch_shape_and_label_validation():
+    """The engine reads raw pointers: a batch whose shape does not match args, or labels outside [0, N), must be rejected
+    on the host -- checked before any device work, so it is testable without a GPU."""
+    g = load_golden("tiny_pp")
+    m = _model(g)
+    xs, xt, ys, yt = g.batch(0)
+    with pytest.raises(ValueError):
+        m._check_batch([xs[:, :, :1], xt, ys, yt])                 # wrong K
+    with pytest.raises(ValueError):
+        m._check_batch([xs[..., :-1], xt, ys, yt])                 # wrong W
+    with pytest.raises(ValueError):
+        m._check_batch([xs, xt, ys])
+    assert m._check_batch([xs, xt, ys, yt]) == xs.shape[0]
