@@ -336,8 +336,10 @@ class MAMLFewShotClassifier(nn.Module):
         for t, d, dev in zip(ts, want, on_dev):
             if d == torch.int64:
                 t = t.to(torch.float32).long() if t.is_floating_point() else t.long()      # reference :357-358
-                if not dev and t.numel() and (int(t.min()) < 0 or int(t.max()) >= int(self.args.num_classes_per_set)):
-                    raise ValueError("labels must lie in [0, num_classes_per_set)")
+                if not dev and t.numel():
+                    lo, hi = torch.aminmax(t)
+                    if int(lo) < 0 or int(hi) >= int(self.args.num_classes_per_set):
+                        raise ValueError("labels must lie in [0, num_classes_per_set)")
             else:
                 t = t.to(d)
             conv.append(t)
