@@ -13,7 +13,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libmaml_b200.so")
 SOURCES = ["kernels_conv.cu", "kernels_bn.cu", "kernels_head.cu", "kernels_param.cu", "kernels_tc.cu", "kernels_wgrad_tc.cu", "engine.cu"]
-HEADERS = ["common.cuh", "tc_common.cuh", "head_body.cuh", os.path.join("..", "..", "include", "maml_b200.h")]
+HEADERS = ["common.cuh", "tc_common.cuh", "head_body.cuh", "head_body_impl.inc", os.path.join("..", "..", "include", "maml_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

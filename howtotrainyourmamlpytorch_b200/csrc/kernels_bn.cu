@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(256) tail_fused_kernel(BnActArgs fa, HeadArgs 
   WinIter it(g);
   bnact_phase(fa, g, task, 0, 1, it, s_mu, s_r, s_g, s_b);
   __syncthreads();
-  head_body(ha, task, 0, smh, s_rowloss, s_rowcorrect);
+  head_body<true>(ha, task, 0, smh, s_rowloss, s_rowcorrect);
   __syncthreads();
   double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
   bnbwd_reduce_phase(ba, g, task, 0, 1, it, s_g, s_b, s1, s2);
@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(256) tail_tan_fused_kernel(BnActTanArgs fa, He
   WinIter it(g);
   bnact_tan_phase(fa, g, task, 0, 1, it, s_r, s_g, s_b, s_md, s_q);
   __syncthreads();
-  head_body(ha, task, 0, smh, s_rowloss, s_rowcorrect);
+  head_body<true>(ha, task, 0, smh, s_rowloss, s_rowcorrect);
   __syncthreads();
   double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
   bnbwd_tan_reduce_phase(ba, g, task, 0, 1, it, s_g, s_b, s1, s2);
@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(256) tail_onchip_kernel(BnActArgs fa, HeadArgs
     hs.f = s_f; hs.f_stride = 0;
     hs.Wfc = s_W; hs.bfc = s_bfc; hs.theta_stride = 0;
     hs.df = s_df; hs.df_stride = 0;
-    head_body(hs, task, 0, smh, s_rowloss, s_rowcorrect);
+    head_body<true>(hs, task, 0, smh, s_rowloss, s_rowcorrect);
   }
   __syncthreads();
   {
