@@ -219,6 +219,7 @@ void launch_bnbwd_tan_reduce(const BnBwdTanArgs& a, cudaStream_t st);
 void launch_bnbwd_tan_apply(const BnBwdTanArgs& a, cudaStream_t st);
 void launch_bnbwd(const BnBwdArgs& a, cudaStream_t st);          // reduce + apply (one cluster kernel for small blocks)
 void launch_bnbwd_tan(const BnBwdTanArgs& a, cudaStream_t st);
+extern int g_bn_cta_cap;            // see kernels_bn.cu (bn_grid)
 void bn_set_fuse(int on);
 void bn_set_fuse_max(int v);
 bool tail_fusable(const BnGeom& g, int n_rows, int rows_per_cta);
@@ -299,7 +300,13 @@ enum { PASS_SUP_FWD = 0, PASS_SUP_BWD = 1, PASS_TGT_FWD = 2, PASS_TGT_BWD = 3, P
 // flushed.  Measured on B200 inside the captured CUDA graph: no gain (4.16 ms vs 4.02 ms per iteration) -- the kernels'
 // own durations, not the launch gaps, set the critical path -- so the attribute is OFF unless MAML_B200_PDL=1.
 // ---------------------------------------------------------------------------------------------
-extern int g_use_pdl;
+extern int g_use_pdl;               // 0: off, 1: every launch, 2: only launches on the iteration's main chain (g_pdl_main_stream),
+                                    // 3: every stream except the weight-gradient side stream (g_pdl_wg_stream)
+extern cudaStream_t g_pdl_main_stream, g_pdl_wg_stream;
+extern int g_pdl_cluster;           // 1: cluster launches (split-K convs, fused BatchNorm backward) take the attribute too
+inline bool pdl_allowed(cudaStream_t st) {
+  return g_use_pdl == 1 || (g_use_pdl == 2 && st == g_pdl_main_stream) || (g_use_pdl == 3 && st != g_pdl_wg_stream);
+}
 extern int g_launch_prio;
 
 // Device-side launch trace (debug; maml_b200_trace): CTA (0,0,0) of every kernel appends (globaltimer ns << 8 | kernel
@@ -338,7 +345,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_allowed(st) ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (g_launch_prio) {          // explicit per-launch priority = the stream's (captured graph nodes keep it)
     int prio = 0;

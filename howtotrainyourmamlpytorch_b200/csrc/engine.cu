@@ -113,6 +113,12 @@ struct maml_b200_handle {
   bool tail_fuse = true;                              // env MAML_B200_TAIL_FUSE=0: last block / head / its BN backward as separate kernels
   bool tan_split = true;                              // env MAML_B200_TAN_SPLIT=0: two-source tangent convs on the main chain
   bool use_graphs = true;
+  cudaStream_t main_stream = nullptr;                 // stream of the iteration's main chain while it is being enqueued
+  int pdl_mode = 0, pdl_cluster = 0;                  // programmatic dependent launch (see common.cuh), chosen per handle
+  int nb_main = 8, wg_nstage = 4;                     // shared-memory ring depths of the tcgen05 conv / weight-gradient kernels (see maml_b200_create)
+  int nb_side = 0;                                    // env MAML_B200_TC_NB_SIDE: B ring depth cap of side-stream convs (0 = the global cap)
+  int side_bn_cap = 0;                                // env MAML_B200_BN_SIDE_CAP: CTA cap of grid-stride BatchNorm launches on side streams
+  int split_cap_side = 0, split_cap_l1 = 0;           // env MAML_B200_TC_SPLIT_SIDE / _L1: split-K caps (0 = none) for side-stream convs / main-chain block 1
   // results produced on s_wg (upper-block parameter reduction, weight packs) that the main chain has not joined yet:
   // consumed right before the first kernel that reads them (block 1's convolution / the head)
   bool wg_pending = false;
@@ -390,6 +396,11 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   if (const char* sk = getenv("MAML_B200_TC_STACK")) h->tc_stack = atoi(sk) != 0;
   if (const char* wt = getenv("MAML_B200_WGRAD_TC")) h->wgrad_tc = atoi(wt) != 0;
   if (const char* sp = getenv("MAML_B200_TC_SPLIT")) tc_conv_set_split(atoi(sp));
+  tc_conv_set_ring_fit(getenv("MAML_B200_TC_NB_FIT") ? atoi(getenv("MAML_B200_TC_NB_FIT")) : 0);
+  if (const char* sp = getenv("MAML_B200_TC_NB_SIDE")) h->nb_side = atoi(sp);
+  if (const char* sp = getenv("MAML_B200_TC_SPLIT_SIDE")) h->split_cap_side = atoi(sp);
+  if (const char* sp = getenv("MAML_B200_TC_SPLIT_L1")) h->split_cap_l1 = atoi(sp);
+  if (const char* sp = getenv("MAML_B200_BN_SIDE_CAP")) h->side_bn_cap = atoi(sp);
   g_launch_prio = (getenv("MAML_B200_LAUNCH_PRIO") && atoi(getenv("MAML_B200_LAUNCH_PRIO")) != 0) ? 1 : 0;
   if (const char* wr = getenv("MAML_B200_WGRAD_ROW")) wgrad_set_row_variant(atoi(wr));
   if (const char* bf = getenv("MAML_B200_BN_FUSE")) bn_set_fuse(atoi(bf));
@@ -414,7 +425,26 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   e = cudaMallocHost((void**)&h->pinned, 16 * 32 * sizeof(float));
   if (e != cudaSuccess) { cudaFree(h->ws); delete h; return fail(std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
   h->use_graphs = !(cfg->reserved & 4) && !getenv("MAML_B200_NO_GRAPH");
-  g_use_pdl = (getenv("MAML_B200_PDL") && atoi(getenv("MAML_B200_PDL")) != 0) ? 1 : 0;   // measured twice: slower inside the captured graph (round 1: 4.16 vs 4.02 ms; round 2: 2.95 vs 2.77 ms), so off by default
+  // Two regimes, told apart by whether one iteration's block-1 tiles (support + target, all tasks) fit one wave of SMs.
+  //  * latency-bound (Omniglot 5-way at 8 tasks: 144 tiles): programmatic dependent launch on the MAIN chain only (the next
+  //    kernel of the support / tangent chain is scheduled while the current one drains, ~1 us per link: 2.742 -> 2.671 ms;
+  //    on every stream 2.89 ms, with cluster launches included 2.91 ms -- early-launched CTAs hold the SM slots the other
+  //    streams want), deep shared-memory rings (all B stages of a short pipeline prefetched at once; ring = 3 / 4: 2.82 ms;
+  //    a ring cut to the stages one CTA has in flight, which lets other kernels share the SM: 2.69 -> 2.73 ms).
+  //  * throughput-bound (Mini-ImageNet, 20-way): no PDL (11.75 -> 11.97 ms, 19.66 -> 19.89 ms), shallow rings (conv ring 4 +
+  //    wgrad ring 2: 19.73 -> 19.10 ms, 11.79 -> 11.58 ms -- the shared memory they give up lets the BatchNorm / first-block
+  //    kernels of the other streams share the SM).
+  // All numbers: profiles/ab_contention_r2.txt (scripts/ab_inproc.py).
+  {
+    const int l1 = h->L > 1 ? 1 : 0;
+    const long long tiles = (((long long)h->n_s * h->geo[l1].G + 127) / 128 + ((long long)h->n_t * h->geo[l1].G + 127) / 128) * h->maxT;
+    const bool small = tiles <= 160;
+    h->pdl_mode = getenv("MAML_B200_PDL") ? atoi(getenv("MAML_B200_PDL")) : (small ? 2 : 0);
+    h->pdl_cluster = getenv("MAML_B200_PDL_CLUSTER") ? atoi(getenv("MAML_B200_PDL_CLUSTER")) : 0;
+    h->nb_main = getenv("MAML_B200_TC_NB") ? std::max(2, std::min(8, atoi(getenv("MAML_B200_TC_NB")))) : (small ? 8 : 4);
+    h->wg_nstage = getenv("MAML_B200_WG_NSTAGE") ? std::max(2, std::min(4, atoi(getenv("MAML_B200_WG_NSTAGE")))) : (small ? 4 : 2);
+    g_use_pdl = h->pdl_mode; g_pdl_cluster = h->pdl_cluster;
+  }
   // Priorities: the support chain (capture stream) is the critical path; the weight-gradient and target streams only
   // have to finish by the end of a step.  Their many small CTAs would otherwise occupy every SM and keep the
   // whole-SM tcgen05 conv CTAs of the critical path waiting (measured: ~20 us per step).
@@ -593,7 +623,8 @@ static void tc_conv(maml_b200_handle* h, int l, int n, int nsrc, const TcOp* ops
   TcConvArgs a{};
   a.nsrc = nsrc; a.kc = h->F; a.rows = n * g.G; a.gw = g.gw; a.G = g.G; a.h = g.h; a.w = g.w; a.ncols = h->F; a.mode = mode; a.tasks = T; a.plan_tasks = h->maxT;
   a.stack = h->tc_stack;
-  a.halo = g.gw + 1; a.rpad = tc_conv_rpad(g.gw); a.nb = tc_conv_ring(h->F, g.gw); a.bo_mode = h->tc_bo_mode; { const char* tl = getenv("MAML_B200_TC_TIMELINE"); a.timeline = (tl && (atoi(tl) <= 0 || atoi(tl) == l)) ? 1 : 0; }
+  a.split_cap = (h->main_stream && st != h->main_stream) ? h->split_cap_side : (l == 1 ? h->split_cap_l1 : 0);
+  a.halo = g.gw + 1; a.rpad = tc_conv_rpad(g.gw); a.nb = std::min(tc_conv_ring(h->F, g.gw), h->nb_main); if (h->nb_side >= 2 && h->main_stream && st != h->main_stream && a.nb > h->nb_side) a.nb = h->nb_side; a.bo_mode = h->tc_bo_mode; { const char* tl = getenv("MAML_B200_TC_TIMELINE"); a.timeline = (tl && (atoi(tl) <= 0 || atoi(tl) == l)) ? 1 : 0; }
   for (int s = 0; s < nsrc; ++s) {
     maps.m[s * 4 + 0] = ops[s].a_maps[0]; maps.m[s * 4 + 1] = ops[s].a_maps[1];
     maps.m[s * 4 + 2] = ops[s].b_maps[ops[s].b_pair]; maps.m[s * 4 + 3] = ops[s].b_maps[ops[s].b_pair + 1];
@@ -626,7 +657,7 @@ static void tc_wgrad(maml_b200_handle* h, int l, int n, int nsrc, const WgSrc* s
   }
   if (nsrc == 1) for (int k = 4; k < 8; ++k) maps.m[k] = maps.m[k - 4];
   a.partial = partial + cp.pd.off[2 * l]; a.partial_task_stride = cp.pd.task_stride; a.chunk_stride = cp.pd.cstride[2 * l];
-  a.tasks = T;
+  a.tasks = T; a.nstage = h->wg_nstage;
   a.alg_flops = conv_flops(h, l, n, T, nsrc);
   launch_wgrad_tc(maps, a, st);
 }
@@ -634,6 +665,8 @@ static void tc_wgrad(maml_b200_handle* h, int l, int n, int nsrc, const WgSrc* s
 // primal forward of one pass: conv -> stats -> BN/leaky/pool for every block
 static void forward_pass(maml_b200_handle* h, const PassSet& ps, int slot, const float* theta, int th_step, const float* meta,
                          int bn_step, int stat_kind, int T, cudaStream_t st, BnActArgs* defer_last = nullptr) {
+  struct CapScope { CapScope(int v) { g_bn_cta_cap = v; } ~CapScope() { g_bn_cta_cap = 0; } }
+      cap_scope((h->main_stream && st != h->main_stream) ? h->side_bn_cap : 0);
   for (int l = 0; l < h->L; ++l) {
     const LayerGeom& g = h->geo[l];
     if (l == 1 && st != h->s_tgt && st != h->s_tgt2) join_pending(h, st);
@@ -683,6 +716,8 @@ static void backward_pass(maml_b200_handle* h, const PassSet& ps, int slot, cons
   // wgrad of block l >= 1 only feeds the parameter-space reduction: it runs on a side stream, concurrently with
   // dgrad(l) and the BatchNorm backward of block l-1.  With a ReduceSpec the reduction itself is split (see
   // reduce_upper_on_side); without one the caller reduces after this function returns.
+  struct CapScope { CapScope(int v) { g_bn_cta_cap = v; } ~CapScope() { g_bn_cta_cap = 0; } }
+      cap_scope((h->main_stream && st != h->main_stream) ? h->side_bn_cap : 0);
   cudaStream_t wst = fork_wgrad ? h->s_wg : st;
   const bool split = fork_wgrad && rs != nullptr;
   bool lower_fused = false;
@@ -929,6 +964,7 @@ static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it,
                              const long long* ys, const float* x_target, const long long* yt, float* result, float* last_logits,
                              cudaStream_t st) {
   g_launch_base = g_launch_counter;      // launch tags (device trace) count from the start of the iteration
+  h->main_stream = st; g_pdl_main_stream = st; g_pdl_wg_stream = h->s_wg; g_use_pdl = h->pdl_mode; g_pdl_cluster = h->pdl_cluster;
   const int T = it->n_tasks;
   const unsigned mask = it->target_mask & ((1u << it->num_steps) - 1u);
   const long long TP = (long long)h->maxT * h->Ppad;
@@ -1141,6 +1177,7 @@ extern "C" int maml_b200_net_forward(maml_b200_handle* h, int32_t n_tasks, int32
   if (n_tasks < 1 || n_tasks > h->maxT) return fail("n_tasks out of range");
   if (num_step < 0 || num_step >= h->S) return fail("num_step out of range");
   cudaStream_t st = (cudaStream_t)stream;
+  h->main_stream = st; g_pdl_main_stream = st; g_use_pdl = h->pdl_mode; g_pdl_cluster = h->pdl_cluster;
   const int T = n_tasks;
   CK(cudaMemsetAsync(h->stats, 0, (size_t)h->stats_count * sizeof(double), st));
   CK(cudaMemsetAsync(h->losses, 0, (size_t)h->maxT * MAML_MAX_STEPS * sizeof(float), st));
@@ -1174,6 +1211,7 @@ extern "C" int maml_b200_net_backward(maml_b200_handle* h, int32_t n_tasks, int3
   if (n_tasks < 1 || n_tasks > h->maxT) return fail("n_tasks out of range");
   if (num_step < 0 || num_step >= h->S) return fail("num_step out of range");
   cudaStream_t st = (cudaStream_t)stream;
+  h->main_stream = st; g_pdl_main_stream = st; g_use_pdl = h->pdl_mode; g_pdl_cluster = h->pdl_cluster;
   const int T = n_tasks;
   // backward statistics (and the tangent ones export subtracts) start from zero; forward statistics are kept
   for (int kind : {PASS_TGT_BWD, PASS_TAN_BWD})

@@ -110,6 +110,9 @@ __global__ void __launch_bounds__(256) bnact_kernel(BnActArgs a) {
   bnact_phase(a, g, task, blockIdx.x, gridDim.x, it, s_mu, s_r, s_g, s_b);
 }
 
+// > 0: launches enqueued right now sit on a side stream (target passes): at most this many CTAs per launch, so that the
+// grid-stride BatchNorm kernels leave SM slots to the main chain (set by the engine around side-stream passes)
+int g_bn_cta_cap = 0;
 static inline dim3 bn_grid(const BnGeom& g, int tasks, int* block) {
   const int F4 = g.F / 4;
   const int wpb = 256 / F4;
@@ -117,6 +120,7 @@ static inline dim3 bn_grid(const BnGeom& g, int tasks, int* block) {
   const int NW = g.n * ((g.h + 1) / 2) * ((g.w + 1) / 2);
   int bx = (NW + wpb - 1) / wpb;
   if (bx > 592) bx = 592;
+  if (g_bn_cta_cap > 0 && (long long)bx * tasks > g_bn_cta_cap) bx = g_bn_cta_cap / tasks;
   if (bx < 1) bx = 1;
   return dim3(bx, tasks);
 }
@@ -376,10 +380,12 @@ template <class A>
 static inline void launch_cluster(void (*kernel)(A), const A& a, int cl, int tasks, int block, cudaStream_t st) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(cl, tasks); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = (g_pdl_cluster && pdl_allowed(st)) ? 2 : 1;
   cudaLaunchKernelEx(&cfg, kernel, a);
 }
 static int g_bn_fuse = 1;            // env MAML_B200_BN_FUSE=0 -> always the two-kernel path

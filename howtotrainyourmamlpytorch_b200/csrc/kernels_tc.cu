@@ -463,15 +463,18 @@ int tc_read_timeline(long long* out16) { return cudaMemcpyFromSymbol(out16, g_tc
 
 // halo tile rows (multiple of 8) for a grid of pitch gw, and the deepest B ring that fits next to 4 halo buffers
 int tc_conv_rpad(int gw) { return ((128 + 2 * (gw + 1)) + 7) / 8 * 8; }
+static int g_tc_ring_cap = 8;         // env MAML_B200_TC_NB: B ring depth cap (a shallower ring leaves shared memory to co-resident kernels)
+void tc_conv_set_ring_cap(int nb) { g_tc_ring_cap = nb < 2 ? 2 : (nb > 8 ? 8 : nb); }
 int tc_conv_ring(int ncols, int gw) {
   const long long avail = 227LL * 1024 - 4096 /* static smem */ - 1024 /* alignment */ - 4LL * tc_conv_rpad(gw) * 128;
   long long nb = avail / (2LL * ncols * 128);
-  if (nb > 8) nb = 8;
+  if (nb > g_tc_ring_cap) nb = g_tc_ring_cap;
   return (int)nb;
 }
 size_t tc_conv_smem_bytes(int ncols, int gw) {
   return (size_t)4 * tc_conv_rpad(gw) * 128 + (size_t)tc_conv_ring(ncols, gw) * 2 * ncols * 128 + 1024;
 }
+static size_t tc_conv_smem_for(int ncols, int gw, int nb) { return (size_t)4 * tc_conv_rpad(gw) * 128 + (size_t)nb * 2 * ncols * 128 + 1024; }
 
 int tc_conv_prepare() {
   const int maxs = 227 * 1024 - 4096;    // static shared memory (barriers, row flags, fp64 partials) takes the rest
@@ -486,6 +489,8 @@ int tc_conv_prepare() {
 // serial pipeline (~18 stages x ~1000 cycles) is then the whole kernel.  Spreading the (phase, tap) stages of a tile
 // over a cluster of S CTAs shortens that to 18 / S stages + one distributed-shared-memory reduction.  S is the largest
 // of {8, 4, 2} whose clusters are all co-resident (asked from the occupancy calculator once per shape).
+static int g_tc_ring_fit = 1;        // env MAML_B200_TC_NB_FIT=0: keep the full ring for short pipelines
+void tc_conv_set_ring_fit(int on) { g_tc_ring_fit = on; }
 static int g_tc_split_max = 8;       // env MAML_B200_TC_SPLIT (1 disables split-K)
 template <int NCOLS>
 static int max_clusters(size_t smem, int S) {
@@ -505,25 +510,37 @@ static int max_clusters(size_t smem, int S) {
 }
 
 template <int NCOLS>
-static void launch_conv_tc_n(const TcMaps& maps, const TcConvArgs& a, size_t smem, cudaStream_t st) {
+static void launch_conv_tc_n(const TcMaps& maps, const TcConvArgs& a_in, size_t smem, cudaStream_t st) {
+  TcConvArgs a = a_in;
   const int tiles = ((a.rows + 127) / 128) * (a.plan_tasks > a.tasks ? a.plan_tasks : a.tasks);
   const int stages = a.nsrc * ((a.kc + 31) / 32) * 9;
   int S = 1;
-  for (int cand = g_tc_split_max; cand >= 2; cand >>= 1) {
+  int smax = g_tc_split_max;
+  if (a.split_cap > 0 && a.split_cap < smax) { smax = 1; while (smax * 2 <= a.split_cap) smax *= 2; }
+  for (int cand = smax; cand >= 2; cand >>= 1) {
     if (cand > 8 || stages < 2 * cand) continue;
     if (tiles <= max_clusters<NCOLS>(smem, cand)) { S = cand; break; }
   }
   dim3 grid((a.rows + 127) / 128, a.tasks, S);
+  // a CTA never has more than ceil(stages / S) B stages in flight: a ring deeper than that only takes shared memory
+  // away from the kernels of the other streams that could share the SM (block-0 / BatchNorm kernels need 10-27 KB)
+  if (g_tc_ring_fit) {
+    const int per_cta = (stages + S - 1) / S;
+    if (a.nb > per_cta) a.nb = per_cta < 2 ? 2 : per_cta;
+  }
+  smem = tc_conv_smem_for(NCOLS, a.gw, a.nb);
   if (S == 1) {
     launch_pdl(conv_tc_kernel<NCOLS>, grid, dim3(224), smem, st, maps, tagged(a));
     return;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = dim3(224); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = S;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = (g_pdl_cluster && pdl_allowed(st)) ? 2 : 1;
   cudaLaunchKernelEx(&cfg, conv_tc_kernel<NCOLS>, maps, tagged(a));
 }
 

@@ -36,12 +36,12 @@ constexpr int WG_A_ROWS = 40;                     // A tile rows: 32 + 2 (three 
 constexpr int WG_A_TILE = WG_A_ROWS * 128;        // bytes of one 32-channel atom of A
 constexpr int WG_B_TILE = WG_STAGE_ROWS * 128;
 constexpr int WG_STAGE_BYTES = 4 * WG_A_TILE + 4 * WG_B_TILE;     // A_hi0 A_hi1 A_lo0 A_lo1 | D_hi0 D_hi1 D_lo0 D_lo1
-constexpr int WG_NSTAGE = 4;
+constexpr int WG_NSTAGE = 4;                      // deepest stage ring (WgTcArgs::nstage in [2, 4] is used at run time)
 constexpr int WG_ONES_BYTES = 4096;               // 4 atoms x 8 rows x 128 B of 1.0f
 constexpr int WG_SEG_KSTEPS = 8;                  // K-steps (of 8 rows) per accumulator segment
 constexpr int WG_ACC_PITCH = 65;                  // final exchange buffer [tap][f][c] (reuses the stage ring), pitch 65: conflict-free
 constexpr int WG_XCHG_BYTES = 3 * 64 * WG_ACC_PITCH * 4;
-static_assert(WG_XCHG_BYTES <= WG_NSTAGE * WG_STAGE_BYTES, "exchange buffer must fit in the stage ring");
+static_assert(WG_XCHG_BYTES <= 2 * WG_STAGE_BYTES, "exchange buffer must fit in the stage ring");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -112,10 +112,11 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
   const int total = nst * a.nsrc;
   const int ks_src = (r_end - r_begin + 7) >> 3;                              // K-steps per source
   const int nseg = (ks_src * a.nsrc + WG_SEG_KSTEPS - 1) / WG_SEG_KSTEPS;    // accumulator segments
-  uint8_t* ones = smem + (size_t)WG_NSTAGE * WG_STAGE_BYTES;
+  const int nstg = a.nstage;                        // stage ring depth (2..WG_NSTAGE)
+  uint8_t* ones = smem + (size_t)nstg * WG_STAGE_BYTES;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < WG_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < nstg; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
         tma_load_2d(bb + 1 * WG_B_TILE, &maps.m[s * 4 + 2], &full[stage], 32, brow);
         tma_load_2d(bb + 2 * WG_B_TILE, &maps.m[s * 4 + 3], &full[stage], 0, brow);
         tma_load_2d(bb + 3 * WG_B_TILE, &maps.m[s * 4 + 3], &full[stage], 32, brow);
-        if (++stage == WG_NSTAGE) { stage = 0; phase ^= 1u; }
+        if (++stage == nstg) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
           }
         }
         tc_commit(&empty[stage]);
-        if (++stage == WG_NSTAGE) { stage = 0; phase ^= 1u; }
+        if (++stage == nstg) { stage = 0; phase ^= 1u; }
       }
       if constexpr (LITE) tc_commit(&acc_full[0]);
       else if (kcount > 0) tc_commit(&acc_full[seg & 1]);
@@ -336,7 +337,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
 
 }  // namespace
 
+static int g_wg_nstage = WG_NSTAGE;     // env MAML_B200_WG_NSTAGE: a shallower ring leaves shared memory to co-resident kernels
+void wgrad_tc_set_stages(int n) { g_wg_nstage = n < 2 ? 2 : (n > WG_NSTAGE ? WG_NSTAGE : n); }
 size_t wgrad_tc_smem_bytes() { return (size_t)WG_NSTAGE * WG_STAGE_BYTES + WG_ONES_BYTES + 1024; }
+static size_t wgrad_tc_smem_for(int nstage) { return (size_t)nstage * WG_STAGE_BYTES + WG_ONES_BYTES + 1024; }
 
 int wgrad_tc_prepare() {
   return (cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_tc_smem_bytes()) == cudaSuccess &&
@@ -347,8 +351,10 @@ void launch_wgrad_tc(const TcMaps& maps, const WgTcArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_WGRAD, a.alg_flops, st);
   dim3 grid(a.nchunks, 3, a.tasks);
   const int ksteps = a.nsrc * ((a.rows_per_chunk + 7) / 8);
-  if (ksteps <= 48 && !a.force_flush) launch_pdl(wgrad_tc_kernel<true>, grid, dim3(192), wgrad_tc_smem_bytes(), st, maps, tagged(a));
-  else launch_pdl(wgrad_tc_kernel<false>, grid, dim3(192), wgrad_tc_smem_bytes(), st, maps, tagged(a));
+  WgTcArgs b = tagged(a);
+  if (b.nstage < 2 || b.nstage > WG_NSTAGE) b.nstage = g_wg_nstage;
+  if (ksteps <= 48 && !a.force_flush) launch_pdl(wgrad_tc_kernel<true>, grid, dim3(192), wgrad_tc_smem_for(b.nstage), st, maps, b);
+  else launch_pdl(wgrad_tc_kernel<false>, grid, dim3(192), wgrad_tc_smem_for(b.nstage), st, maps, b);
   CUDA_CHECK_LAUNCH();
 }
 

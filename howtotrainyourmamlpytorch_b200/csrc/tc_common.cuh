@@ -9,6 +9,7 @@ struct TcConvArgs {
   int nsrc, kc, rows, gw, G, h, w, ncols, mode, tasks;
   int plan_tasks;        // split-K is planned for this many tasks (the handle's max_tasks) so that a task's arithmetic
                          // does not depend on how many tasks share the call
+  int split_cap;         // > 0: largest split-K cluster size for THIS launch (side-stream launches: fewer, longer CTAs)
   int stack;             // 1: N-stacked 3xTF32 (A_hi x [B_hi; B_lo] as one N = 2 * ncols MMA), 0: three MMAs per k-step
   int halo, rpad, nb, bo_mode, timeline;   // halo = gw + 1 rows; rpad = halo-tile rows (multiple of 8); nb = B ring depth
   int a_row_base[2];     // row (in the A tensor map) of grid row 0 of task 0 for this pass slot (includes the guard)
@@ -26,6 +27,8 @@ struct TcConvArgs {
 
 int tc_conv_rpad(int gw);
 int tc_conv_ring(int ncols, int gw);
+void tc_conv_set_ring_cap(int nb);
+void tc_conv_set_ring_fit(int on);     // 1: ring depth = min(cap, B stages one CTA ever has in flight)     // B ring depth cap in [2, 8]
 size_t tc_conv_smem_bytes(int ncols, int gw);
 int tc_conv_prepare();
 void tc_conv_set_split(int max_split);   // largest split-K cluster size (1 = off)
@@ -39,6 +42,7 @@ void launch_pack_weights(const ParamLayout& pl, const float* theta, long long th
 struct WgTcArgs {
   int nsrc, kc, ncols, rows, gw;
   int rows_per_chunk, nchunks;          // rows_per_chunk is a multiple of 32
+  int nstage;                           // stage ring depth (set by the launcher)
   int force_flush;                      // 1: always the draining variant (env MAML_B200_WGRAD_LITE=0)
   int a_row_base[2], a_task_rows[2];    // row (in the A map) of grid row 0 of task 0 for this pass slot; rows per task
   int b_row_base[2], b_task_rows[2];
@@ -49,4 +53,5 @@ struct WgTcArgs {
 };
 size_t wgrad_tc_smem_bytes();
 int wgrad_tc_prepare();
+void wgrad_tc_set_stages(int n);        // stage ring depth in [2, 4]
 void launch_wgrad_tc(const TcMaps& maps, const WgTcArgs& a, cudaStream_t st);
