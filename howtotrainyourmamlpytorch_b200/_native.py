@@ -218,7 +218,13 @@ class Engine(object):
         _check(self.lib, rc, "maml_b200_adam_step")
 
     def running_stats_update(self, result, running_mean, running_var, decay):
-        arr = (ctypes.c_float * MAX_STEPS)(*([float(d) for d in decay] + [1.0] * (MAX_STEPS - len(decay))))
+        cache = self.__dict__.setdefault("_decay_arrays", {})
+        key = tuple(decay)
+        arr = cache.get(key)
+        if arr is None:
+            if len(cache) > 64:
+                cache.clear()
+            arr = cache[key] = (ctypes.c_float * MAX_STEPS)(*([float(d) for d in decay] + [1.0] * (MAX_STEPS - len(decay))))
         rc = self.lib.maml_b200_running_stats_update(self.h, result.data_ptr(), running_mean.data_ptr(),
                                                      running_var.data_ptr(), arr, self._stream())
         _check(self.lib, rc, "maml_b200_running_stats_update")

@@ -303,7 +303,7 @@ enum { PASS_SUP_FWD = 0, PASS_SUP_BWD = 1, PASS_TGT_FWD = 2, PASS_TGT_BWD = 3, P
 extern int g_use_pdl;               // 0: off, 1: every launch, 2: only launches on the iteration's main chain (g_pdl_main_stream),
                                     // 3: every stream except the weight-gradient side stream (g_pdl_wg_stream)
 extern cudaStream_t g_pdl_main_stream, g_pdl_wg_stream;
-extern int g_pdl_cluster;           // 1: cluster launches (split-K convs, fused BatchNorm backward) take the attribute too
+extern int g_pdl_cluster;           // cluster launches that take the attribute too: bit 0 fused BatchNorm backward, bit 1 split-K convs
 inline bool pdl_allowed(cudaStream_t st) {
   return g_use_pdl == 1 || (g_use_pdl == 2 && st == g_pdl_main_stream) || (g_use_pdl == 3 && st != g_pdl_wg_stream);
 }

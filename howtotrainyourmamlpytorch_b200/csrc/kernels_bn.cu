@@ -385,7 +385,7 @@ static inline void launch_cluster(void (*kernel)(A), const A& a, int cl, int tas
   attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = (g_pdl_cluster && pdl_allowed(st)) ? 2 : 1;
+  cfg.attrs = attr; cfg.numAttrs = ((g_pdl_cluster & 1) && pdl_allowed(st)) ? 2 : 1;
   cudaLaunchKernelEx(&cfg, kernel, a);
 }
 static int g_bn_fuse = 1;            // env MAML_B200_BN_FUSE=0 -> always the two-kernel path

@@ -202,15 +202,28 @@ __global__ void export_kernel(ExportArgs a) {
   if (a.comm.world > 1) comm_signal_when_last(a.comm, seq);
 }
 
+// Layout of the launch: blocks [0, ceil(P / 256)) = range 1, one THREAD per inner (fast-weight) element; the remaining
+// blocks = range 2, one WARP per remaining entry of the result vector (BatchNorm beta / gamma, LSLR, loss, accuracy count,
+// running-stat partial sums): the lanes share the (task, step) terms of the entry and a fixed shuffle tree adds them
+// (fp64, deterministic).  Each of those entries is a sum of 8..80 scattered fp64 loads (+ a pow() per term for the
+// running statistics); as a sequential per-thread loop they were the tail of the kernel (export alone: 50 us).
+__device__ __forceinline__ long long export_range1_blocks(const ParamLayout& pl) { return (pl.P + 255) / 256; }
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 __device__ void export_body(const ExportArgs& a) {
   const ParamLayout& pl = a.pl;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long LSF = (long long)pl.L * pl.S * pl.F;
-  const long long total = pl.meta_size + 2 + (pl.per_step_bn ? 2 * LSF : 0);
   const double invB = 1.0 / (double)a.tasks_global;
+  const long long nb1 = export_range1_blocks(pl);
   // ---- range 1: the inner (fast-weight) tensors, walked in the INTERNAL order so that the per-task reads are coalesced
   // (the reference layout is a transposition of it: [F][C][3][3] vs [tap][c][f]); one scattered 4-byte store per element
-  if (gid < pl.P) {
+  if ((long long)blockIdx.x < nb1) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= pl.P) return;
     int seg;
     const long long mi = internal_to_meta(pl, gid, &seg);
     double val = 0.0;
@@ -219,96 +232,93 @@ __device__ void export_body(const ExportArgs& a) {
     a.result[mi] = (float)(val * invB);
     return;
   }
-  // ---- range 2: everything else of the result vector (BatchNorm gamma / beta, LSLR, loss, accuracy count, running stats)
-  const long long i = gid - pl.P;
-  if (i >= total) return;
-  double val = 0.0;
-  if (i < pl.meta_size) {
-    bool done = false;
-    for (int l = 0; l < pl.L && !done; ++l) {
-      const long long wsz = 9LL * pl.cin[l] * pl.F;
-      const long long bnsz = (long long)(pl.per_step_bn ? pl.S : 1) * pl.F;
-      if ((i >= pl.m_w[l] && i < pl.m_w[l] + wsz) || (i >= pl.m_b[l] && i < pl.m_b[l] + pl.F)) return;      // range 1
-      if ((i >= pl.m_beta[l] && i < pl.m_beta[l] + bnsz) || (i >= pl.m_gamma[l] && i < pl.m_gamma[l] + bnsz)) {
-        if (!a.training) { a.result[i] = 0.f; return; }
-        const bool is_gamma = (i >= pl.m_gamma[l] && i < pl.m_gamma[l] + bnsz);
-        const long long rel = i - (is_gamma ? pl.m_gamma[l] : pl.m_beta[l]);
-        const int f = (int)(rel % pl.F);
-        const int s_sel = (int)(rel / pl.F);
-        const int which = is_gamma ? 1 : 0;
-        for (int s = 0; s < a.num_steps; ++s) {
-          if (pl.per_step_bn && s != s_sel) continue;
-          for (int t = 0; t < a.tasks; ++t) {
-            val += stat_ptr(a, t, PASS_TGT_BWD, s, l)[f * 2 + which];
-            val -= stat_ptr(a, t, PASS_TAN_BWD, s, l)[f * 2 + which];
-          }
+  // ---- range 2: one warp per entry
+  const int lane = threadIdx.x & 31;
+  long long e = ((long long)blockIdx.x - nb1) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long bnsz = (long long)(pl.per_step_bn ? pl.S : 1) * pl.F;
+  const long long E_bn = 2LL * pl.L * bnsz, E_lslr = (long long)pl.nseg_inner * (pl.S + 1), E_run = pl.per_step_bn ? 2 * LSF : 0;
+  double val = 0.0, scale = invB;
+  long long dst;
+  if (e < E_bn) {
+    // BatchNorm beta / gamma: target-pass gradient minus the Hessian-vector terms (second order)
+    const int l = (int)(e / (2 * bnsz));
+    const long long r = e - (long long)l * 2 * bnsz;
+    const bool is_gamma = r >= bnsz;
+    const long long rel = r - (is_gamma ? bnsz : 0);
+    dst = (is_gamma ? pl.m_gamma[l] : pl.m_beta[l]) + rel;
+    if (a.training) {
+      const int f = (int)(rel % pl.F), s_sel = (int)(rel / pl.F), which = is_gamma ? 1 : 0;
+      const int per = pl.per_step_bn ? 1 : a.num_steps;               // steps that feed this entry
+      if (!pl.per_step_bn || s_sel < a.num_steps) {
+        for (int k = lane; k < a.tasks * per; k += 32) {
+          const int t = k / per, s = pl.per_step_bn ? s_sel : k - t * per;
+          val += stat_ptr(a, t, PASS_TGT_BWD, s, l)[f * 2 + which];
+          val -= stat_ptr(a, t, PASS_TAN_BWD, s, l)[f * 2 + which];
         }
-        done = true;
       }
     }
-    if (!done) {
-      const long long D = (long long)pl.pix * pl.F;
-      if ((i >= pl.m_fcw && i < pl.m_fcw + (long long)pl.N * D) || (i >= pl.m_fcb && i < pl.m_fcb + pl.N)) return;   // range 1
-      if (!a.training) { a.result[i] = 0.f; return; }
-      const long long rel = i - pl.m_lslr;
-      const int seg = (int)(rel / (pl.S + 1));
-      const int s = (int)(rel % (pl.S + 1));
-      if (s < a.num_steps)
-        for (int t = 0; t < a.tasks; ++t)
-          val += a.abar[((long long)t * pl.nseg_inner + seg) * MAML_MAX_STEPS + s];
-    }
-    a.result[i] = (float)(val * invB);
-    return;
-  }
-  if (i == pl.meta_size) {
-    for (int t = 0; t < a.tasks; ++t)
-      for (int s = 0; s < a.num_steps; ++s)
+  } else if ((e -= E_bn) < E_lslr) {
+    const int seg = (int)(e / (pl.S + 1)), s = (int)(e % (pl.S + 1));
+    dst = pl.m_lslr + e;
+    if (a.training && s < a.num_steps)
+      for (int t = lane; t < a.tasks; t += 32) val += a.abar[((long long)t * pl.nseg_inner + seg) * MAML_MAX_STEPS + s];
+  } else if ((e -= E_lslr) < 2) {
+    dst = pl.meta_size + e;
+    if (e == 0) {
+      for (int k = lane; k < a.tasks * a.num_steps; k += 32) {
+        const int t = k / a.num_steps, s = k - t * a.num_steps;
         if (a.target_mask & (1u << s)) val += (double)a.weights[s] * (double)a.losses[(long long)t * MAML_MAX_STEPS + s];
-    a.result[i] = (float)(val * invB);
-    return;
-  }
-  if (i == pl.meta_size + 1) {
-    for (int t = 0; t < a.tasks; ++t) val += (double)a.correct[t];
-    a.result[i] = (float)val;
-    return;
-  }
-  // running-statistic partial sums (per-step BN only).  For block l, step s the reference applies, for
-  // global task g = 0..B-1 in order: support update, then (if a target pass runs at s) target update;
-  // r <- 0.9 r + 0.1 stat.  Unrolled: r_new = 0.9^U r_old + sum_k 0.1 * 0.9^(U-1-k) stat_k.
-  long long rel = i - (pl.meta_size + 2);
-  const int which = (int)(rel / LSF);           // 0: mean, 1: var
-  rel -= (long long)which * LSF;
-  const int l = (int)(rel / ((long long)pl.S * pl.F));
-  const int s = (int)((rel / pl.F) % pl.S);
-  const int f = (int)(rel % pl.F);
-  // evaluation passes leave the EMA side effect behind too (the reference's backup is an alias, see run_validation_iter)
-  if (s >= a.num_steps) { a.result[i] = 0.f; return; }
-  const bool has_t = (a.target_mask >> s) & 1u;
-  const int c = has_t ? 2 : 1;
-  const int U = c * a.tasks_global;
-  for (int t = 0; t < a.tasks; ++t) {
-    const int gidx = a.task_offset + t;
-    for (int j = 0; j < c; ++j) {
-      const int k = c * gidx + j;
-      const double wgt = 0.1 * pow(0.9, (double)(U - 1 - k));
-      const double* sp = stat_ptr(a, t, j == 0 ? PASS_SUP_FWD : PASS_TGT_FWD, s, l);
-      const double m = (double)(j == 0 ? a.n_s : a.n_t) * (double)a.hw[l];
-      const double mean = sp[f * 2] / m;
-      if (which == 0) val += wgt * mean;
-      else {
-        double var = sp[f * 2 + 1] / m - mean * mean;
-        if (var < 0.0) var = 0.0;
-        val += wgt * var * (m / (m > 1.0 ? m - 1.0 : 1.0));
+      }
+    } else {
+      for (int t = lane; t < a.tasks; t += 32) val += (double)a.correct[t];
+      scale = 1.0;
+    }
+  } else if ((e -= 2) < E_run) {
+    // running-statistic partial sums (per-step BN only).  For block l, step s the reference applies, for
+    // global task g = 0..B-1 in order: support update, then (if a target pass runs at s) target update;
+    // r <- 0.9 r + 0.1 stat.  Unrolled: r_new = 0.9^U r_old + sum_k 0.1 * 0.9^(U-1-k) stat_k.
+    dst = pl.meta_size + 2 + e;
+    scale = 1.0;
+    long long rel = e;
+    const int which = (int)(rel / LSF);           // 0: mean, 1: var
+    rel -= (long long)which * LSF;
+    const int l = (int)(rel / ((long long)pl.S * pl.F));
+    const int s = (int)((rel / pl.F) % pl.S);
+    const int f = (int)(rel % pl.F);
+    // evaluation passes leave the EMA side effect behind too (the reference's backup is an alias, see run_validation_iter)
+    if (s < a.num_steps) {
+      const bool has_t = (a.target_mask >> s) & 1u;
+      const int c = has_t ? 2 : 1;
+      const int U = c * a.tasks_global;
+      for (int kk = lane; kk < a.tasks * c; kk += 32) {
+        const int t = kk / c, j = kk - t * c;
+        const int k = c * (a.task_offset + t) + j;
+        const double wgt = 0.1 * pow(0.9, (double)(U - 1 - k));
+        const double* sp = stat_ptr(a, t, j == 0 ? PASS_SUP_FWD : PASS_TGT_FWD, s, l);
+        const double m = (double)(j == 0 ? a.n_s : a.n_t) * (double)a.hw[l];
+        const double mean = sp[f * 2] / m;
+        if (which == 0) val += wgt * mean;
+        else {
+          double var = sp[f * 2 + 1] / m - mean * mean;
+          if (var < 0.0) var = 0.0;
+          val += wgt * var * (m / (m > 1.0 ? m - 1.0 : 1.0));
+        }
       }
     }
+  } else {
+    return;                                        // warp-uniform
   }
-  a.result[i] = (float)val;
+  val = warp_sum_f64(val);
+  if (lane == 0) a.result[dst] = (float)(val * scale);
 }
 
 void launch_export(const ExportArgs& a, cudaStream_t st) {
   ProfScope prof_scope__(PROF_PARAM, 0.0, st);
-  const long long total = a.pl.P + a.pl.meta_size + 2 + (a.pl.per_step_bn ? 2LL * a.pl.L * a.pl.S * a.pl.F : 0);
-  launch_pdl(export_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st, tagged(a));
+  const ParamLayout& pl = a.pl;
+  const long long bnsz = (long long)(pl.per_step_bn ? pl.S : 1) * pl.F;
+  const long long entries = 2LL * pl.L * bnsz + (long long)pl.nseg_inner * (pl.S + 1) + 2 + (pl.per_step_bn ? 2LL * pl.L * pl.S * pl.F : 0);
+  const long long blocks = (pl.P + 255) / 256 + (entries + 7) / 8;        // range 1: thread per element; range 2: warp per entry
+  launch_pdl(export_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), st, tagged(a));
   CUDA_CHECK_LAUNCH();
 }
 

@@ -91,10 +91,15 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t dsmem_addr(uint32_t local, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
   return r;
+}
+__device__ __forceinline__ void dsmem_st4(uint32_t addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ float4 dsmem_ld4(uint32_t addr) {
   float4 v;
@@ -138,6 +143,35 @@ __device__ __forceinline__ void splitk_reduce(uint32_t tile_local, int zrank, in
 }
 
 
+// Push-based variant (default): every CTA has already WRITTEN the rows it does not own into the owner's receive buffer
+// recv[source rank][128 / S rows][NCOLS + 4] (st.shared::cluster, before the one cluster barrier), so the owner sums S
+// LOCAL buffers -- no remote load latency, and nobody reads a peer's shared memory after the barrier, so the second
+// cluster barrier ("do not exit while a peer still reads") is gone.  Same summation order as the pull variant.
+template <int NCOLS, int S>
+__device__ __forceinline__ void splitk_reduce_local(const float* __restrict__ recv, int zrank, int et, const float* __restrict__ bias,
+                                                    float* __restrict__ tile2, float* __restrict__ out, int j0, int rows) {
+  constexpr int P4 = NCOLS + 4;
+  constexpr int ROWS = 128 / S;
+  constexpr int TOTAL4 = ROWS * (NCOLS / 4);
+  constexpr int ITEMS = (TOTAL4 + 127) / 128;
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int idx = et + it * 128;
+    if (idx >= TOTAL4) continue;
+    const int rr = idx / (NCOLS / 4), c4 = idx - rr * (NCOLS / 4);
+    float4 v[S];
+#pragma unroll
+    for (int z = 0; z < S; ++z) v[z] = *reinterpret_cast<const float4*>(recv + ((z * ROWS + rr) * P4 + c4 * 4));
+    float4 acc = v[0];
+#pragma unroll
+    for (int z = 1; z < S; ++z) { acc.x += v[z].x; acc.y += v[z].y; acc.z += v[z].z; acc.w += v[z].w; }
+    if (bias) { acc.x += bias[c4 * 4]; acc.y += bias[c4 * 4 + 1]; acc.z += bias[c4 * 4 + 2]; acc.w += bias[c4 * 4 + 3]; }
+    *reinterpret_cast<float4*>(tile2 + rr * P4 + c4 * 4) = acc;
+    const int g = j0 + zrank * ROWS + rr;
+    if (g < rows) *reinterpret_cast<float4*>(out + (long long)g * NCOLS + c4 * 4) = acc;
+  }
+}
+
 // K-major SWIZZLE_128B descriptor whose start is `row_off` rows into a 1024B-aligned tile.  Measured on B200: the
 // 128B swizzle XOR is a function of the ABSOLUTE shared-memory address bits [7,10) (as for TMA writes), so a start
 // address moved by row_off * 128 B addresses rows row_off .. row_off+127 of the tile correctly with the
@@ -179,6 +213,9 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
   const int nsplit = (int)gridDim.z, zrank = (int)blockIdx.z;
   const int st_lo = zrank * (nph * 9) / nsplit, st_hi = (zrank + 1) * (nph * 9) / nsplit;
   const int ph_lo = st_lo / 9, ph_hi = (st_hi - 1) / 9;
+  // push variant: a CTA writes into its peers' shared memory as soon as ITS accumulators are done, so every CTA of the
+  // cluster must be known to have started by then: arrive here, wait right before the first remote store (free by then)
+  if (nsplit > 1 && a.push) cluster_arrive_relaxed();
   const int abuf = a.rpad * 128;                 // bytes of one A halo buffer (hi or lo)
   uint8_t* bring = smem + 4 * (size_t)abuf;
 
@@ -332,6 +369,14 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
     const bool want_stats = (a.mode != CONV_PLAIN);
     const int grow = j0 + r;
     float* orow = a.out + (long long)task * a.out_stride + (long long)grow * NCOLS;
+    float* push_local = nullptr;
+    uint32_t push_row = 0;                       // split-K, push variant: this thread's row inside the owner's receive buffer
+    if (nsplit > 1 && a.push) {
+      cluster_wait();                            // phase 1 (arrived at kernel start): all peers are running
+      const int rows_per = 128 / nsplit, owner = r / rows_per, rloc = r - owner * rows_per;
+      push_row = dsmem_addr(smem_u32(bring + (size_t)nb * BSTAGE) + (uint32_t)(((zrank * rows_per + rloc) * (NCOLS + 4)) * 4), (uint32_t)owner);
+      if (owner == zrank) push_local = reinterpret_cast<float*>(bring + (size_t)nb * BSTAGE) + (zrank * rows_per + rloc) * (NCOLS + 4);   // own rows: plain st.shared
+    }
 #pragma unroll
     for (int c0 = 0; c0 < NCOLS; c0 += 16) {
       uint32_t v0[16], v1[16], v2[16], v3[16], v4[16];
@@ -380,9 +425,20 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
           const float big = (__uint_as_float(v0[i]) + __uint_as_float(v1[i])) + (__uint_as_float(v2[i]) + __uint_as_float(v3[i]));
           o[i] = big + __uint_as_float(v4[i]);
         }
+        if (a.push) {
+          // row r of the tile belongs to cluster rank r / (128 / nsplit): straight into that CTA's receive buffer
+          if (push_local != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4)
-          *reinterpret_cast<float4*>(tile + r * (NCOLS + 4) + c0 + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(push_local + c0 + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) dsmem_st4(push_row + (uint32_t)((c0 + i) * 4), make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<float4*>(tile + r * (NCOLS + 4) + c0 + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+        }
       }
     }
     if (et == 0) TC_MARK(7);
@@ -393,7 +449,9 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
   const float* sbuf = reinterpret_cast<const float*>(smem);   // where those rows live (row index relative to row_lo)
   if (nsplit > 1) {
     __syncwarp();
-    cluster_sync_all();                            // every CTA's partial tile is in its shared memory
+    if (a.push && !(warp >= 2 && warp < 6)) cluster_wait();     // phase 1 for the non-epilogue warps
+    cluster_sync_all();                            // pull: every CTA's partial tile is in its shared memory; push: every receive buffer is complete
+    if (threadIdx.x == 64) TC_MARK(10);
     row_n = 128 / nsplit; row_lo = zrank * row_n; spitch = NCOLS + 4;
     float* tile2 = reinterpret_cast<float*>(smem + 40 * 1024);
     sbuf = tile2;
@@ -402,12 +460,18 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
       const uint32_t tile_local = smem_u32(smem);
       const float* bias = a.bias ? a.bias + (long long)task * a.bias_stride : nullptr;
       float* outp = a.out + (long long)task * a.out_stride;
-      if (nsplit == 2) splitk_reduce<NCOLS, 2>(tile_local, zrank, et, bias, tile2, outp, j0, a.rows);
+      if (a.push) {
+        const float* recv = reinterpret_cast<const float*>(bring + (size_t)nb * BSTAGE);
+        if (nsplit == 2) splitk_reduce_local<NCOLS, 2>(recv, zrank, et, bias, tile2, outp, j0, a.rows);
+        else if (nsplit == 4) splitk_reduce_local<NCOLS, 4>(recv, zrank, et, bias, tile2, outp, j0, a.rows);
+        else splitk_reduce_local<NCOLS, 8>(recv, zrank, et, bias, tile2, outp, j0, a.rows);
+      } else if (nsplit == 2) splitk_reduce<NCOLS, 2>(tile_local, zrank, et, bias, tile2, outp, j0, a.rows);
       else if (nsplit == 4) splitk_reduce<NCOLS, 4>(tile_local, zrank, et, bias, tile2, outp, j0, a.rows);
       else splitk_reduce<NCOLS, 8>(tile_local, zrank, et, bias, tile2, outp, j0, a.rows);
     }
   }
 
+  if (threadIdx.x == 64) TC_MARK(11);
   if (warp >= 2 && warp < 6) {
     const int et = threadIdx.x - 64;
     const bool want_stats = (a.mode != CONV_PLAIN);
@@ -418,6 +482,9 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
       const int col = et % NCOLS, part = et / NCOLS;
       double s1 = 0.0, s2 = 0.0;
       if (part < PARTS) {
+        // (a 4-row-batched variant of this loop -- all loads of a batch issued before the first add, four independent fp64
+        // chains -- and an integer re-bias instead of F2F.F64.F32 both measured SLOWER: 11.6 -> 12.0 ms on Mini-ImageNet,
+        // 19.1 -> 19.7 / 20.0 ms on 20-way; see DESIGN.md, negative results)
         for (int rr = part; rr < row_n; rr += PARTS) {
           if (row_ok[row_lo + rr]) {
             const float v = sbuf[rr * spitch + col];
@@ -442,9 +509,10 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
       }
     }
   }
-  if (nsplit > 1) {
+  if (threadIdx.x == 64) TC_MARK(12);
+  if (nsplit > 1 && !a.push) {
     __syncwarp();
-    cluster_sync_all();                            // nobody leaves while a peer still reads its partial tile
+    cluster_sync_all();                            // pull variant: nobody leaves while a peer still reads its partial tile
   }
 
   if (threadIdx.x == 64) TC_MARK(8);
@@ -489,6 +557,8 @@ int tc_conv_prepare() {
 // serial pipeline (~18 stages x ~1000 cycles) is then the whole kernel.  Spreading the (phase, tap) stages of a tile
 // over a cluster of S CTAs shortens that to 18 / S stages + one distributed-shared-memory reduction.  S is the largest
 // of {8, 4, 2} whose clusters are all co-resident (asked from the occupancy calculator once per shape).
+static int g_tc_push = 1;            // env MAML_B200_TC_PUSH=0: pull-based split-K reduction (two cluster barriers)
+void tc_conv_set_push(int on) { g_tc_push = on; }
 static int g_tc_ring_fit = 1;        // env MAML_B200_TC_NB_FIT=0: keep the full ring for short pipelines
 void tc_conv_set_ring_fit(int on) { g_tc_ring_fit = on; }
 static int g_tc_split_max = 8;       // env MAML_B200_TC_SPLIT (1 disables split-K)
@@ -515,6 +585,17 @@ static void launch_conv_tc_n(const TcMaps& maps, const TcConvArgs& a_in, size_t 
   const int tiles = ((a.rows + 127) / 128) * (a.plan_tasks > a.tasks ? a.plan_tasks : a.tasks);
   const int stages = a.nsrc * ((a.kc + 31) / 32) * 9;
   int S = 1;
+  // push-based split-K epilogue: a receive buffer [128 rows][NCOLS + 4] behind the B ring (peers write it while this CTA's
+  // MMAs may still read the operand buffers, so it cannot alias them); the ring gives up the stages that no longer fit
+  const size_t recv_bytes = (size_t)128 * (NCOLS + 4) * 4;
+  int nb_push = a.nb;
+  {
+    const long long avail = 227LL * 1024 - 4096 - 1024 - 4LL * tc_conv_rpad(a.gw) * 128 - (long long)recv_bytes;
+    const long long fit = avail / (2LL * NCOLS * 128);
+    if (fit < nb_push) nb_push = (int)fit;
+  }
+  const bool push = g_tc_push && nb_push >= 2;
+  if (push) smem = tc_conv_smem_for(NCOLS, a.gw, nb_push) + recv_bytes;
   int smax = g_tc_split_max;
   if (a.split_cap > 0 && a.split_cap < smax) { smax = 1; while (smax * 2 <= a.split_cap) smax *= 2; }
   for (int cand = smax; cand >= 2; cand >>= 1) {
@@ -528,7 +609,9 @@ static void launch_conv_tc_n(const TcMaps& maps, const TcConvArgs& a_in, size_t 
     const int per_cta = (stages + S - 1) / S;
     if (a.nb > per_cta) a.nb = per_cta < 2 ? 2 : per_cta;
   }
-  smem = tc_conv_smem_for(NCOLS, a.gw, a.nb);
+  a.push = (S > 1 && push) ? 1 : 0;
+  if (a.push) a.nb = nb_push;
+  smem = tc_conv_smem_for(NCOLS, a.gw, a.nb) + (a.push ? recv_bytes : 0);
   if (S == 1) {
     launch_pdl(conv_tc_kernel<NCOLS>, grid, dim3(224), smem, st, maps, tagged(a));
     return;
@@ -540,7 +623,7 @@ static void launch_conv_tc_n(const TcMaps& maps, const TcConvArgs& a_in, size_t 
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = S;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = (g_pdl_cluster && pdl_allowed(st)) ? 2 : 1;
+  cfg.attrs = attr; cfg.numAttrs = ((g_pdl_cluster & 2) && pdl_allowed(st)) ? 2 : 1;
   cudaLaunchKernelEx(&cfg, conv_tc_kernel<NCOLS>, maps, tagged(a));
 }
 

@@ -414,8 +414,7 @@ class MAMLFewShotClassifier(nn.Module):
                 if self._comm_checks % 512 == 0 and eng.comm_status() != 0:
                     raise RuntimeError("peer-memory all-reduce timed out waiting for another rank (status %#x)" % eng.comm_status())
             ms = eng.meta_size
-            out[:2].copy_(reduced[ms:ms + 2])
-            head = out
+            head = (reduced[ms:ms + 2], out[2:])      # [loss, n_correct] of the (reduced) result vector, logits: read by _finish
             if training_phase and apply_update:
                 self.optimizer.step_count += 1
                 eng.adam_step(self._flat, reduced, self._exp_avg, self._exp_avg_sq, lr=self._current_lr,
@@ -426,7 +425,13 @@ class MAMLFewShotClassifier(nn.Module):
                 # reference's backup is copy(tensor.data), an alias, so restore_backup_stats restores the mutated values
                 # (meta_neural_network_architectures.py:240-255; pinned by the val/ golden entries).
                 S = int(self.args.number_of_training_steps_per_iter)
-                decay = sharding.decay_vector(mask, num_steps, S, B_global)
+                dkey = (mask, num_steps, S, B_global)
+                dcache = self.__dict__.setdefault("_decay_cache", {})
+                decay = dcache.get(dkey)
+                if decay is None:
+                    if len(dcache) > 64:
+                        dcache.clear()
+                    decay = dcache[dkey] = tuple(sharding.decay_vector(mask, num_steps, S, B_global))
                 eng.running_stats_update(reduced, self._running[0], self._running[1], decay)
         return head, logits, w_msl, B_global, n_t
 
@@ -522,7 +527,18 @@ class MAMLFewShotClassifier(nn.Module):
 
     def _finish(self, head, logits, w_msl, B_global, n_t):
         """One D2H read of (loss, n_correct, logits) -- the reference syncs per task (:246,:249,:261)."""
-        host = head.cpu()                      # [loss, n_correct | logits] in one read
+        # [loss, n_correct | logits]: two asynchronous copies into one pinned block, ONE wait (``.cpu()`` goes through
+        # pageable memory: an extra staging copy and a full stream synchronisation)
+        n = 2 + head[1].numel()
+        hp = self._staging.get(("host_out", n))
+        if hp is None:
+            hp = self._staging[("host_out", n)] = (torch.empty(n, dtype=torch.float32).pin_memory(), torch.cuda.Event())
+        with torch.cuda.device(self.device):
+            hp[0][:2].copy_(head[0], non_blocking=True)
+            hp[0][2:].copy_(head[1], non_blocking=True)
+            hp[1].record()
+        hp[1].synchronize()
+        host = hp[0].clone()                   # the caller keeps the arrays; the pinned block is reused next iteration
         head_h = host[:2]
         preds = host[2:].view(logits.shape).numpy()
         losses = {"loss": head_h[0].clone(), "accuracy": float(head_h[1]) / float(B_global * n_t)}

@@ -19,4 +19,4 @@ for _ in range(3):
     m._run(db, 0, mode == "train", False)
 torch.cuda.synchronize()
 t = m._engine.debug_read("tc_timeline")
-print(name, mode, "block", os.environ["MAML_B200_TC_TIMELINE"], "cycles since start:", [int(x) for x in t[:10]])
+print(name, mode, "block", os.environ["MAML_B200_TC_TIMELINE"], "push", os.environ.get("MAML_B200_TC_PUSH", "1"), "cycles since start:", [int(x) for x in t[:13]])
