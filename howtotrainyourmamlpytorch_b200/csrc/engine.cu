@@ -464,7 +464,7 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   for (int s = 0; ok && s < 2 * MAML_MAX_LAYERS; ++s) ok = cudaEventCreateWithFlags(&h->ev_pre[s], cudaEventDisableTiming) == cudaSuccess;
   if (const char* ts = getenv("MAML_B200_TAN_SPLIT")) h->tan_split = atoi(ts) != 0;
   if (const char* tf = getenv("MAML_B200_TAIL_FUSE")) h->tail_fuse = atoi(tf) != 0;
-  if (const char* tf = getenv("MAML_B200_TAIL_ONCHIP")) tail_set_onchip(atoi(tf));
+  tail_set_onchip(getenv("MAML_B200_TAIL_ONCHIP") ? atoi(getenv("MAML_B200_TAIL_ONCHIP")) : 3);      // bit 0 primal, bit 1 tangent
   if (!ok) { maml_b200_destroy(h); return fail("stream / event creation failed"); }
   *out = h;
   return 0;
@@ -986,10 +986,16 @@ static int enqueue_iteration(maml_b200_handle* h, const maml_b200_iter_args* it,
   CK(cudaMemsetAsync(h->correct, 0, (size_t)h->maxT * sizeof(float), st));
 
   launch_prep_x(x_support, h->sup.xg, h->sup.xg_stride, T, h->n_s, h->C, h->H, h->W, st);
-  launch_prep_x(x_target, h->tgt.xg, h->tgt.xg_stride, T, h->n_t, h->C, h->H, h->W, st);
   launch_import_theta(h->pl, meta, h->theta, h->Ppad, T, st);
-  pack_theta_step(h, 0, T, st);
-  h->wg_pending = false;
+  // The target images and the tensor-core packs of theta^0 are first needed after block 0 of the first support pass: both
+  // go to the side stream (15 us off the head of the main chain).  Every consumer already waits for ev_wg: the main chain
+  // through join_pending before block 1, the target streams before each pass.
+  CK(cudaEventRecord(h->ev_fork, st));
+  CK(cudaStreamWaitEvent(h->s_wg, h->ev_fork, 0));
+  launch_prep_x(x_target, h->tgt.xg, h->tgt.xg_stride, T, h->n_t, h->C, h->H, h->W, h->s_wg);
+  pack_theta_step(h, 0, T, h->s_wg);
+  CK(cudaEventRecord(h->ev_wg, h->s_wg));
+  h->wg_pending = true;
 
   // ---------------- phase A: unroll the inner loop.  Support chain on `st`; the target pass of step s (forward at
   // theta^{s+1}, and its backward) only feeds phase B, so it runs on a side stream concurrently with step s+1.

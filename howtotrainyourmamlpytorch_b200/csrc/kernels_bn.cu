@@ -859,7 +859,185 @@ __global__ void __launch_bounds__(256) tail_onchip_kernel(BnActArgs fa, HeadArgs
   }
 }
 
-static int g_tail_onchip = 1;          // env MAML_B200_TAIL_ONCHIP=0: tail_fused_kernel (stages exchange data through L2)
+// On-chip variant of tail_tan_fused_kernel (tangent pass), same plan as tail_onchip_kernel:
+//   stage 1  every thread owns <= MAXI (pooling window, channel quad) items: loads the primal zh and the tangent zdot
+//            (both addends) once, keeps zh[4], zhdot[4], the arg-max and the leaky slope in REGISTERS, writes zhdot / pdot to
+//            global for the record and pdot into shared memory (tangent features);
+//   stage 2  head_body (HEAD_TANGENT) on shared-memory copies of f, fdot, W_fc, u_W, b_fc, u_b; leaves d(f)dot in shared memory;
+//   stage 3  tangent BatchNorm backward of the same items from registers + shared memory; the primal dp / dz it also needs
+//            are loaded at the top of the kernel (they were written in phase A).
+template <int MAXI>
+__global__ void __launch_bounds__(256) tail_tan_onchip_kernel(BnActTanArgs fa, HeadArgs ha, BnBwdTanArgs ba) {
+  pdl_prologue(24, fa.tag);
+  extern __shared__ float smh[];                  // [head scratch 5*R*N | f n*D | fdot n*D | dfdot n*D | W N*D | uW N*D | b N | ub N]
+  __shared__ float s_mu[64], s_r[64], s_g[64], s_b[64], s_md[64], s_q[64], s_c2[64], s_t1[64], s_t2[64];
+  __shared__ float s_rowloss[64], s_rowcorrect[64];
+  const BnGeom g = fa.g;
+  const int task = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int n = ha.n, N = ha.N, D = ha.D;
+  float* s_f = smh + 5 * ha.rows_per_cta * N;
+  float* s_fd = s_f + n * D;
+  float* s_dfd = s_fd + n * D;
+  float* s_W = s_dfd + n * D;
+  float* s_uW = s_W + N * D;
+  float* s_bfc = s_uW + N * D;
+  float* s_ub = s_bfc + N;
+  const double m = (double)g.n * g.h * g.w;
+  bnact_tan_setup(fa, g, task, m, s_mu, s_r, s_g, s_b, s_md, s_q);
+  if (tid < g.F) s_c2[tid] = (float)((ba.stats_bwd + (long long)task * ba.stats_bwd_stride)[tid * 2 + 1] / m);
+  {
+    const float* W = ha.Wfc + (long long)task * ha.theta_stride;
+    const float* bb = ha.bfc + (long long)task * ha.theta_stride;
+    const float* uW = ha.uW + (long long)task * ha.u_stride;
+    const float* ub = ha.ub + (long long)task * ha.u_stride;
+    const float* f = ha.f + (long long)task * ha.f_stride;
+    for (int o = tid; o < N * D; o += 256) { s_W[o] = W[o]; s_uW[o] = uW[o]; }
+    for (int o = tid; o < n * D; o += 256) s_f[o] = f[o];
+    if (tid < N) { s_bfc[tid] = bb[tid]; s_ub[tid] = ub[tid]; }
+  }
+  __syncthreads();
+  WinIter it(g);
+  const bool worker = it.lane < it.WPB;
+  float4 zh[MAXI][4], zhd[MAXI][4]; int4 arg[MAXI]; float4 sl[MAXI]; float4 dprim[MAXI];
+  int wy_[MAXI], wx_[MAXI], img_[MAXI]; bool have[MAXI], full[MAXI];
+  float4 r, ga, be, md, qq;
+  if (worker) { r = ld4s(s_r, it.q); ga = ld4s(s_g, it.q); be = ld4s(s_b, it.q); md = ld4s(s_md, it.q); qq = ld4s(s_q, it.q); }
+  float* zd = fa.zdot + (long long)task * fa.zdot_stride;
+  const float* zd2 = fa.zdot2 ? fa.zdot2 + (long long)task * fa.zdot_stride : nullptr;
+  const float* zhp = fa.zh + (long long)task * fa.zh_stride;
+  float* pdg = fa.pdot + (long long)task * fa.pdot_stride;
+  const float* dpp = ba.dp + (long long)task * ba.dp_stride;
+  // ---------------- stage 1: tangent of BatchNorm + leaky-ReLU + max-pool at the primal arg-max (first max wins)
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    const int wi = it.lane + i * it.WPB;
+    have[i] = worker && wi < it.NW;
+    full[i] = false;
+    dprim[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!have[i]) continue;
+    const int img = wi / (it.hc * it.wc);
+    const int rem = wi - img * it.hc * it.wc;
+    const int wy = rem / it.wc, wx = rem - wy * it.wc;
+    img_[i] = img; wy_[i] = wy; wx_[i] = wx;
+    full[i] = (wy < g.ph && wx < g.pw);
+    const long long pidx = ((long long)img * g.pG + (wy + g.pb) * g.pgw + (wx + g.pb)) * g.F + it.q * 4;
+    if (full[i]) dprim[i] = ld4(dpp + pidx);                 // primal d(loss)/d(pooled), written in phase A
+    float4 best = make_float4(0.f, 0.f, 0.f, 0.f), ybest = best, pbest = best;
+    int4 am = make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = 2 * wy + (k >> 1), xx = 2 * wx + (k & 1);
+      zh[i][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      zhd[i][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (yy < g.h && xx < g.w) {
+        const long long idx = ((long long)img * g.G + (yy + 1) * g.gw + (xx + 1)) * g.F + it.q * 4;
+        const float4 z = ld4(zhp + idx);
+        float4 zv = ld4(zd + idx);
+        if (zd2) { const float4 z2 = ld4(zd2 + idx); zv.x += z2.x; zv.y += z2.y; zv.z += z2.z; zv.w += z2.w; }
+        float4 d;
+        d.x = r.x * (zv.x - md.x - z.x * qq.x); d.y = r.y * (zv.y - md.y - z.y * qq.y);
+        d.z = r.z * (zv.z - md.z - z.z * qq.z); d.w = r.w * (zv.w - md.w - z.w * qq.w);
+        st4(zd + idx, d);
+        zh[i][k] = z; zhd[i][k] = d;
+        float4 y, act, pdv;
+        y.x = fmaf(ga.x, z.x, be.x); y.y = fmaf(ga.y, z.y, be.y); y.z = fmaf(ga.z, z.z, be.z); y.w = fmaf(ga.w, z.w, be.w);
+        act.x = leaky(y.x); act.y = leaky(y.y); act.z = leaky(y.z); act.w = leaky(y.w);
+        pdv.x = slope_of(y.x) * ga.x * d.x; pdv.y = slope_of(y.y) * ga.y * d.y;
+        pdv.z = slope_of(y.z) * ga.z * d.z; pdv.w = slope_of(y.w) * ga.w * d.w;
+        if (k == 0) { best = act; ybest = y; pbest = pdv; }
+        else {
+          if (act.x > best.x) { best.x = act.x; ybest.x = y.x; pbest.x = pdv.x; am.x = k; }
+          if (act.y > best.y) { best.y = act.y; ybest.y = y.y; pbest.y = pdv.y; am.y = k; }
+          if (act.z > best.z) { best.z = act.z; ybest.z = y.z; pbest.z = pdv.z; am.z = k; }
+          if (act.w > best.w) { best.w = act.w; ybest.w = y.w; pbest.w = pdv.w; am.w = k; }
+        }
+      }
+    }
+    arg[i] = am;
+    sl[i] = make_float4(slope_of(ybest.x), slope_of(ybest.y), slope_of(ybest.z), slope_of(ybest.w));
+    if (full[i]) {
+      st4(pdg + pidx, pbest);
+      st4(s_fd + pidx, pbest);                     // pb = 0 on the last block: pidx is the feature index img * D + ...
+    }
+  }
+  __syncthreads();
+  // ---------------- stage 2: tangent of the classifier head on the shared-memory copies
+  {
+    HeadArgs hs = ha;
+    hs.f = s_f; hs.f_stride = 0;
+    hs.fdot = s_fd; hs.fdot_stride = 0;
+    hs.Wfc = s_W; hs.bfc = s_bfc; hs.theta_stride = 0;
+    hs.uW = s_uW; hs.ub = s_ub; hs.u_stride = 0;
+    hs.df = s_dfd; hs.df_stride = 0;
+    head_body<true>(hs, task, 0, smh, s_rowloss, s_rowcorrect);
+  }
+  __syncthreads();
+  {
+    float* dfg = ha.df + (long long)task * ha.df_stride;
+    for (int o = tid; o < n * D; o += 256) dfg[o] = s_dfd[o];
+  }
+  // ---------------- stage 3: tangent BatchNorm backward of the same items
+  //   T1 = sum dydot, T2 = sum (dydot * zh + dy * zhdot) at the arg-max;  dzdot = -r q dz + r gamma (dydot - T1/m - zhdot S2/m - zh T2/m)
+  const float* dzp = ba.dz + (long long)task * ba.dz_stride;
+  double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  float4 dydv[MAXI];
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    dydv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!have[i] || !full[i]) continue;
+    const long long pidx = ((long long)img_[i] * g.pG + (wy_[i] + g.pb) * g.pgw + (wx_[i] + g.pb)) * g.F + it.q * 4;
+    const float4 dd = ld4(s_dfd + pidx);
+    const int ar[4] = {arg[i].x, arg[i].y, arg[i].z, arg[i].w};
+    const float slv[4] = {sl[i].x, sl[i].y, sl[i].z, sl[i].w};
+    const float dv[4] = {dprim[i].x, dprim[i].y, dprim[i].z, dprim[i].w};
+    const float ddv[4] = {dd.x, dd.y, dd.z, dd.w};
+    float dydc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float zhk = pick(zh[i], ar[c], c);
+      const float zhdk = pick(zhd[i], ar[c], c);
+      const float dy = dv[c] * slv[c], dyd = ddv[c] * slv[c];
+      dydc[c] = dyd;
+      s1[c] += dyd;
+      s2[c] += (double)dyd * (double)zhk + (double)dy * (double)zhdk;
+    }
+    dydv[i] = make_float4(dydc[0], dydc[1], dydc[2], dydc[3]);
+  }
+  const double t = block_reduce_totals(s1, s2, it, g.F);
+  if (tid < g.F * 2) {
+    ((tid & 1) ? s_t2 : s_t1)[tid >> 1] = (float)(t / m);
+    (ba.stats_tbwd + (long long)task * ba.stats_tbwd_stride)[tid] = t;
+  }
+  __syncthreads();
+  if (!worker) return;
+  const float4 c2 = ld4s(s_c2, it.q), t1 = ld4s(s_t1, it.q), t2 = ld4s(s_t2, it.q);
+  const float4 rg = make_float4(r.x * ga.x, r.y * ga.y, r.z * ga.z, r.w * ga.w);
+  const float4 rq = make_float4(-r.x * qq.x, -r.y * qq.y, -r.z * qq.z, -r.w * qq.w);
+  float* dzd = ba.dzdot + (long long)task * ba.dzdot_stride;
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    if (!have[i]) continue;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = 2 * wy_[i] + (k >> 1), xx = 2 * wx_[i] + (k & 1);
+      if (yy < g.h && xx < g.w) {
+        const long long idx = ((long long)img_[i] * g.G + (yy + 1) * g.gw + (xx + 1)) * g.F + it.q * 4;
+        const float4 dzv = ld4(dzp + idx);
+        const float4 z = zh[i][k], zdk = zhd[i][k];
+        float4 o;
+        o.x = rq.x * dzv.x + rg.x * ((full[i] && arg[i].x == k ? dydv[i].x : 0.f) - t1.x - zdk.x * c2.x - z.x * t2.x);
+        o.y = rq.y * dzv.y + rg.y * ((full[i] && arg[i].y == k ? dydv[i].y : 0.f) - t1.y - zdk.y * c2.y - z.y * t2.y);
+        o.z = rq.z * dzv.z + rg.z * ((full[i] && arg[i].z == k ? dydv[i].z : 0.f) - t1.z - zdk.z * c2.z - z.z * t2.z);
+        o.w = rq.w * dzv.w + rg.w * ((full[i] && arg[i].w == k ? dydv[i].w : 0.f) - t1.w - zdk.w * c2.w - z.w * t2.w);
+        st4(dzd + idx, o);
+        if (ba.dzdot_hi) st4_split(ba.dzdot_hi + (long long)task * ba.dzdot_stride, ba.dzdot_lo + (long long)task * ba.dzdot_stride, idx, o);
+      }
+    }
+  }
+}
+
+static int g_tail_onchip = 3;          // env MAML_B200_TAIL_ONCHIP: bit 0 primal, bit 1 tangent on-chip kernels (0: stages exchange data through L2)
 void tail_set_onchip(int on) { g_tail_onchip = on; }
 
 // the last block of `n` images is small enough for the fused kernels
@@ -875,7 +1053,7 @@ void launch_tail_fused(const BnActArgs& fa, const HeadArgs& ha, const BnBwdArgs&
     const int F4 = fa.g.F / 4, wpb = 256 / F4;
     const int NW = fa.g.n * ((fa.g.h + 1) / 2) * ((fa.g.w + 1) / 2);
     const size_t words = (size_t)5 * ha.rows_per_cta * ha.N + 2 * (size_t)ha.n * ha.D + (size_t)ha.N * ha.D + ha.N;
-    if (g_tail_onchip && fa.g.pb == 0 && fa.p_hi == nullptr && NW <= 2 * wpb && words * sizeof(float) <= 40 * 1024) {
+    if ((g_tail_onchip & 1) && fa.g.pb == 0 && fa.p_hi == nullptr && NW <= 2 * wpb && words * sizeof(float) <= 40 * 1024) {
       if (NW <= wpb) launch_pdl(tail_onchip_kernel<1>, dim3(1, fa.tasks), dim3(256), words * sizeof(float), st, tagged(fa), ha, ba);
       else launch_pdl(tail_onchip_kernel<2>, dim3(1, fa.tasks), dim3(256), words * sizeof(float), st, tagged(fa), ha, ba);
       CUDA_CHECK_LAUNCH();
@@ -889,6 +1067,17 @@ void launch_tail_fused(const BnActArgs& fa, const HeadArgs& ha, const BnBwdArgs&
 
 void launch_tail_tan_fused(const BnActTanArgs& fa, const HeadArgs& ha, const BnBwdTanArgs& ba, cudaStream_t st) {
   ProfScope prof_scope__(PROF_HEAD, 0.0, st);
+  {
+    const int F4 = fa.g.F / 4, wpb = 256 / F4;
+    const int NW = fa.g.n * ((fa.g.h + 1) / 2) * ((fa.g.w + 1) / 2);
+    const size_t words = (size_t)5 * ha.rows_per_cta * ha.N + 3 * (size_t)ha.n * ha.D + 2 * (size_t)ha.N * ha.D + 2 * ha.N;
+    if ((g_tail_onchip & 2) && fa.g.pb == 0 && fa.pdot_hi == nullptr && ba.dpdot2 == nullptr && NW <= 2 * wpb && words * sizeof(float) <= 40 * 1024) {
+      if (NW <= wpb) launch_pdl(tail_tan_onchip_kernel<1>, dim3(1, fa.tasks), dim3(256), words * sizeof(float), st, tagged(fa), ha, ba);
+      else launch_pdl(tail_tan_onchip_kernel<2>, dim3(1, fa.tasks), dim3(256), words * sizeof(float), st, tagged(fa), ha, ba);
+      CUDA_CHECK_LAUNCH();
+      return;
+    }
+  }
   const size_t smem = (size_t)5 * ha.rows_per_cta * ha.N * sizeof(float);
   launch_pdl(tail_tan_fused_kernel, dim3(1, fa.tasks), dim3(256), smem, st, tagged(fa), ha, ba);
   CUDA_CHECK_LAUNCH();
