@@ -161,9 +161,14 @@ __device__ __forceinline__ void argmax_window(const float* __restrict__ zhp, con
   slope_at.x = slope_of(ybest.x); slope_at.y = slope_of(ybest.y); slope_at.z = slope_of(ybest.z); slope_at.w = slope_of(ybest.w);
 }
 
+// component `comp` (a literal at every call site) of v[k], k = the run-time arg-max position: a select chain -- indexing
+// the register array with k would move it to local memory (STL / LDL in the middle of latency-bound kernels)
 __device__ __forceinline__ float pick(const float4 (&v)[4], int k, int comp) {
-  const float4 t = v[k];
-  return comp == 0 ? t.x : comp == 1 ? t.y : comp == 2 ? t.z : t.w;
+  const float a0 = comp == 0 ? v[0].x : comp == 1 ? v[0].y : comp == 2 ? v[0].z : v[0].w;
+  const float a1 = comp == 0 ? v[1].x : comp == 1 ? v[1].y : comp == 2 ? v[1].z : v[1].w;
+  const float a2 = comp == 0 ? v[2].x : comp == 1 ? v[2].y : comp == 2 ? v[2].z : v[2].w;
+  const float a3 = comp == 0 ? v[3].x : comp == 1 ? v[3].y : comp == 2 ? v[3].z : v[3].w;
+  return k == 0 ? a0 : k == 1 ? a1 : k == 2 ? a2 : a3;
 }
 
 // block-level reduction of per-thread (4 channels x 2 sums) fp64 partials, then one atomic per channel

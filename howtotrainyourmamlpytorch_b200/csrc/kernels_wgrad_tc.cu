@@ -97,7 +97,7 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 // between the two accumulator sets (<= 48 accumulations each) and the epilogue adds them once at the end.  It needs ~90
 // registers per thread instead of 254, which matters because these CTAs share SMs with the latency-critical main chain.
 template <bool LITE>
-__global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ TcMaps maps, const WgTcArgs a) {
+__global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ WgTcArgs a) {
   pdl_trigger();
   trace_mark(27, a.tag);
   extern __shared__ uint8_t smem_raw[];

@@ -657,6 +657,45 @@ def test_fused_and_cluster_paths_match_plain_paths(cuda_device):
             assert rel_err(g1[n], g0[n]) <= 2e-5, (n, rel_err(g1[n], g0[n]))
 
 
+_POLICY_SWITCHES = [
+    {"MAML_B200_PDL": "0"},                                  # no programmatic dependent launch
+    {"MAML_B200_PDL": "1", "MAML_B200_PDL_CLUSTER": "3"},    # ... on every stream, cluster launches included
+    {"MAML_B200_TC_PUSH": "0"},                              # pull-based split-K reduction (two cluster barriers)
+    {"MAML_B200_TAIL_ONCHIP": "0"},                          # last-block kernels that exchange their stages through L2
+    {"MAML_B200_TC_NB": "3", "MAML_B200_WG_NSTAGE": "2", "MAML_B200_TC_NB_FIT": "1"},     # shallow shared-memory rings
+    {"MAML_B200_TC_SPLIT_SIDE": "1", "MAML_B200_TC_NB_SIDE": "2", "MAML_B200_BN_SIDE_CAP": "16"},   # side-stream caps
+]
+
+
+@pytest.mark.parametrize("case", ["tiny_pp", "tiny_bern"])
+@pytest.mark.parametrize("switches", _POLICY_SWITCHES, ids=lambda d: "+".join("%s=%s" % (k[10:], v) for k, v in d.items()))
+def test_launch_policy_switches_do_not_change_results(case, switches, cuda_device):
+    """Round-2 launch policy (programmatic dependent launch, push-based split-K epilogue, on-chip last-block kernels,
+    shared-memory ring depths, side-stream caps): every switch is scheduling only -- the meta-gradient must agree with
+    the default build to summation-order noise."""
+    g = load_golden(case)
+    batch, epoch = g.batch(0), g.iters[0][0]
+    m1 = _model(g, cuda_device)
+    l1, p1, g1 = m1.meta_gradient(batch, epoch)
+    saved = {k: os.environ.get(k) for k in switches}
+    try:
+        os.environ.update(switches)
+        m0 = _model(g, cuda_device)
+        l0, p0, g0 = m0.meta_gradient(batch, epoch)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert abs(float(l0["loss"]) - float(l1["loss"])) <= 1e-6 * abs(float(l0["loss"]))
+    for n in g0:
+        if "conv.bias" in n or "conv-bias" in n:
+            assert float((g0[n] - g1[n]).abs().max()) <= 1e-5
+        else:
+            assert rel_err(g1[n], g0[n]) <= 2e-5, (n, rel_err(g1[n], g0[n]))
+
+
 def test_device_trace(cuda_device):
     """maml_b200_trace: one entry per kernel start of an iteration (also inside the replayed CUDA graph)."""
     g = load_golden("tiny_pp")
