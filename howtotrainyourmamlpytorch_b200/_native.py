@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libmaml_b200.so")
+# MAML_B200_LIB: diagnostic override (A/B of compile-time variants built by scripts/build_variant.sh)
+LIB_PATH = os.environ.get("MAML_B200_LIB") or os.path.join(_PKG, "lib", "libmaml_b200.so")
 
 MAX_STAGES = 4
 MAX_STEPS = 8

@@ -312,10 +312,17 @@ extern int g_launch_prio;
 // Device-side launch trace (debug; maml_b200_trace): CTA (0,0,0) of every kernel appends (globaltimer ns << 8 | kernel
 // id) to a buffer -> the start-time sequence of one captured iteration, the only timeline available without nsys.
 // One pointer copy per translation unit (no relocatable device code), all set to the same buffer; null = off.
+// The trace is armed through a bit of the launch tag, i.e. a kernel ARGUMENT: with tracing off no kernel touches memory for
+// it.  Before, every thread of every kernel began with a load of the buffer pointer (a __device__ variable) and a branch on
+// it -- a dependent global load in front of the first useful instruction: 2.663 -> 2.586 ms per iteration without it (same
+// box, scripts/build_variant.sh).  Moving the pointer to __constant__ memory + reading it from one thread only was SLOWER
+// (2.683 ms).  Enabling the trace drops the handle's cached CUDA graphs so that they are re-captured with armed tags.
+#define MAML_TRACE_ARMED 0x40000000
 static __device__ unsigned long long* t_trace_buf = nullptr;
 #define MAML_TRACE_SETTER(fn) void fn(unsigned long long* p) { cudaMemcpyToSymbol(t_trace_buf, &p, sizeof(p)); }
 #define MAML_TRACE_CAP 4094
 __device__ __forceinline__ void trace_mark(int kid, int tag = 0) {
+  if (!(tag & MAML_TRACE_ARMED)) return;
   unsigned long long* t = t_trace_buf;
   if (t != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
     unsigned long long now;
@@ -358,7 +365,8 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 
 extern long long g_launch_counter;   // bumped by every launcher
 extern long long g_launch_base;      // value of g_launch_counter when the current iteration started to be enqueued
-inline int launch_tag() { return (int)(g_launch_counter - g_launch_base); }
+extern int g_trace_flag;             // MAML_TRACE_ARMED while maml_b200_trace(h, 1) is in effect, else 0
+inline int launch_tag() { return (int)(g_launch_counter - g_launch_base) | g_trace_flag; }
 template <class A> inline A tagged(const A& a) { A t = a; t.tag = launch_tag(); return t; }
 
 #define CUDA_CHECK_LAUNCH() do { g_launch_counter++; } while (0)

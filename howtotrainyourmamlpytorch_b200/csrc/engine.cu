@@ -1429,6 +1429,10 @@ static void trace_set_all(unsigned long long* p) {
 extern "C" int maml_b200_trace(maml_b200_handle* h, int32_t enable) {
   if (!h) return fail("null argument");
   CK(cudaDeviceSynchronize());
+  // kernels trace only when their launch tag carries MAML_TRACE_ARMED: cached graphs hold the old tags -> re-capture
+  g_trace_flag = enable ? MAML_TRACE_ARMED : 0;
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
   if (enable) {
     if (!g_trace_dev) CK(cudaMalloc(&g_trace_dev, (size_t)(MAML_TRACE_CAP + 2) * sizeof(unsigned long long)));
     CK(cudaMemset(g_trace_dev, 0, (size_t)(MAML_TRACE_CAP + 2) * sizeof(unsigned long long)));

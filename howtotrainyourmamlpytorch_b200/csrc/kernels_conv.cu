@@ -14,6 +14,7 @@ long long g_launch_base = 0;
 int g_use_pdl = 0;
 cudaStream_t g_pdl_main_stream = nullptr, g_pdl_wg_stream = nullptr;
 int g_launch_prio = 0;
+int g_trace_flag = 0;
 int g_pdl_cluster = 1;
 
 __device__ __forceinline__ int tap_shift(int tap, int gw) { return (tap / 3 - 1) * gw + (tap % 3 - 1); }

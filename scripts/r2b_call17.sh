@@ -1,0 +1,9 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+O=gpurun_out
+L=$PWD/howtotrainyourmamlpytorch_b200/lib/libmaml_b200_notrace.so
+for r in 1 2; do
+  timeout 300 python scripts/ab_inproc.py --steps 20 --rounds 2 "" > $O/ab17_default_$r.txt 2>&1
+  MAML_B200_LIB=$L timeout 300 python scripts/ab_inproc.py --steps 20 --rounds 2 "" > $O/ab17_notrace_$r.txt 2>&1
+done
+for f in $O/ab17_default_1.txt $O/ab17_notrace_1.txt $O/ab17_default_2.txt $O/ab17_notrace_2.txt; do echo $f; tail -1 $f; done
