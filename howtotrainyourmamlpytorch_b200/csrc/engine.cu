@@ -396,6 +396,7 @@ extern "C" int maml_b200_create(const maml_b200_config* cfg, maml_b200_handle** 
   if (const char* sk = getenv("MAML_B200_TC_STACK")) h->tc_stack = atoi(sk) != 0;
   if (const char* wt = getenv("MAML_B200_WGRAD_TC")) h->wgrad_tc = atoi(wt) != 0;
   if (const char* sp = getenv("MAML_B200_TC_SPLIT")) tc_conv_set_split(atoi(sp));
+  tc_conv_set_zstage(getenv("MAML_B200_TC_ZSTAGE") ? atoi(getenv("MAML_B200_TC_ZSTAGE")) : 1);
   tc_conv_set_push(getenv("MAML_B200_TC_PUSH") ? atoi(getenv("MAML_B200_TC_PUSH")) : 1);
   tc_conv_set_ring_fit(getenv("MAML_B200_TC_NB_FIT") ? atoi(getenv("MAML_B200_TC_NB_FIT")) : 0);
   if (const char* sp = getenv("MAML_B200_TC_NB_SIDE")) h->nb_side = atoi(sp);

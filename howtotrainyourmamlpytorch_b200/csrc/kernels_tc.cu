@@ -362,6 +362,23 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
       if (et < NCOLS) s_bias[et] = a.bias ? a.bias[(long long)task * a.bias_stride + et] : 0.f;
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (a.zstage) {
+      // tangent mode: the statistics below need the primal zh of the rows this CTA finishes.  Copy them into shared
+      // memory NOW (coalesced float4 loads, a region of its own behind the ring / receive buffer) while the MMAs run --
+      // the statistics loop then reads shared memory instead of one dependent global load per row (tangent-mode launches
+      // ran 5.0 / 3.1 / 1.7 us longer than forward-mode launches of the same grid, ncu)
+      constexpr int ZP = NCOLS + 4, Q = NCOLS / 4;
+      float* zbuf = reinterpret_cast<float*>(bring + (size_t)nb * BSTAGE + ((nsplit > 1 && a.push) ? (size_t)128 * (NCOLS + 4) * 4 : 0));
+      const float* zhg = a.zh + (long long)task * a.zh_stride;
+      const int rows_own = 128 / nsplit, row0 = j0 + zrank * rows_own;
+      for (int idx = et; idx < rows_own * Q; idx += 128) {
+        const int rr = idx / Q, c4 = idx - rr * Q;
+        const int gr = row0 + rr;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr < a.rows) v = *reinterpret_cast<const float4*>(zhg + (long long)gr * NCOLS + c4 * 4);
+        *reinterpret_cast<float4*>(zbuf + rr * ZP + c4 * 4) = v;
+      }
+    }
     mbar_wait(&accum_bar, 0);
     if (et == 0) TC_MARK(6);
     tc_fence_after();
@@ -478,6 +495,7 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
     if (want_stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const float* zh = a.zh ? a.zh + (long long)task * a.zh_stride : nullptr;
+      const float* zbuf_s = reinterpret_cast<const float*>(bring + (size_t)nb * BSTAGE + ((nsplit > 1 && a.push) ? (size_t)128 * (NCOLS + 4) * 4 : 0));
       constexpr int PARTS = 128 / NCOLS;           // 2 for 64 and 48, 4 for 32, 8 for 16
       const int col = et % NCOLS, part = et / NCOLS;
       double s1 = 0.0, s2 = 0.0;
@@ -490,7 +508,7 @@ __global__ void __launch_bounds__(224, 1) conv_tc_kernel(const __grid_constant__
             const float v = sbuf[rr * spitch + col];
             if (a.mode == CONV_FWD_STATS) { s1 += (double)v; s2 += (double)v * (double)v; }
             else {
-              const float zv = zh[(long long)(j0 + row_lo + rr) * NCOLS + col];
+              const float zv = a.zstage ? zbuf_s[rr * (NCOLS + 4) + col] : zh[(long long)(j0 + row_lo + rr) * NCOLS + col];
               s1 += (double)v; s2 += (double)zv * (double)v;
             }
           }
@@ -557,6 +575,8 @@ int tc_conv_prepare() {
 // serial pipeline (~18 stages x ~1000 cycles) is then the whole kernel.  Spreading the (phase, tap) stages of a tile
 // over a cluster of S CTAs shortens that to 18 / S stages + one distributed-shared-memory reduction.  S is the largest
 // of {8, 4, 2} whose clusters are all co-resident (asked from the occupancy calculator once per shape).
+static int g_tc_zstage = 1;          // env MAML_B200_TC_ZSTAGE=0: tangent-mode statistics read the primal zh from global memory row by row
+void tc_conv_set_zstage(int on) { g_tc_zstage = on; }
 static int g_tc_push = 1;            // env MAML_B200_TC_PUSH=0: pull-based split-K reduction (two cluster barriers)
 void tc_conv_set_push(int on) { g_tc_push = on; }
 static int g_tc_ring_fit = 1;        // env MAML_B200_TC_NB_FIT=0: keep the full ring for short pipelines
@@ -611,7 +631,18 @@ static void launch_conv_tc_n(const TcMaps& maps, const TcConvArgs& a_in, size_t 
   }
   a.push = (S > 1 && push) ? 1 : 0;
   if (a.push) a.nb = nb_push;
-  smem = tc_conv_smem_for(NCOLS, a.gw, a.nb) + (a.push ? recv_bytes : 0);
+  // tangent mode: room for the primal zh rows this CTA finishes (see the kernel); the ring gives up stages if it must
+  a.zstage = 0;
+  size_t zbytes = 0;
+  if (g_tc_zstage && a.mode == CONV_TAN_STATS && a.zh != nullptr) {
+    zbytes = (size_t)(128 / S) * (NCOLS + 4) * 4;
+    const long long limit = 227LL * 1024 - 4096;
+    int nb2 = a.nb;
+    auto total = [&](int nbx) { return (long long)tc_conv_smem_for(NCOLS, a.gw, nbx) + (long long)(a.push ? recv_bytes : 0) + (long long)zbytes; };
+    while (nb2 > 2 && total(nb2) > limit) --nb2;
+    if (total(nb2) <= limit) { a.nb = nb2; a.zstage = 1; } else zbytes = 0;
+  }
+  smem = tc_conv_smem_for(NCOLS, a.gw, a.nb) + (a.push ? recv_bytes : 0) + zbytes;
   if (S == 1) {
     launch_pdl(conv_tc_kernel<NCOLS>, grid, dim3(224), smem, st, maps, tagged(a));
     return;

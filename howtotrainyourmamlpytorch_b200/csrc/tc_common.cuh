@@ -10,6 +10,7 @@ struct TcConvArgs {
   int plan_tasks;        // split-K is planned for this many tasks (the handle's max_tasks) so that a task's arithmetic
                          // does not depend on how many tasks share the call
   int push;              // split-K only, set by the launcher: 1 = partial rows are pushed into the owner CTA's receive buffer
+  int zstage;            // tangent mode, set by the launcher: 1 = the primal zh rows are staged in shared memory during the MMAs
   int split_cap;         // > 0: largest split-K cluster size for THIS launch (side-stream launches: fewer, longer CTAs)
   int stack;             // 1: N-stacked 3xTF32 (A_hi x [B_hi; B_lo] as one N = 2 * ncols MMA), 0: three MMAs per k-step
   int halo, rpad, nb, bo_mode, timeline;   // halo = gw + 1 rows; rpad = halo-tile rows (multiple of 8); nb = B ring depth
@@ -30,6 +31,7 @@ int tc_conv_rpad(int gw);
 int tc_conv_ring(int ncols, int gw);
 void tc_conv_set_ring_cap(int nb);
 void tc_conv_set_push(int on);         // split-K reduction: 1 push (one cluster barrier), 0 pull (two)
+void tc_conv_set_zstage(int on);       // tangent-mode statistics: 1 = primal zh staged in shared memory, 0 = read from global
 void tc_conv_set_ring_fit(int on);     // 1: ring depth = min(cap, B stages one CTA ever has in flight)     // B ring depth cap in [2, 8]
 size_t tc_conv_smem_bytes(int ncols, int gw);
 int tc_conv_prepare();

@@ -661,6 +661,7 @@ _POLICY_SWITCHES = [
     {"MAML_B200_PDL": "0"},                                  # no programmatic dependent launch
     {"MAML_B200_PDL": "1", "MAML_B200_PDL_CLUSTER": "3"},    # ... on every stream, cluster launches included
     {"MAML_B200_TC_PUSH": "0"},                              # pull-based split-K reduction (two cluster barriers)
+    {"MAML_B200_TC_ZSTAGE": "0"},                            # tangent-mode statistics read the primal zh from global memory
     {"MAML_B200_TAIL_ONCHIP": "0"},                          # last-block kernels that exchange their stages through L2
     {"MAML_B200_TC_NB": "3", "MAML_B200_WG_NSTAGE": "2", "MAML_B200_TC_NB_FIT": "1"},     # shallow shared-memory rings
     {"MAML_B200_TC_SPLIT_SIDE": "1", "MAML_B200_TC_NB_SIDE": "2", "MAML_B200_BN_SIDE_CAP": "16"},   # side-stream caps
