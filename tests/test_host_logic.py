@@ -193,3 +193,16 @@ def test_batch_shape_and_label_validation():
     with pytest.raises(ValueError):
         m._check_batch([xs, xt, ys])
     assert m._check_batch([xs, xt, ys, yt]) == xs.shape[0]
+
+
+def test_library_override_fails_loudly_when_the_variant_is_missing(tmp_path):
+    """MAML_B200_LIB (same-box A/B of compile-time variants, scripts/build_variant.sh) selects another build of the
+    engine; a path that does not exist must raise, never fall back to the default library or to a CPU path."""
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r); os.environ['MAML_B200_LIB'] = %r\n"
+            "from howtotrainyourmamlpytorch_b200 import _native\n"
+            "try:\n    _native.load_library()\nexcept _native.NativeLibraryError as e:\n    print('RAISED', 'missing.so' in str(e))\n"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path / "missing.so")))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "RAISED True" in out.stdout, (out.stdout, out.stderr[-500:])
